@@ -1,0 +1,845 @@
+/* Oracle (TEST INFRASTRUCTURE ONLY) -- plain-C CPU restatement of XNet's per-zone implicit step.
+ *
+ * This file is the checker for the CUDA path and the "port" CPU baseline of bench.py.  Product
+ * code (xnet_b200/) must never include, link or call it.
+ *
+ * Restates, with the same operation order as the Fortran (paths relative to /root/reference):
+ *   full_net                       source/xnet_evolve.F90:19-269
+ *   solve_be / step_be             source/xnet_integrate_be.F90:32-482
+ *   timestep / cross_sect / yderiv source/xnet_integrate.F90:13-984
+ *   update_eos (Ye from y_moment)  source/xnet_integrate.F90:319-362, xnet_eos_starkiller.F90:107-204,
+ *                                  source/xnet_abundances.F90:93-185
+ *   partf / benuc / enudot         source/xnet_data.F90:119-283, 958-1023
+ *   ffn_rate (table branch)        source/xnet_ffn.F90:139-324
+ *   t9rhofind                      source/xnet_conditions.F90:50-102
+ *   jacobian_build/scale/decomp/bksub  source/xnet_jacobian_dense.F90:136-434, 549-732
+ *   DGETRF/DGETRF2/DGETRS/DLASWP/DTRSM/DGEMM/IDAMAX/DSCAL  tools/LAPACK/{dgetrf,dgetrf2,...}.f (Reference-LAPACK 3.8.0)
+ *   safe_exp                       source/xnet_util.F90:17-18,55-72
+ * Screening/EOS/self-heating (iscrn>0, iheat>0) live in ox_eos.c.
+ *
+ * Parity status: the reference cannot be built in this environment (no Fortran compiler) and ships
+ * no numeric golden trajectories (SURVEY F1,F3).  Integer/index work is pinned by the net_desc
+ * goldens (oracle/xnet_loader.py); the LU is pinned against LAPACK (scipy) in tests; the
+ * floating-point trajectory itself is "parity unpinned" beyond code review.
+ */
+#include "xnet_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define NG 24
+#define NT9GRID 13
+#define NENEGRID 11
+#define NGRID 143
+
+/* xnet_constants.F90 */
+static const double avn = 6.022140857e+23, epmev = 1.6021766208e-06;
+
+/* eos/screening hooks implemented in ox_eos.c */
+int ox_eos_interface(const ox_net *net, const ox_ctl *ctl, double t9, double rho, const double *y,
+                     double xext, double aext, double zext, double *ye, double *cv, double *etae,
+                     double *detaedt9);
+int ox_screening(const ox_net *net, const ox_ctl *ctl, double t9, double rho, const double *y,
+                 double xext, double aext, double zext, double etae, double detaedt9,
+                 double *h[4], double *dh[4]);
+void ox_effphase(double t9, double chem, double qec, double *phasei, double *dphaseidt9);
+
+typedef struct {
+  const ox_net *net; const ox_ctl *ctl;
+  int ny, msize;
+  /* trajectory */
+  int nh; const double *th, *t9h, *rhoh; double rho_scale; int has_scale;
+  double tstart, tstop, tdelstart;
+  /* conditions */
+  double t, tt, to, tdel, tdel_next, tdel_old;
+  double t9, t9t, t9o, t9dot, rho, rhot, rhoo, ye, yet, yeo, cv, etae, detaedt9;
+  int nt, ntt, nto, ints, intso, iweak;
+  double xext, aext, zext;
+  double *y, *yo, *yt, *ydot;
+  double *csect[4], *dcsect[4], *h[4], *dh[4], *b[4];
+  double *gg, *dlngdt9;             /* 0..ny */
+  double *rffn, *dlnrffndt9, *qkffn; /* qkffn is 0..nffn */
+  double *phasei, *dphaseidt9;
+  double *dydotdy, *jac, *rhs; int *indx; int info;
+  double *yrhs, *dy, *reldy; double t9rhs, dt9, relt9;
+  int *n_n[4][4];                   /* expanded reactant indices n_cj [nan_c], 1-based */
+  int kmon[5], ktot[5];
+  double *rtau;
+} zone_t;
+
+/* -------------------------------------------------------------------------------------------- */
+static double safe_exp(double x) {
+  /* xnet_util.F90:17-18,69 */
+  const double ln_2 = log(2.0);
+  const double exp_max = 1024.0 * ln_2 * 0.9, exp_min = -1021.0 * ln_2 * 0.9;
+  double v = x > exp_min ? x : exp_min;
+  v = v < exp_max ? v : exp_max;
+  return exp(v);
+}
+
+static double rhoh_at(const zone_t *z, int n) { /* n 1-based */
+  return z->has_scale ? z->rhoh[n - 1] * z->rho_scale : z->rhoh[n - 1];
+}
+
+static void t9rhofind(const zone_t *z, double tf, int *nf, double *t9f, double *rhof) {
+  /* xnet_conditions.F90:72-99 */
+  int ns = z->nh, n;
+  if (ns == 1) { *t9f = z->t9h[0]; *rhof = rhoh_at(z, 1); *nf = 1; return; }
+  for (n = 1; n <= ns; n++) if (tf <= z->th[n - 1]) break;
+  *nf = n;
+  if (n > 1 && n <= ns) {
+    double rdt = 1.0 / (z->th[n - 1] - z->th[n - 2]);
+    double dt = tf - z->th[n - 2];
+    double dt9 = z->t9h[n - 1] - z->t9h[n - 2];
+    double drho = rhoh_at(z, n) - rhoh_at(z, n - 1);
+    *t9f = dt * rdt * dt9 + z->t9h[n - 2];
+    *rhof = dt * rdt * drho + rhoh_at(z, n - 1);
+  } else if (n == 1) {
+    *t9f = z->t9h[0]; *rhof = rhoh_at(z, 1);
+  } else {
+    *t9f = z->t9h[ns - 1]; *rhof = rhoh_at(z, ns);
+  }
+}
+
+static void partf(zone_t *z, double t9) {
+  /* xnet_data.F90:217-267 */
+  const ox_net *net = z->net; int ny = z->ny, i, k, ii;
+  const double *g = net->g, *t9i = net->t9i;
+  for (i = 1; i <= NG; i++) if (t9 <= t9i[i - 1]) break;
+  ii = i;
+  z->gg[0] = 1.0;
+  if (ii == 1) {
+    for (k = 1; k <= ny; k++) z->gg[k] = g[(k - 1) * NG + 0];
+  } else if (ii == NG + 1) {
+    for (k = 1; k <= ny; k++) z->gg[k] = g[(k - 1) * NG + NG - 1];
+  } else {
+    double rdt9 = (t9 - t9i[ii - 2]) / (t9i[ii - 1] - t9i[ii - 2]);
+    for (k = 1; k <= ny; k++)
+      z->gg[k] = safe_exp(rdt9 * log(g[(k - 1) * NG + ii - 1]) + (1.0 - rdt9) * log(g[(k - 1) * NG + ii - 2]));
+  }
+  if (z->ctl->iheat > 0) {
+    z->dlngdt9[0] = 0.0;
+    if (ii == 1) {
+      for (k = 1; k <= ny; k++) z->dlngdt9[k] = log(g[(k - 1) * NG + 1] / g[(k - 1) * NG + 0]) / (t9i[1] - t9i[0]);
+    } else if (ii == NG + 1) {
+      for (k = 1; k <= ny; k++)
+        z->dlngdt9[k] = log(g[(k - 1) * NG + NG - 1] / g[(k - 1) * NG + NG - 2]) / (t9i[NG - 1] - t9i[NG - 2]);
+    } else {
+      for (k = 1; k <= ny; k++)
+        z->dlngdt9[k] = log(g[(k - 1) * NG + ii - 1] / g[(k - 1) * NG + ii - 2]) / (t9i[ii - 1] - t9i[ii - 2]);
+    }
+  }
+}
+
+static void ffn_rate(zone_t *z, double t9, double ene) {
+  /* xnet_ffn.F90:139-301 */
+  static const double t9grid[NT9GRID] = {0.01, 0.1, 0.2, 0.4, 0.7, 1.0, 1.5, 2.0, 3.0, 5.0, 10.0, 30.0, 100.0};
+  static const double enegrid[NENEGRID] = {1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0, 9.0, 10.0, 11.0};
+  const double lqkmin = -90.0, lrfmin = -30.0, rfmin = 1.0e-30;
+  const double ln_2 = log(2.0), ln_10 = log(10.0);
+  const double bok = 8.6173303e-02, m_e = 0.5109989461;
+  const ox_net *net = z->net; int nffn = net->nffn, k, i, lt1;
+  for (k = 1; k <= nffn; k++) {
+    if (net->has_logft[k - 1] > 0) {
+      double cheme = z->etae * bok * t9 + m_e;
+      /* sign(cheme, -has_logft-1.5): magnitude of cheme with negative sign */
+      cheme = -fabs(cheme);
+      ox_effphase(t9, cheme, net->ffn_qval[k - 1], &z->phasei[k - 1], &z->dphaseidt9[k - 1]);
+    }
+  }
+  for (i = 1; i <= NT9GRID; i++) if (t9 <= t9grid[i - 1]) break;
+  lt1 = (i - 1 > 1) ? i - 1 : 1;
+  for (k = 1; k <= nffn; k++) {
+    double enel = log10(ene);
+    int le1 = (int)enel; if (le1 < 1) le1 = 1;
+    double dt9 = t9grid[lt1] - t9grid[lt1 - 1];
+    double rdt9 = (t9 - t9grid[lt1 - 1]) / dt9;
+    double dene = enegrid[le1] - enegrid[le1 - 1];
+    double rdene = (enel - enegrid[le1 - 1]) / dene;
+    int i1 = NT9GRID * (le1 - 1) + lt1, i2 = i1 + 1, i3 = NT9GRID * le1 + lt1, i4 = i3 + 1;
+    const double *enu = net->ffnenu + (size_t)(k - 1) * NGRID;
+    const double *sum = net->ffnsum + (size_t)(k - 1) * NGRID;
+    double qdr1 = enu[i2 - 1] - enu[i1 - 1], qdr2 = enu[i4 - 1] - enu[i3 - 1];
+    double qr1 = enu[i1 - 1] + rdt9 * qdr1, qr2 = enu[i3 - 1] + rdt9 * qdr2;
+    double qk = qr1 + rdene * (qr2 - qr1);
+    z->qkffn[k] = (qk > lqkmin) ? pow(10.0, qk) : 0.0;
+    if (net->has_logft[k - 1] > 0) {
+      const double *ec = net->ffn_ec + (size_t)(k - 1) * NGRID;
+      const double *be = net->ffn_beta + (size_t)(k - 1) * NGRID;
+      double dr1_ec = ec[i2 - 1] - ec[i1 - 1], dr2_ec = ec[i4 - 1] - ec[i3 - 1];
+      double r1 = ec[i1 - 1] + rdt9 * dr1_ec, r2 = ec[i3 - 1] + rdt9 * dr2_ec;
+      double rf_ec = r1 + rdene * (r2 - r1), rf_beta, dr1, dr2, rf;
+      if (z->phasei[k - 1] > rfmin && rf_ec > lrfmin) rf_ec = ln_2 * z->phasei[k - 1] / pow(10.0, rf_ec);
+      else rf_ec = 0.0;
+      dr1 = be[i2 - 1] - be[i1 - 1]; dr2 = be[i4 - 1] - be[i3 - 1];
+      r1 = be[i1 - 1] + rdt9 * dr1; r2 = be[i3 - 1] + rdt9 * dr2;
+      rf_beta = r1 + rdene * (r2 - r1);
+      rf_beta = (rf_beta > lrfmin) ? pow(10.0, rf_beta) : 0.0;
+      rf = rf_beta + rf_ec;
+      if (rf_beta < rfmin && rf_ec < rfmin) { z->rffn[k - 1] = 0.0; z->dlnrffndt9[k - 1] = 0.0; }
+      else {
+        z->rffn[k - 1] = rf;
+        if (rf_ec < rfmin) z->dlnrffndt9[k - 1] = ln_10 * (rdene * dr2 + (1.0 - rdene) * dr1) / dt9;
+        else {
+          double drbeta_dt = rf_beta * ln_10 * (rdene * dr2 + (1.0 - rdene) * dr1) / dt9;
+          double drec_dt = rf_ec * (-ln_10 * (rdene * dr2_ec + (1.0 - rdene) * dr1_ec) / dt9
+                                    + z->dphaseidt9[k - 1] / z->phasei[k - 1]);
+          z->dlnrffndt9[k - 1] = (drbeta_dt + drec_dt) / rf;
+        }
+      }
+    } else {
+      double dr1 = sum[i2 - 1] - sum[i1 - 1], dr2 = sum[i4 - 1] - sum[i3 - 1];
+      double r1 = sum[i1 - 1] + rdt9 * dr1, r2 = sum[i3 - 1] + rdt9 * dr2;
+      double rf = r1 + rdene * (r2 - r1);
+      if (rf < lrfmin) { z->rffn[k - 1] = 0.0; z->dlnrffndt9[k - 1] = 0.0; }
+      else { z->rffn[k - 1] = pow(10.0, rf); z->dlnrffndt9[k - 1] = ln_10 * (rdene * dr2 + (1.0 - rdene) * dr1) / dt9; }
+    }
+  }
+}
+
+static int cross_sect(zone_t *z) {
+  /* xnet_integrate.F90:569-927 for one zone (mask true) */
+  const ox_net *net = z->net; const ox_ctl *ctl = z->ctl;
+  int iheat = ctl->iheat, c, k, j, rc_;
+  double t09[7], dt09[7], ene, ascrn, t9t = z->t9t, rhot = z->rhot;
+  /* update_eos: Ye always from y_moment; cv/eta only if iscrn>0 or iheat>0 */
+  rc_ = ox_eos_interface(net, ctl, t9t, rhot, z->yt, z->xext, z->aext, z->zext,
+                         &z->yet, &z->cv, &z->etae, &z->detaedt9);
+  if (rc_) return rc_;
+  if (ctl->iscrn >= 1) {
+    ascrn = 1.0;
+    rc_ = ox_screening(net, ctl, t9t, rhot, z->yt, z->xext, z->aext, z->zext, z->etae, z->detaedt9, z->h, z->dh);
+    if (rc_) return rc_;
+  } else ascrn = 0.0;
+  /* update_iweak :300-311 */
+  if (t9t < 0.01 && ctl->iweak0 != 0) z->iweak = -abs(ctl->iweak0); else z->iweak = ctl->iweak0;
+  partf(z, t9t);
+  ene = z->yet * rhot;
+  t09[0] = 1.0; t09[1] = 1.0 / t9t; t09[2] = pow(t9t, -1.0 / 3.0); t09[3] = pow(t9t, 1.0 / 3.0);
+  t09[4] = t9t; t09[5] = pow(t9t, 5.0 / 3.0); t09[6] = log(t9t);
+  dt09[0] = 0.0; dt09[1] = -(1.0 / (t9t * t9t)); dt09[2] = -pow(t9t, -4.0 / 3.0) / 3.0;
+  dt09[3] = pow(t9t, -2.0 / 3.0) / 3.0; dt09[4] = 1.0; dt09[5] = pow(t9t, 2.0 / 3.0) * 5.0 / 3.0;
+  dt09[6] = 1.0 / t9t;
+  if (net->nffn > 0) ffn_rate(z, t9t, ene);
+  /* nnu_rate: ineutrino=0 -> rnnu = 0 (xnet_nnu.F90:222-233) */
+  for (c = 0; c < 4; c++) {
+    int nr = net->nr[c];
+    for (k = 0; k < nr; k++) {
+      double lam = 0.0, dlam = 0.0;
+      for (j = 0; j < 7; j++) { lam = lam + net->rc[c][k * 7 + j] * t09[j]; dlam = dlam + net->rc[c][k * 7 + j] * dt09[j]; }
+      z->h[c][k] = ascrn * z->h[c][k] + lam;
+      z->dh[c][k] = ascrn * z->dh[c][k] + dlam;
+    }
+  }
+  for (c = 0; c < 4; c++) {
+    int nr = net->nr[c], nreact = c + 1;
+    double rhofac = 1.0;
+    if (c == 1) rhofac = rhot; else if (c == 2) rhofac = rhot * rhot; else if (c == 3) rhofac = rhot * rhot * rhot;
+    for (k = 0; k < nr; k++) {
+      int iwk = net->iwk[c][k];
+      const int *ni = net->ni[c] + k * 6;
+      if ((z->iweak < 0 && iwk == 0) || (z->iweak == 0 && iwk != 0)) {
+        z->csect[c][k] = 0.0; z->dcsect[c][k] = 0.0; continue;
+      }
+      double rpf = 1.0, dlnrpf = 0.0;
+      if (net->irev[c][k] == 1) {
+        int nslot = (c == 0) ? 5 : 6;
+        double p, s;
+        if (c == 0) { p = z->gg[ni[0]]; s = z->dlngdt9[ni[0]]; }
+        else { p = 1.0; s = 0.0; for (j = 0; j < nreact; j++) { p = p * z->gg[ni[j]]; s = s + z->dlngdt9[ni[j]]; } }
+        for (j = nreact; j < nslot; j++) { rpf = rpf * z->gg[ni[j]]; dlnrpf = dlnrpf + z->dlngdt9[ni[j]]; }
+        rpf = rpf / p; dlnrpf = dlnrpf - s;
+      }
+      double cs;
+      if (c == 0) {
+        if (iwk == 1) cs = ene * rpf * safe_exp(z->h[0][k]);
+        else if (iwk == 2 || iwk == 3) cs = z->rffn[net->iffn[k] - 1];
+        else if (iwk == 7 || iwk == 8) cs = rpf * 0.0;
+        else cs = rpf * safe_exp(z->h[0][k]);
+      } else {
+        if (iwk == 1) cs = rhofac * ene * rpf * safe_exp(z->h[c][k]);
+        else cs = rhofac * rpf * safe_exp(z->h[c][k]);
+        if (c == 2 && cs < 1.0e-20) cs = 0.0;
+      }
+      z->csect[c][k] = cs;
+      if (iheat > 0) {
+        if (c == 0 && (iwk == 2 || iwk == 3)) z->dcsect[c][k] = cs * z->dlnrffndt9[net->iffn[k] - 1];
+        else if (c == 0 && (iwk == 7 || iwk == 8)) z->dcsect[c][k] = cs * dlnrpf;
+        else z->dcsect[c][k] = cs * (z->dh[c][k] + dlnrpf);
+      }
+    }
+  }
+  z->ktot[4] += 1;
+  return 0;
+}
+
+static void yderiv(zone_t *z) {
+  /* xnet_integrate.F90:409-495 */
+  const ox_net *net = z->net; int ny = z->ny, i0, i1, c;
+  const double *yt = z->yt;
+  for (i0 = 0; i0 < ny; i0++) {
+    double s[4];
+    for (c = 0; c < 4; c++) {
+      int la = net->la[c * ny + i0], le = net->le[c * ny + i0];
+      double sc = 0.0;
+      for (i1 = la; i1 <= le; i1++) {
+        double bb = net->a[c][i1 - 1] * z->csect[c][net->mu[c][i1 - 1] - 1];
+        double t;
+        z->b[c][i1 - 1] = bb;
+        t = bb * yt[z->n_n[c][0][i1 - 1] - 1];
+        if (c >= 1) t = t * yt[z->n_n[c][1][i1 - 1] - 1];
+        if (c >= 2) t = t * yt[z->n_n[c][2][i1 - 1] - 1];
+        if (c >= 3) t = t * yt[z->n_n[c][3][i1 - 1] - 1];
+        sc = sc + t;
+      }
+      s[c] = sc;
+    }
+    z->ydot[i0] = s[0] + s[1] + s[2] + s[3];
+  }
+  if (z->ctl->iheat > 0) {
+    double sdot = 0.0;
+    for (i0 = 0; i0 < ny; i0++) sdot = sdot - net->mex[i0] * z->ydot[i0] / z->cv;
+    z->t9dot = sdot;
+  }
+  z->ktot[3] += 1;
+}
+
+static void jacobian_build(zone_t *z, double diag, double mult) {
+  /* xnet_jacobian_dense.F90:303-399 then jacobian_scale :183-200 */
+  const ox_net *net = z->net; int ny = z->ny, m = z->msize, i0, j1, c;
+  const double *yt = z->yt; double *d = z->dydotdy;
+  int iheat = z->ctl->iheat;
+  /* d[(i0)*m + j1] == dydotdy(j1+1,i0+1) */
+  for (i0 = 0; i0 < ny; i0++) {
+    double *row = d + (size_t)i0 * m;
+    for (j1 = 0; j1 < m; j1++) row[j1] = 0.0;
+    {
+      int la = net->la[0 * ny + i0], le = net->le[0 * ny + i0];
+      for (j1 = la; j1 <= le; j1++) row[z->n_n[0][0][j1 - 1] - 1] += z->b[0][j1 - 1];
+    }
+    {
+      int la = net->la[1 * ny + i0], le = net->le[1 * ny + i0];
+      for (j1 = la; j1 <= le; j1++) {
+        int n1 = z->n_n[1][0][j1 - 1] - 1, n2 = z->n_n[1][1][j1 - 1] - 1; double bb = z->b[1][j1 - 1];
+        row[n1] += bb * yt[n2];
+        row[n2] += bb * yt[n1];
+      }
+    }
+    {
+      int la = net->la[2 * ny + i0], le = net->le[2 * ny + i0];
+      for (j1 = la; j1 <= le; j1++) {
+        int n1 = z->n_n[2][0][j1 - 1] - 1, n2 = z->n_n[2][1][j1 - 1] - 1, n3 = z->n_n[2][2][j1 - 1] - 1;
+        double bb = z->b[2][j1 - 1];
+        row[n1] += bb * yt[n2] * yt[n3];
+        row[n2] += bb * yt[n3] * yt[n1];
+        row[n3] += bb * yt[n1] * yt[n2];
+      }
+    }
+    {
+      int la = net->la[3 * ny + i0], le = net->le[3 * ny + i0];
+      for (j1 = la; j1 <= le; j1++) {
+        int n1 = z->n_n[3][0][j1 - 1] - 1, n2 = z->n_n[3][1][j1 - 1] - 1, n3 = z->n_n[3][2][j1 - 1] - 1,
+            n4 = z->n_n[3][3][j1 - 1] - 1;
+        double bb = z->b[3][j1 - 1];
+        row[n1] += bb * yt[n2] * yt[n3] * yt[n4];
+        row[n2] += bb * yt[n3] * yt[n4] * yt[n1];
+        row[n3] += bb * yt[n4] * yt[n1] * yt[n2];
+        row[n4] += bb * yt[n1] * yt[n2] * yt[n3];
+      }
+    }
+    if (iheat > 0) {
+      double s[4];
+      for (c = 0; c < 4; c++) {
+        int la = net->la[c * ny + i0], le = net->le[c * ny + i0]; double sc = 0.0;
+        for (j1 = la; j1 <= le; j1++) {
+          double t = net->a[c][j1 - 1] * z->dcsect[c][net->mu[c][j1 - 1] - 1] * yt[z->n_n[c][0][j1 - 1] - 1];
+          if (c >= 1) t = t * yt[z->n_n[c][1][j1 - 1] - 1];
+          if (c >= 2) t = t * yt[z->n_n[c][2][j1 - 1] - 1];
+          if (c >= 3) t = t * yt[z->n_n[c][3][j1 - 1] - 1];
+          sc = sc + t;
+        }
+        s[c] = sc;
+      }
+      row[ny] = s[0] + s[1] + s[2] + s[3];
+    }
+  }
+  if (iheat > 0) {
+    for (j1 = 0; j1 < m; j1++) {
+      double sdot = 0.0;
+      for (i0 = 0; i0 < ny; i0++) sdot = sdot - net->mex[i0] * d[(size_t)i0 * m + j1] / z->cv;
+      d[(size_t)ny * m + j1] = sdot;
+    }
+  }
+  z->ktot[2] += 1;
+  /* jacobian_scale: jac(i0,j1) = mult*dydotdy(j1,i0) (+diag) ; jac col-major */
+  for (j1 = 0; j1 < m; j1++)
+    for (i0 = 0; i0 < m; i0++) {
+      double v = mult * d[(size_t)i0 * m + j1];
+      if (i0 == j1) v = v + diag;
+      z->jac[(size_t)j1 * m + i0] = v;
+    }
+}
+
+/* ------------------------------- LAPACK 3.8.0 restatement ----------------------------------- */
+#define A_(i, j) a[(size_t)((j)-1) * lda + ((i)-1)]
+static void dlaswp(int n, double *a, int lda, int k1, int k2, const int *ipiv) {
+  /* incx = 1; the 32-column blocking of dlaswp.f does not change results */
+  int i, k;
+  for (i = k1; i <= k2; i++) {
+    int ip = ipiv[i - 1];
+    if (ip != i)
+      for (k = 1; k <= n; k++) { double t = A_(i, k); A_(i, k) = A_(ip, k); A_(ip, k) = t; }
+  }
+}
+static void dtrsm_llnu(int m, int n, const double *a, int lda, double *b, int ldb) {
+  int i, j, k;
+  for (j = 1; j <= n; j++)
+    for (k = 1; k <= m; k++) {
+      double bkj = b[(size_t)(j - 1) * ldb + k - 1];
+      if (bkj != 0.0)
+        for (i = k + 1; i <= m; i++) b[(size_t)(j - 1) * ldb + i - 1] -= bkj * A_(i, k);
+    }
+}
+static void dtrsm_lunn(int m, int n, const double *a, int lda, double *b, int ldb) {
+  int i, j, k;
+  for (j = 1; j <= n; j++)
+    for (k = m; k >= 1; k--) {
+      double *bkj = &b[(size_t)(j - 1) * ldb + k - 1];
+      if (*bkj != 0.0) {
+        *bkj = *bkj / A_(k, k);
+        for (i = 1; i <= k - 1; i++) b[(size_t)(j - 1) * ldb + i - 1] -= *bkj * A_(i, k);
+      }
+    }
+}
+static void dgemm_nn_m1(int m, int n, int k, const double *a, int lda, const double *b, int ldb, double *c, int ldc) {
+  /* C := C - A*B  (alpha=-1, beta=1), reference loop order j,l,i */
+  int i, j, l;
+  for (j = 1; j <= n; j++)
+    for (l = 1; l <= k; l++) {
+      double temp = -1.0 * b[(size_t)(j - 1) * ldb + l - 1];
+      for (i = 1; i <= m; i++) c[(size_t)(j - 1) * ldc + i - 1] += temp * A_(i, l);
+    }
+}
+static void dgetrf2(int m, int n, double *a, int lda, int *ipiv, int *info) {
+  *info = 0;
+  if (m == 0 || n == 0) return;
+  if (m == 1) {
+    ipiv[0] = 1;
+    if (A_(1, 1) == 0.0) *info = 1;
+  } else if (n == 1) {
+    const double sfmin = DBL_MIN; /* dlamch('S') */
+    int i, imax = 1; double dmax = fabs(A_(1, 1));
+    for (i = 2; i <= m; i++) if (fabs(A_(i, 1)) > dmax) { imax = i; dmax = fabs(A_(i, 1)); }
+    ipiv[0] = imax;
+    if (A_(imax, 1) != 0.0) {
+      if (imax != 1) { double t = A_(1, 1); A_(1, 1) = A_(imax, 1); A_(imax, 1) = t; }
+      if (fabs(A_(1, 1)) >= sfmin) {
+        double r = 1.0 / A_(1, 1);
+        for (i = 2; i <= m; i++) A_(i, 1) = r * A_(i, 1);
+      } else {
+        for (i = 1; i <= m - 1; i++) A_(1 + i, 1) = A_(1 + i, 1) / A_(1, 1);
+      }
+    } else *info = 1;
+  } else {
+    int mn = m < n ? m : n, n1 = mn / 2, n2 = n - n1, iinfo, i;
+    dgetrf2(m, n1, a, lda, ipiv, &iinfo);
+    if (*info == 0 && iinfo > 0) *info = iinfo;
+    dlaswp(n2, &A_(1, n1 + 1), lda, 1, n1, ipiv);
+    dtrsm_llnu(n1, n2, a, lda, &A_(1, n1 + 1), lda);
+    dgemm_nn_m1(m - n1, n2, n1, &A_(n1 + 1, 1), lda, &A_(1, n1 + 1), lda, &A_(n1 + 1, n1 + 1), lda);
+    dgetrf2(m - n1, n2, &A_(n1 + 1, n1 + 1), lda, ipiv + n1, &iinfo);
+    if (*info == 0 && iinfo > 0) *info = iinfo + n1;
+    for (i = n1 + 1; i <= mn; i++) ipiv[i - 1] += n1;
+    dlaswp(n1, a, lda, n1 + 1, mn, ipiv);
+  }
+}
+void ox_dgetrf(int m, int n, double *a, int lda, int *ipiv, int *info) {
+  /* dgetrf.f with NB = 64 (ilaenv.f:272-279) */
+  const int nb = 64; int mn = m < n ? m : n, j, i, iinfo;
+  *info = 0;
+  if (m == 0 || n == 0) return;
+  if (nb <= 1 || nb >= mn) { dgetrf2(m, n, a, lda, ipiv, info); return; }
+  for (j = 1; j <= mn; j += nb) {
+    int jb = (mn - j + 1 < nb) ? mn - j + 1 : nb;
+    dgetrf2(m - j + 1, jb, &A_(j, j), lda, ipiv + j - 1, &iinfo);
+    if (*info == 0 && iinfo > 0) *info = iinfo + j - 1;
+    for (i = j; i <= ((m < j + jb - 1) ? m : j + jb - 1); i++) ipiv[i - 1] = j - 1 + ipiv[i - 1];
+    dlaswp(j - 1, a, lda, j, j + jb - 1, ipiv);
+    if (j + jb <= n) {
+      dlaswp(n - j - jb + 1, &A_(1, j + jb), lda, j, j + jb - 1, ipiv);
+      dtrsm_llnu(jb, n - j - jb + 1, &A_(j, j), lda, &A_(j, j + jb), lda);
+      if (j + jb <= m)
+        dgemm_nn_m1(m - j - jb + 1, n - j - jb + 1, jb, &A_(j + jb, j), lda, &A_(j, j + jb), lda,
+                    &A_(j + jb, j + jb), lda);
+    }
+  }
+}
+void ox_dgetrs(int n, int nrhs, const double *a, int lda, const int *ipiv, double *b, int ldb) {
+  /* dgetrs.f, TRANS='N' */
+  dlaswp(nrhs, b, ldb, 1, n, ipiv);
+  dtrsm_llnu(n, nrhs, a, lda, b, ldb);
+  dtrsm_lunn(n, nrhs, a, lda, b, ldb);
+}
+#undef A_
+
+/* -------------------------------------------------------------------------------------------- */
+static int step_be(zone_t *z, int *inr) {
+  /* xnet_integrate_be.F90:233-482 for one zone; *inr: 0 active on input; >0 its on convergence */
+  const ox_net *net = z->net; const ox_ctl *ctl = z->ctl;
+  int ny = z->ny, k, kit, iterate, iheat = ctl->iheat, rc_;
+  double xtot_init, rdt, mult, s1;
+  if (*inr != 0) return 0;
+  iterate = 1;
+  s1 = 0.0;
+  for (k = 0; k < ny; k++) s1 = s1 + net->aa[k] * z->y[k];
+  xtot_init = s1 + z->xext - 1.0;
+  rdt = 1.0 / z->tdel; mult = -1.0;
+  for (kit = 1; kit <= ctl->kitmx; kit++) {
+    int rebuild = iterate && ((kit - 1) % ctl->ijac == 0);
+    int eval_rates;
+    double s2, s3, testc, testc2, xtot, testm, testn, toln;
+    if (iheat > 0) eval_rates = iterate; else if (kit == 1) eval_rates = iterate && z->nh > 1; else eval_rates = 0;
+    if (eval_rates) { rc_ = cross_sect(z); if (rc_) return rc_; }
+    yderiv(z);
+    if (rebuild) {
+      jacobian_build(z, rdt, mult);
+      ox_dgetrf(z->msize, z->msize, z->jac, z->msize, z->indx, &z->info);
+    }
+    if (kit > 1) {
+      for (k = 0; k < ny; k++) z->yrhs[k] = (z->y[k] - z->yt[k]) * rdt + z->ydot[k];
+      if (iheat > 0) z->t9rhs = (z->t9 - z->t9t) * rdt + z->t9dot;
+    } else {
+      for (k = 0; k < ny; k++) z->yrhs[k] = z->ydot[k];
+      if (iheat > 0) z->t9rhs = z->t9dot;
+    }
+    for (k = 0; k < ny; k++) z->rhs[k] = z->yrhs[k];
+    if (iheat > 0) z->rhs[ny] = z->t9rhs;
+    ox_dgetrs(z->msize, 1, z->jac, z->msize, z->indx, z->rhs, z->msize);
+    for (k = 0; k < ny; k++) z->dy[k] = z->rhs[k];
+    if (iheat > 0) z->dt9 = z->rhs[ny];
+    s1 = 0.0; s2 = 0.0; s3 = 0.0;
+    for (k = 0; k < ny; k++) {
+      double ytmp = z->yt[k] + z->dy[k];
+      if (ytmp < ctl->ymin) { z->dy[k] = -z->yt[k]; z->yt[k] = 0.0; z->reldy[k] = 0.0; }
+      else { z->yt[k] = ytmp; z->reldy[k] = fabs(z->dy[k] / z->yt[k]); }
+      s1 = s1 + z->reldy[k];
+      s2 = s2 + net->aa[k] * z->dy[k];
+      s3 = s3 + net->aa[k] * z->yt[k];
+    }
+    testc = s1; testc2 = s2; (void)testc2;
+    xtot = s3 + z->xext - 1.0;
+    testm = xtot - xtot_init;
+    if (iheat > 0) {
+      z->t9t = z->t9t + z->dt9;
+      if (fabs(z->t9t) > DBL_MIN) z->relt9 = fabs(z->dt9 / z->t9t); else z->relt9 = 0.0;
+    } else z->relt9 = 0.0;
+    if (ctl->iconvc != 0) { testn = testc; toln = ctl->tolc; } else { testn = testm; toln = ctl->tolm; }
+    if (fabs(testn) <= toln && z->relt9 < ctl->tolt9) { *inr = kit; iterate = 0; } else iterate = 1;
+    if (!iterate) break;
+  }
+  return 0;
+}
+
+static int timestep(zone_t *z, int kstep);
+
+static int solve_be(zone_t *z, int kstep, int *its) {
+  /* xnet_integrate_be.F90:32-231 for one zone */
+  const ox_ctl *ctl = z->ctl; const int ktsmx = 10;
+  int ny = z->ny, inr, mykts = 0, kts, k, lzstep, rc_;
+  if (*its != 0) return 0;
+  inr = 0; lzstep = 1;
+  for (kts = 1; kts <= ktsmx; kts++) {
+    rc_ = step_be(z, &inr); if (rc_) return rc_;
+    if (inr == 0) {
+      z->tdel = z->tdel / ctl->tdel_maxmult;
+      z->tt = z->t + z->tdel;
+      z->yet = z->ye;
+      mykts = kts + 1;
+      for (k = 0; k < ny; k++) z->yt[k] = z->y[k];
+      z->kmon[1] = ctl->kitmx + 1; z->ktot[1] += ctl->kitmx + 1;
+    } else if (inr > 0) {
+      mykts = kts;
+      z->kmon[1] = inr; z->ktot[1] += inr;
+    }
+    lzstep = (inr == 0);
+    if (lzstep) {
+      t9rhofind(z, z->tt, &z->ntt, &z->t9t, &z->rhot);
+      if (ctl->iheat > 0) z->t9t = z->t9;
+      if (kts == ktsmx - 1) {
+        z->tdel = 0.0; /* tdelstart = 0 too */
+        z->tdelstart = 0.0;
+        rc_ = timestep(z, kstep); if (rc_) return rc_;
+      }
+    }
+    if (!lzstep) break;
+  }
+  z->kmon[0] = mykts; z->ktot[0] += mykts;
+  if (inr > 0) {
+    z->tdel_next = z->tdel * ctl->tdel_maxmult;
+    z->nto = z->nt; z->nt = z->ntt;
+    z->to = z->t; z->t = z->tt;
+    z->t9o = z->t9; z->t9 = z->t9t;
+    z->rhoo = z->rho; z->rho = z->rhot;
+    z->yeo = z->ye; z->ye = z->yet;
+    for (k = 0; k < ny; k++) { z->yo[k] = z->y[k]; z->y[k] = z->yt[k]; }
+  } else *its = 1;
+  return 0;
+}
+
+static int timestep(zone_t *z, int kstep) {
+  /* xnet_integrate.F90:13-268 for one zone (mask true) */
+  const ox_ctl *ctl = z->ctl; const double changeth = 0.1;
+  int ny = z->ny, k, mask_init, rc_;
+  double changest, changey, changet9, tdel_init, tdel_stop, tdel_dy = 0.0, tdel_dt9 = 0.0, rtau_t9;
+  (void)kstep;
+  z->tdel_old = z->tdel;
+  mask_init = (fabs(z->tdel_old) < DBL_MIN);
+  if (mask_init) { rc_ = cross_sect(z); if (rc_) return rc_; yderiv(z); }
+  tdel_stop = z->tstop - z->t;
+  if (mask_init) {
+    z->intso = 0;
+    changest = (z->tdelstart < 0.0) ? 0.5 : 0.01;
+    changey = changest * (0.1 < ctl->changemx ? 0.1 : ctl->changemx);
+    changet9 = changest * (0.01 < ctl->changemxt ? 0.01 : ctl->changemxt);
+    tdel_init = changest * fabs(z->tdelstart); if (tdel_stop < tdel_init) tdel_init = tdel_stop;
+    if (z->nh > 2) z->tdel_next = 1.0e-4 * tdel_stop; else z->tdel_next = tdel_stop;
+  } else { changey = ctl->changemx; changet9 = ctl->changemxt; tdel_init = 0.0; }
+  if (z->tdel_old >= 0.0) {
+    int imax = 0; double vmax;
+    for (k = 0; k < ny; k++) {
+      if (z->y[k] > ctl->ymin) {
+        double yfloor = z->y[k] > ctl->yacc ? z->y[k] : ctl->yacc;
+        if (mask_init) z->rtau[k] = fabs(z->ydot[k] / yfloor);
+        else z->rtau[k] = fabs((z->y[k] - z->yo[k]) / yfloor) / z->tdel_old;
+      } else z->rtau[k] = 0.0;
+    }
+    vmax = z->rtau[0];
+    for (k = 1; k < ny; k++) if (z->rtau[k] > vmax) { vmax = z->rtau[k]; imax = k; }
+    z->ints = imax + 1;
+    if (fabs(z->rtau[imax]) > 0.0) tdel_dy = changey / z->rtau[imax]; else tdel_dy = z->tdel_next;
+    if (ctl->iheat > 0) {
+      if (mask_init) rtau_t9 = fabs(z->t9dot / z->t9);
+      else rtau_t9 = fabs((z->t9 - z->t9o) / z->t9) / z->tdel_old;
+    } else rtau_t9 = 0.0;
+    if (rtau_t9 > 0.0) tdel_dt9 = changet9 / rtau_t9; else tdel_dt9 = z->tdel_next;
+    {
+      double m = tdel_stop;
+      if (z->tdel_next < m) m = z->tdel_next;
+      if (tdel_dy < m) m = tdel_dy;
+      if (tdel_dt9 < m) m = tdel_dt9;
+      z->tdel = m;
+    }
+    if (tdel_init > z->tdel) z->tdel = tdel_init;
+  } else z->tdel = -z->tdel_old;
+  { double v = z->t + z->tdel; z->tt = v < z->tstop ? v : z->tstop; }
+  if (ctl->iheat == 0 && z->nh > 1) {
+    int j, i; double dtherm;
+    t9rhofind(z, z->tt, &z->ntt, &z->t9t, &z->rhot);
+    if (z->ntt - 1 > z->nt) {
+      for (j = z->nt; j <= z->ntt - 1; j++) {
+        double t9j = z->t9h[j - 1], rhoj = rhoh_at(z, j);
+        if ((t9j > z->t9 && t9j > z->t9t) || (t9j < z->t9 && t9j < z->t9t) ||
+            (rhoj > z->rho && rhoj > z->rhot) || (rhoj < z->rho && rhoj < z->rhot)) {
+          z->tdel = z->th[j - 1] - z->t; break;
+        }
+      }
+      { double v = z->t + z->tdel; z->tt = v < z->tstop ? v : z->tstop; }
+    }
+    dtherm = 0.0;
+    for (i = 1; i <= 10; i++) {
+      t9rhofind(z, z->tt, &z->ntt, &z->t9t, &z->rhot);
+      if (z->t9 > 0.0) dtherm = 10.0 * fabs(z->t9t - z->t9) / z->t9 + fabs(z->rhot - z->rho) / z->rho;
+      if (dtherm < changeth) break;
+      z->tdel = 0.5 * z->tdel;
+      { double v = z->t + z->tdel; z->tt = v < z->tstop ? v : z->tstop; }
+    }
+  }
+  return 0;
+}
+
+static void benuc(const zone_t *z, const double *y, double *enb, double *enm) {
+  /* xnet_data.F90:157-175 */
+  const ox_net *net = z->net; double ztot = 0.0, btot = 0.0; int k;
+  for (k = 0; k < z->ny; k++) { ztot = ztot + y[k] * net->zz[k]; btot = btot + y[k] * net->be[k]; }
+  *enb = btot;
+  *enm = net->mex_p * ztot + net->mex_n * (1.0 - ztot) - btot;
+  *enb = epmev * avn * *enb;
+  *enm = epmev * avn * *enm;
+}
+
+static void enudot(const zone_t *z, const double *y, double *sqnu) {
+  /* xnet_data.F90:990-1020 */
+  const ox_net *net = z->net; int k;
+  if (net->nffn > 0) {
+    double s = 0.0;
+    for (k = 0; k < net->nr[0]; k++) s = s + y[net->ni[0][k * 6] - 1] * z->qkffn[net->iffn[k]];
+    *sqnu = epmev * avn * s;
+  }
+}
+
+static double *dalloc(size_t n) { double *p = (double *)calloc(n ? n : 1, sizeof(double)); return p; }
+
+static zone_t *zone_new(const ox_net *net, const ox_ctl *ctl) {
+  zone_t *z = (zone_t *)calloc(1, sizeof(zone_t)); int c, r, j, ny = net->ny;
+  z->net = net; z->ctl = ctl; z->ny = ny; z->msize = ny + (ctl->iheat > 0 ? 1 : 0);
+  z->y = dalloc(ny); z->yo = dalloc(ny); z->yt = dalloc(ny); z->ydot = dalloc(ny);
+  z->yrhs = dalloc(ny); z->dy = dalloc(ny); z->reldy = dalloc(ny); z->rtau = dalloc(ny);
+  for (c = 0; c < 4; c++) {
+    z->csect[c] = dalloc(net->nr[c]); z->dcsect[c] = dalloc(net->nr[c]);
+    z->h[c] = dalloc(net->nr[c]); z->dh[c] = dalloc(net->nr[c]); z->b[c] = dalloc(net->nan[c]);
+    for (r = 0; r <= c; r++) {
+      z->n_n[c][r] = (int *)calloc(net->nan[c] ? net->nan[c] : 1, sizeof(int));
+      for (j = 0; j < net->nan[c]; j++) z->n_n[c][r][j] = net->ni[c][(net->mu[c][j] - 1) * 6 + r];
+    }
+  }
+  z->gg = dalloc(ny + 1); z->dlngdt9 = dalloc(ny + 1);
+  z->rffn = dalloc(net->nffn); z->dlnrffndt9 = dalloc(net->nffn); z->qkffn = dalloc(net->nffn + 1);
+  z->phasei = dalloc(net->nffn); z->dphaseidt9 = dalloc(net->nffn);
+  z->dydotdy = dalloc((size_t)z->msize * z->msize); z->jac = dalloc((size_t)z->msize * z->msize);
+  z->rhs = dalloc(z->msize); z->indx = (int *)calloc(z->msize, sizeof(int));
+  return z;
+}
+static void zone_free(zone_t *z) {
+  int c, r;
+  free(z->y); free(z->yo); free(z->yt); free(z->ydot); free(z->yrhs); free(z->dy); free(z->reldy); free(z->rtau);
+  for (c = 0; c < 4; c++) {
+    free(z->csect[c]); free(z->dcsect[c]); free(z->h[c]); free(z->dh[c]); free(z->b[c]);
+    for (r = 0; r <= c; r++) free(z->n_n[c][r]);
+  }
+  free(z->gg); free(z->dlngdt9); free(z->rffn); free(z->dlnrffndt9); free(z->qkffn); free(z->phasei); free(z->dphaseidt9);
+  free(z->dydotdy); free(z->jac); free(z->rhs); free(z->indx); free(z);
+}
+static void zone_reset_scratch(zone_t *z) {
+  const ox_net *net = z->net; int c;
+  for (c = 0; c < 4; c++) {
+    memset(z->csect[c], 0, sizeof(double) * net->nr[c]); memset(z->dcsect[c], 0, sizeof(double) * net->nr[c]);
+    memset(z->h[c], 0, sizeof(double) * net->nr[c]); memset(z->dh[c], 0, sizeof(double) * net->nr[c]);
+    memset(z->b[c], 0, sizeof(double) * net->nan[c]);
+  }
+  memset(z->qkffn, 0, sizeof(double) * (net->nffn + 1));
+  memset(z->rffn, 0, sizeof(double) * (net->nffn ? net->nffn : 1));
+  memset(z->ydot, 0, sizeof(double) * z->ny);
+  z->cv = z->etae = z->detaedt9 = 0.0; z->t9dot = 0.0;
+}
+
+static void hist_put(const ox_out *out, int iz, int ny, int kstep, const zone_t *z, double edot, double sqnu) {
+  int n;
+  if (out->hist_cap <= 0) return;
+  n = out->hist_n[iz];
+  if (n < out->hist_cap) {
+    size_t o = (size_t)iz * out->hist_cap + n;
+    out->hist_kstep[o] = kstep; out->hist_kmon[2 * o] = z->kmon[0]; out->hist_kmon[2 * o + 1] = z->kmon[1];
+    out->hist_t[o] = z->t; out->hist_t9[o] = z->t9; out->hist_rho[o] = z->rho; out->hist_tdel[o] = z->tdel;
+    out->hist_edot[o] = edot; out->hist_sqnu[o] = sqnu;
+    memcpy(out->hist_y + o * ny, z->y, sizeof(double) * ny);
+  }
+  out->hist_n[iz] = n + 1;
+}
+
+static int full_net_zone(zone_t *z, const ox_zones *zn, int iz, ox_out *out) {
+  /* net.F90:246-272 (zone load) + xnet_evolve.F90:19-269 */
+  const ox_ctl *ctl = z->ctl; int ny = z->ny, fx = zn->zfix[iz], k, kstep, its, lzsolve, mykstep = 0, rc_ = 0, kstep0 = 0;
+  double enb, enm, enold, edot, sqnu;
+  zone_reset_scratch(z);
+  z->nh = zn->nh[fx]; z->th = zn->th + zn->off[fx]; z->t9h = zn->t9h + zn->off[fx]; z->rhoh = zn->rhoh + zn->off[fx];
+  z->has_scale = zn->rho_scale != NULL; z->rho_scale = z->has_scale ? zn->rho_scale[iz] : 1.0;
+  z->tstart = zn->tstart[fx]; z->tstop = zn->tstop[fx]; z->tdelstart = zn->tdelstart[fx];
+  z->xext = zn->xext[fx]; z->aext = zn->aext[fx]; z->zext = zn->zext[fx];
+  z->tdel = 0.0; z->nt = zn->nstart[fx]; z->t = z->tstart; z->t9 = zn->t9start[fx];
+  z->rho = z->has_scale ? zn->rhostart[fx] * z->rho_scale : zn->rhostart[fx];
+  z->ye = zn->yestart[fx];
+  for (k = 0; k < ny; k++) z->y[k] = zn->ystart[(size_t)fx * ny + k];
+  its = 0; lzsolve = 1;
+  for (k = 0; k < 5; k++) { z->kmon[k] = 0; z->ktot[k] = 0; }
+  z->ints = 0; z->intso = 0;
+  if (out->hist_cap > 0) out->hist_n[iz] = 0;
+  if (zn->rs_t != NULL) {
+    /* restart from a recorded accepted step (state after solve_be's roll, xnet_integrate_be.F90:181-196) */
+    double t9x, rhox;
+    kstep0 = zn->rs_kstep0[iz];
+    z->t = zn->rs_t[iz]; z->tdel = zn->rs_tdel[iz]; z->tdel_next = z->tdel * ctl->tdel_maxmult;
+    z->t9 = zn->rs_t9[iz]; z->rho = zn->rs_rho[iz]; z->t9o = zn->rs_t9o[iz];
+    for (k = 0; k < ny; k++) { z->y[k] = zn->rs_y[(size_t)iz * ny + k]; z->yo[k] = zn->rs_yo[(size_t)iz * ny + k]; z->yt[k] = z->y[k]; }
+    t9rhofind(z, z->t, &z->nt, &t9x, &rhox);
+    z->tdel_old = z->tdel; z->nto = z->nt; z->ntt = z->nt; z->to = z->t; z->tt = z->t;
+    z->t9t = z->t9; z->rhoo = z->rho; z->rhot = z->rho; z->yeo = z->ye; z->yet = z->ye;
+    benuc(z, z->y, &enb, &enm);
+    enold = enm; edot = 0.0; sqnu = 0.0;
+  } else {
+  benuc(z, z->y, &enb, &enm);
+  z->tdel_old = z->tdel; z->tdel_next = z->tdel; z->nto = z->nt; z->ntt = z->nt; z->to = z->t; z->tt = z->t;
+  z->t9o = z->t9; z->t9t = z->t9; z->rhoo = z->rho; z->rhot = z->rho; z->yeo = z->ye; z->yet = z->ye;
+  for (k = 0; k < ny; k++) { z->yo[k] = z->y[k]; z->yt[k] = z->y[k]; }
+  enold = 0.0; edot = 0.0; sqnu = 0.0;
+  hist_put(out, iz, ny, 0, z, edot, sqnu);
+  }
+  for (kstep = kstep0 + 1; kstep <= kstep0 + ctl->kstmx; kstep++) {
+    int lzoutput;
+    if (lzsolve) { rc_ = timestep(z, kstep); if (rc_) break; }
+    rc_ = solve_be(z, kstep, &its); if (rc_) break;
+    lzoutput = 1;
+    if (its == 0) {
+      enold = enm;
+      if (z->t >= z->tstop) { mykstep = kstep; its = -1; lzsolve = 0; }
+    } else if (its == 1) { its = 2; lzsolve = 0; lzoutput = 0; }
+    else { lzsolve = 0; lzoutput = 0; }
+    if (lzoutput) {
+      benuc(z, z->yt, &enb, &enm);
+      enudot(z, z->yt, &sqnu);
+      edot = -(enm - enold) / z->tdel;
+      hist_put(out, iz, ny, kstep, z, edot, sqnu);
+    }
+    if (!lzsolve) break;
+  }
+  for (k = 0; k < ny; k++) out->y[(size_t)iz * ny + k] = z->y[k];
+  out->t[iz] = z->t; out->t9[iz] = z->t9; out->rho[iz] = z->rho; out->tdel[iz] = z->tdel;
+  out->kstep[iz] = mykstep; out->status[iz] = its;
+  for (k = 0; k < 5; k++) out->ktot[(size_t)iz * 5 + k] = z->ktot[k];
+  return rc_;
+}
+
+int ox_full_net(const ox_net *net, const ox_ctl *ctl, const ox_zones *zn, ox_out *out, int nthreads) {
+  int rc_all = 0;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+  {
+    zone_t *z = zone_new(net, ctl);
+    int iz;
+#pragma omp for schedule(dynamic, 1)
+    for (iz = 0; iz < zn->nzone; iz++) {
+      int r = full_net_zone(z, zn, iz, out);
+      if (r) {
+#pragma omp critical
+        rc_all = r;
+      }
+    }
+    zone_free(z);
+  }
+  return rc_all;
+}
+
+int ox_eval_point(const ox_net *net, const ox_ctl *ctl, double t9, double rho, const double *y,
+                  double xext, double aext, double zext, double diag, double mult,
+                  double *csect, double *ydot, double *jac, double *ye_out) {
+  zone_t *z = zone_new(net, ctl); int k, c, o = 0, rc_;
+  zone_reset_scratch(z);
+  z->t9t = t9; z->rhot = rho; z->xext = xext; z->aext = aext; z->zext = zext; z->nh = 2;
+  for (k = 0; k < z->ny; k++) { z->yt[k] = y[k]; z->y[k] = y[k]; }
+  rc_ = cross_sect(z);
+  if (!rc_) {
+    yderiv(z);
+    jacobian_build(z, diag, mult);
+    for (c = 0; c < 4; c++) { memcpy(csect + o, z->csect[c], sizeof(double) * net->nr[c]); o += net->nr[c]; }
+    memcpy(ydot, z->ydot, sizeof(double) * z->ny);
+    memcpy(jac, z->jac, sizeof(double) * z->msize * z->msize);
+    *ye_out = z->yet;
+  }
+  zone_free(z);
+  return rc_;
+}
