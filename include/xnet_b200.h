@@ -1,0 +1,182 @@
+/* xnet_b200 -- C ABI of the B200-native batched per-zone implicit step for XNet.
+ *
+ * This is the drop-in boundary: everything a Fortran `xnet_jacobian_b200.F90` /
+ * `xnet_integrate_b200.F90` shim (iso_c_binding) binds.  Plain C types only;
+ * every pointer is a HOST pointer to caller-owned memory unless the name starts with `d_`.
+ * Fortran arrays are passed as they lie in memory (column-major, zone index last), Fortran
+ * LOGICAL(4) masks as int32 (non-zero = .true.), species/reaction indices stay 1-based.
+ *
+ * Return value of every function: 0 = ok; <0 = error (message via xb_last_error()); numerical
+ * singularity is NOT an error (reported per zone in `info`, LAPACK meaning).  There is no CPU
+ * fallback anywhere: without a usable CUDA device every compute entry point returns XB_ERR_CUDA.
+ *
+ * Reference interfaces replaced (paths relative to the XNet tree, /root/reference):
+ *   xb_net_from_arrays    <- read_reaction_data / read_nuclear_data module state
+ *                            (source/xnet_data.F90:391-513, 654-956)
+ *   xb_net_load           <- net_preprocess + read_* from files (source/xnet_preprocess.F90:505-1011)
+ *   xb_ctx_create         <- read_jacobian_data (source/xnet_jacobian_dense.F90:54-119), be_init
+ *                            (source/xnet_integrate_be.F90:484-551)
+ *   xb_ctx_destroy        <- jacobian_finalize (source/xnet_jacobian_dense.F90:121-134)
+ *   xb_cross_sect         <- cross_sect (source/xnet_integrate.F90:569-984)
+ *   xb_yderiv             <- yderiv (source/xnet_integrate.F90:364-567)
+ *   xb_jacobian_build     <- jacobian_build + jacobian_scale (source/xnet_jacobian_dense.F90:136-434)
+ *   xb_jacobian_decomp    <- jacobian_decomp -> LUDecompBatched_GPU/cublasDgetrfBatched
+ *                            (source/xnet_jacobian_dense.F90:549-616, source/xnet_linalg.F90:1814-1870)
+ *   xb_jacobian_bksub     <- jacobian_bksub -> cublasDgetrsBatched
+ *                            (source/xnet_jacobian_dense.F90:618-732, source/xnet_linalg.F90:1895-1960)
+ *   xb_jacobian_solve     <- jacobian_solve (source/xnet_jacobian_dense.F90:436-547)
+ *   xb_step_be            <- step_be Newton loop (source/xnet_integrate_be.F90:233-482)
+ *   xb_evolve             <- full_net + solve_be + timestep, device resident
+ *                            (source/xnet_evolve.F90:19-269, xnet_integrate_be.F90:32-231,
+ *                             xnet_integrate.F90:13-268)
+ */
+#ifndef XNET_B200_H
+#define XNET_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XB_OK 0
+#define XB_ERR_ARG (-1)
+#define XB_ERR_IO (-2)
+#define XB_ERR_CUDA (-3)
+#define XB_ERR_UNSUPPORTED (-4)
+
+typedef struct xb_net xb_net;   /* zone-invariant network tables (host copy)     */
+typedef struct xb_ctx xb_ctx;   /* device context: tables + per-zone state in HBM */
+
+/* Network tables as the Fortran modules hold them (nuclear_data, reaction_data, xnet_ffn).
+ * c = 0..3 indexes 1..4-reactant reactions.  All index values 1-based, 0 = blank slot. */
+typedef struct {
+  int32_t ny, nffn, nnnu;
+  int32_t nreac[4], nan[4];
+  const double *rc[4];       /* rc_n(7,nreac)                                        */
+  const int32_t *ni[4];      /* n1i(5,nr1), n2i..n4i(6,nr)  (leading dim given below) */
+  int32_t ni_ld[4];          /* 5,6,6,6 for Fortran arrays                           */
+  const int32_t *iwk[4], *irev[4];
+  const int32_t *la, *le;    /* la(4,ny), le(4,ny) as in Fortran (class index fastest) */
+  const int32_t *mu[4];      /* mu_n(nan)                                            */
+  const double *a[4];        /* a_n(nan)                                             */
+  const double *aa, *zz, *mex, *be; /* (ny) */
+  double mex_n, mex_p;
+  const double *g;           /* g(24,ny)                                             */
+  const double *t9i;         /* t9i(24)                                              */
+  const double *ffnsum, *ffnenu; /* (nffn,143) Fortran order: rate index fastest     */
+  const double *ffn_ec, *ffn_beta, *ffn_qval; const int32_t *has_logft; /* may be NULL */
+} xb_net_arrays;
+
+/* Controls (xnet_controls.F90:20-62) */
+typedef struct {
+  int32_t iweak0, iscrn, iheat, isolv, kstmx, kitmx, ijac, iconvc;
+  double changemx, changemxt, yacc, tolm, tolc, tolt9, ymin, tdel_maxmult;
+  int32_t arith;             /* 0 = fast (FMA contraction, CUDA libm); 1 = strict (no FMA,
+                                portable elementary functions: bit-reproducible vs the oracle) */
+  int32_t reserved;
+} xb_ctl;
+
+const char *xb_last_error(void);
+int xb_version(void);
+/* number of kernels launched by this library since load / since last reset (bench's gpu_launches) */
+long long xb_launch_count(int reset);
+
+/* ---- network ---------------------------------------------------------------------------- */
+int xb_net_load(const char *data_dir, int iweak0, xb_net **net);
+int xb_net_from_arrays(const xb_net_arrays *arr, xb_net **net);
+void xb_net_free(xb_net *net);
+/* introspection (tests check these bit-exactly): what = "ny","nffn","nnnu","nreac1".."nreac4",
+ * "nan1".."nan4","izmax" */
+int xb_net_int(const xb_net *net, const char *what, int32_t *value);
+/* copies an integer table; what = "la","le" (4*ny, class-major: la[c*ny+i]), "mu1".."mu4",
+ * "n1i".."n4i" (6 per reaction), "iwk1".., "irev1".., "ires1".., "iffn", "chap_la","chap_le" (11) */
+int xb_net_itable(const xb_net *net, const char *what, int32_t *out, int64_t cap, int64_t *n);
+/* what = "a1".."a4","rc1".."rc4" (7 per reaction),"q1".."q4","aa","zz","mex","be","g","t9i",
+ * "ffnsum","ffnenu" (143 per rate) */
+int xb_net_dtable(const xb_net *net, const char *what, double *out, int64_t cap, int64_t *n);
+
+/* ---- per-zone input fixtures (host readers; model_input_ascii.F90) ------------------------ */
+/* thermo trajectory: returns nh and fills th/t9h/rhoh/yeh (cap entries each) + header scalars
+ * hdr[0..2] = tstart,tstop,tdelstart(=min(0,file value)) */
+int xb_read_thermo(const char *path, int32_t cap, int32_t *nh, double *th, double *t9h, double *rhoh,
+                   double *yeh, double *hdr);
+/* initial abundances: y[ny], scal[0..3] = yein,xext,aext,zext */
+int xb_read_inab(const xb_net *net, const char *path, double *y, double *scal);
+
+/* start-of-run conditions of a fixture (net.F90:249-268): scal = output of xb_read_inab;
+ * out4 = t9start, rhostart, yestart, 0 */
+int xb_zone_start(const xb_net *net, int32_t nh, const double *th, const double *t9h, const double *rhoh,
+                  const double *yeh, double tstart, const double *y, const double *scal, int32_t *nstart,
+                  double *out4);
+
+/* ---- device context ------------------------------------------------------------------------ */
+int xb_ctx_create(const xb_net *net, const xb_ctl *ctl, int32_t nzevolve, int32_t device, xb_ctx **ctx);
+void xb_ctx_destroy(xb_ctx *ctx);
+
+/* ---- module-level drop-ins (zone slice [zlo,zhi], 1-based inclusive like zb_lo:zb_hi) ------- */
+/* cross_sect: inputs yt(ny,nz), t9t, rhot (+xext,aext,zext may be NULL = 0,1,0); outputs yet;
+ * csect/h stay device resident.  mask NULL = all. */
+int xb_cross_sect(xb_ctx *ctx, int32_t zlo, int32_t zhi, const int32_t *mask, const double *yt,
+                  const double *t9t, const double *rhot, const double *xext, const double *aext,
+                  const double *zext, double *yet);
+/* copies the device-resident csect back: csect[(nr1+nr2+nr3+nr4), nz] */
+int xb_get_csect(xb_ctx *ctx, int32_t zlo, int32_t zhi, double *csect);
+int xb_yderiv(xb_ctx *ctx, int32_t zlo, int32_t zhi, const int32_t *mask, const double *yt, double *ydot);
+int xb_jacobian_build(xb_ctx *ctx, int32_t zlo, int32_t zhi, const int32_t *mask, const double *diag,
+                      const double *mult);
+/* copies jac(msize,msize,nz) back (idiag>=5 style inspection) */
+int xb_get_jac(xb_ctx *ctx, int32_t zlo, int32_t zhi, double *jac);
+/* uploads jac(msize,msize,nz) (lets a caller use decomp/bksub as a pure batched solver) */
+int xb_set_jac(xb_ctx *ctx, int32_t zlo, int32_t zhi, const double *jac);
+int xb_jacobian_decomp(xb_ctx *ctx, int32_t zlo, int32_t zhi, const int32_t *mask, int32_t *info);
+int xb_get_indx(xb_ctx *ctx, int32_t zlo, int32_t zhi, int32_t *indx);
+int xb_jacobian_bksub(xb_ctx *ctx, int32_t zlo, int32_t zhi, const int32_t *mask, const double *yrhs,
+                      const double *t9rhs, double *dy, double *dt9);
+int xb_jacobian_solve(xb_ctx *ctx, int32_t zlo, int32_t zhi, const int32_t *mask, const double *yrhs,
+                      const double *t9rhs, double *dy, double *dt9, int32_t *info);
+
+/* ---- fused evolve (full_net on device) ------------------------------------------------------ */
+typedef struct {
+  int32_t nfix;              /* distinct fixtures                                          */
+  const int32_t *nh, *off;   /* [nfix] points / offset into th,t9h,rhoh                    */
+  const double *th, *t9h, *rhoh;
+  const double *tstart, *tstop, *tdelstart;  /* [nfix]                                      */
+  const int32_t *nstart;                     /* [nfix]                                      */
+  const double *t9start, *rhostart, *yestart;/* [nfix]                                      */
+  const double *ystart;                      /* [nfix][ny]                                  */
+  const double *xext, *aext, *zext;          /* [nfix]                                      */
+  int32_t nzone;
+  const int32_t *zfix;       /* [nzone] fixture of each zone                               */
+  const double *rho_scale;   /* [nzone] or NULL                                            */
+  /* optional restart state (NULL = start from fixture): see DESIGN.md "restart parity"     */
+  const double *rs_t, *rs_tdel, *rs_t9, *rs_rho, *rs_t9o, *rs_y, *rs_yo; const int32_t *rs_kstep0;
+} xb_zones;
+
+typedef struct {
+  double *y;                 /* [nzone][ny]                                                */
+  double *t, *t9, *rho, *tdel; /* [nzone]                                                  */
+  int32_t *kstep, *ktot, *status; /* [nzone], [nzone][5], [nzone]                          */
+  int32_t hist_cap;          /* 0 = no per-step history                                    */
+  int32_t *hist_n, *hist_kstep, *hist_kmon;
+  double *hist_t, *hist_t9, *hist_rho, *hist_tdel, *hist_edot, *hist_sqnu, *hist_y;
+} xb_out;
+
+/* host buffers in, host buffers out (H2D + kernel + D2H): the end-to-end call */
+int xb_evolve(xb_ctx *ctx, const xb_zones *zones, xb_out *out);
+/* split form for device-resident timing: upload once, run many times, download */
+int xb_zones_upload(xb_ctx *ctx, const xb_zones *zones, int32_t hist_cap);
+int xb_evolve_resident(xb_ctx *ctx, float *kernel_ms);   /* runs on the uploaded zones */
+int xb_results_download(xb_ctx *ctx, xb_out *out);
+/* per-phase cycle counters of the last resident run (sum over CTAs): rates,yderiv,jac,lu,bksub,other,total */
+int xb_phase_cycles(xb_ctx *ctx, double *cycles7);
+/* bytes moved host->device / device->host by the last xb_evolve call */
+int xb_last_copy_bytes(xb_ctx *ctx, int64_t *h2d, int64_t *d2h);
+/* cfg6 = grid, threads per CTA, dynamic smem bytes, jacobian-in-smem flag, SM count, msize */
+int xb_launch_config(xb_ctx *ctx, int32_t *cfg6);
+/* measured FP64 FMA peak of this device (microbenchmark, FLOP/s) */
+int xb_measure_fp64_peak(int32_t device, double *flops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

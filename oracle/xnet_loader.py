@@ -542,7 +542,8 @@ def read_inab_file(path, nuc):
                 else:
                     yin[inuc - 1] = val
     xnet = 0.0; znet = 0.0
-    xnet = float(np.sum(yin * aa)); znet = float(np.sum(yin * zz))
+    for i in range(ny):          # sum(yin*aa), sum(yin*zz) evaluated left to right
+        xnet += yin[i] * aa[i]; znet += yin[i] * zz[i]
     if yext > 0.0 and xnet < 1.0 and znet < yein:
         xext = 1.0 - xnet
         aext = xext / yext

@@ -31,6 +31,19 @@
 #include <omp.h>
 #endif
 
+#ifdef OX_PMATH
+#include "ox_pmath.h"
+#define M_EXP(x) oxp_exp(x)
+#define M_LOG(x) oxp_log(x)
+#define M_LOG10(x) oxp_log10(x)
+#define M_POW10(x) oxp_pow10(x)
+#else
+#define M_EXP(x) exp(x)
+#define M_LOG(x) log(x)
+#define M_LOG10(x) log10(x)
+#define M_POW10(x) pow(10.0, (x))
+#endif
+
 #define NG 24
 #define NT9GRID 13
 #define NENEGRID 11
@@ -78,7 +91,7 @@ static double safe_exp(double x) {
   const double exp_max = 1024.0 * ln_2 * 0.9, exp_min = -1021.0 * ln_2 * 0.9;
   double v = x > exp_min ? x : exp_min;
   v = v < exp_max ? v : exp_max;
-  return exp(v);
+  return M_EXP(v);
 }
 
 static double rhoh_at(const zone_t *z, int n) { /* n 1-based */
@@ -154,7 +167,7 @@ static void ffn_rate(zone_t *z, double t9, double ene) {
   for (i = 1; i <= NT9GRID; i++) if (t9 <= t9grid[i - 1]) break;
   lt1 = (i - 1 > 1) ? i - 1 : 1;
   for (k = 1; k <= nffn; k++) {
-    double enel = log10(ene);
+    double enel = M_LOG10(ene);
     int le1 = (int)enel; if (le1 < 1) le1 = 1;
     double dt9 = t9grid[lt1] - t9grid[lt1 - 1];
     double rdt9 = (t9 - t9grid[lt1 - 1]) / dt9;
@@ -166,19 +179,19 @@ static void ffn_rate(zone_t *z, double t9, double ene) {
     double qdr1 = enu[i2 - 1] - enu[i1 - 1], qdr2 = enu[i4 - 1] - enu[i3 - 1];
     double qr1 = enu[i1 - 1] + rdt9 * qdr1, qr2 = enu[i3 - 1] + rdt9 * qdr2;
     double qk = qr1 + rdene * (qr2 - qr1);
-    z->qkffn[k] = (qk > lqkmin) ? pow(10.0, qk) : 0.0;
+    z->qkffn[k] = (qk > lqkmin) ? M_POW10(qk) : 0.0;
     if (net->has_logft[k - 1] > 0) {
       const double *ec = net->ffn_ec + (size_t)(k - 1) * NGRID;
       const double *be = net->ffn_beta + (size_t)(k - 1) * NGRID;
       double dr1_ec = ec[i2 - 1] - ec[i1 - 1], dr2_ec = ec[i4 - 1] - ec[i3 - 1];
       double r1 = ec[i1 - 1] + rdt9 * dr1_ec, r2 = ec[i3 - 1] + rdt9 * dr2_ec;
       double rf_ec = r1 + rdene * (r2 - r1), rf_beta, dr1, dr2, rf;
-      if (z->phasei[k - 1] > rfmin && rf_ec > lrfmin) rf_ec = ln_2 * z->phasei[k - 1] / pow(10.0, rf_ec);
+      if (z->phasei[k - 1] > rfmin && rf_ec > lrfmin) rf_ec = ln_2 * z->phasei[k - 1] / M_POW10(rf_ec);
       else rf_ec = 0.0;
       dr1 = be[i2 - 1] - be[i1 - 1]; dr2 = be[i4 - 1] - be[i3 - 1];
       r1 = be[i1 - 1] + rdt9 * dr1; r2 = be[i3 - 1] + rdt9 * dr2;
       rf_beta = r1 + rdene * (r2 - r1);
-      rf_beta = (rf_beta > lrfmin) ? pow(10.0, rf_beta) : 0.0;
+      rf_beta = (rf_beta > lrfmin) ? M_POW10(rf_beta) : 0.0;
       rf = rf_beta + rf_ec;
       if (rf_beta < rfmin && rf_ec < rfmin) { z->rffn[k - 1] = 0.0; z->dlnrffndt9[k - 1] = 0.0; }
       else {
@@ -196,7 +209,7 @@ static void ffn_rate(zone_t *z, double t9, double ene) {
       double r1 = sum[i1 - 1] + rdt9 * dr1, r2 = sum[i3 - 1] + rdt9 * dr2;
       double rf = r1 + rdene * (r2 - r1);
       if (rf < lrfmin) { z->rffn[k - 1] = 0.0; z->dlnrffndt9[k - 1] = 0.0; }
-      else { z->rffn[k - 1] = pow(10.0, rf); z->dlnrffndt9[k - 1] = ln_10 * (rdene * dr2 + (1.0 - rdene) * dr1) / dt9; }
+      else { z->rffn[k - 1] = M_POW10(rf); z->dlnrffndt9[k - 1] = ln_10 * (rdene * dr2 + (1.0 - rdene) * dr1) / dt9; }
     }
   }
 }
@@ -219,8 +232,13 @@ static int cross_sect(zone_t *z) {
   if (t9t < 0.01 && ctl->iweak0 != 0) z->iweak = -abs(ctl->iweak0); else z->iweak = ctl->iweak0;
   partf(z, t9t);
   ene = z->yet * rhot;
-  t09[0] = 1.0; t09[1] = 1.0 / t9t; t09[2] = pow(t9t, -1.0 / 3.0); t09[3] = pow(t9t, 1.0 / 3.0);
-  t09[4] = t9t; t09[5] = pow(t9t, 5.0 / 3.0); t09[6] = log(t9t);
+  t09[0] = 1.0; t09[1] = 1.0 / t9t; t09[4] = t9t;
+#ifdef OX_PMATH
+  { double l = M_LOG(t9t);   /* pow(x,y) evaluated as exp(y*log(x)) in the portable-math build */
+    t09[2] = M_EXP((-1.0 / 3.0) * l); t09[3] = M_EXP((1.0 / 3.0) * l); t09[5] = M_EXP((5.0 / 3.0) * l); t09[6] = l; }
+#else
+  t09[2] = pow(t9t, -1.0 / 3.0); t09[3] = pow(t9t, 1.0 / 3.0); t09[5] = pow(t9t, 5.0 / 3.0); t09[6] = log(t9t);
+#endif
   dt09[0] = 0.0; dt09[1] = -(1.0 / (t9t * t9t)); dt09[2] = -pow(t9t, -4.0 / 3.0) / 3.0;
   dt09[3] = pow(t9t, -2.0 / 3.0) / 3.0; dt09[4] = 1.0; dt09[5] = pow(t9t, 2.0 / 3.0) * 5.0 / 3.0;
   dt09[6] = 1.0 / t9t;

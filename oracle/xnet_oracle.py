@@ -53,7 +53,7 @@ class OxOut(C.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, 'liboracle.so')
-    if force or not os.path.exists(so) or not os.path.exists(os.path.join(_HERE, 'liboracle_fast.so')):
+    if force or not all(os.path.exists(os.path.join(_HERE, n)) for n in ('liboracle.so', 'liboracle_fast.so', 'liboracle_pm.so')):
         subprocess.check_call(['make', '-C', _HERE, '-s'])
     return so
 
@@ -62,10 +62,10 @@ _libs = {}
 
 
 def lib(fast=False):
-    key = 'fast' if fast else 'strict'
+    key = fast if isinstance(fast, str) else ('fast' if fast else 'strict')
     if key not in _libs:
         build()
-        l = C.CDLL(os.path.join(_HERE, 'liboracle_fast.so' if fast else 'liboracle.so'))
+        l = C.CDLL(os.path.join(_HERE, {'fast': 'liboracle_fast.so', 'strict': 'liboracle.so', 'pm': 'liboracle_pm.so'}[key]))
         l.ox_full_net.restype = C.c_int
         l.ox_full_net.argtypes = [C.POINTER(OxNet), C.POINTER(OxCtl), C.POINTER(OxZones), C.POINTER(OxOut), C.c_int]
         l.ox_dgetrf.argtypes = [C.c_int, C.c_int, c_dp, C.c_int, c_ip, c_ip]

@@ -1,0 +1,421 @@
+"""ctypes binding of libxnet_b200.so + the host-side mirror of XNet's driver inputs.
+
+Names follow the reference: `read_controls` (xnet_controls.F90:164-396) parses a `control` file,
+`Network` is the nuclear_data/reaction_data module state, `Context` the device-resident state that
+`read_jacobian_data`/`be_init` allocate, and its methods are the module procedures
+(`cross_sect`, `yderiv`, `jacobian_build`, `jacobian_decomp`, `jacobian_bksub`, `full_net`).
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int32)
+
+
+class XnetB200Error(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, 'libxnet_b200.so')
+
+
+class XbCtl(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ('iweak0', 'iscrn', 'iheat', 'isolv', 'kstmx', 'kitmx', 'ijac', 'iconvc')] + \
+               [(n, C.c_double) for n in ('changemx', 'changemxt', 'yacc', 'tolm', 'tolc', 'tolt9', 'ymin', 'tdel_maxmult')] + \
+               [('arith', C.c_int32), ('reserved', C.c_int32)]
+
+
+class XbZones(C.Structure):
+    _fields_ = [('nfix', C.c_int32), ('nh', c_ip), ('off', c_ip), ('th', c_dp), ('t9h', c_dp), ('rhoh', c_dp),
+                ('tstart', c_dp), ('tstop', c_dp), ('tdelstart', c_dp), ('nstart', c_ip),
+                ('t9start', c_dp), ('rhostart', c_dp), ('yestart', c_dp), ('ystart', c_dp),
+                ('xext', c_dp), ('aext', c_dp), ('zext', c_dp),
+                ('nzone', C.c_int32), ('zfix', c_ip), ('rho_scale', c_dp),
+                ('rs_t', c_dp), ('rs_tdel', c_dp), ('rs_t9', c_dp), ('rs_rho', c_dp), ('rs_t9o', c_dp),
+                ('rs_y', c_dp), ('rs_yo', c_dp), ('rs_kstep0', c_ip)]
+
+
+class XbOut(C.Structure):
+    _fields_ = [('y', c_dp), ('t', c_dp), ('t9', c_dp), ('rho', c_dp), ('tdel', c_dp),
+                ('kstep', c_ip), ('ktot', c_ip), ('status', c_ip),
+                ('hist_cap', C.c_int32), ('hist_n', c_ip), ('hist_kstep', c_ip), ('hist_kmon', c_ip),
+                ('hist_t', c_dp), ('hist_t9', c_dp), ('hist_rho', c_dp), ('hist_tdel', c_dp),
+                ('hist_edot', c_dp), ('hist_sqnu', c_dp), ('hist_y', c_dp)]
+
+
+_lib = None
+
+# every symbol include/xnet_b200.h declares (tests check the library exports all of them)
+EXPORTS = ['xb_last_error', 'xb_version', 'xb_launch_count', 'xb_net_load', 'xb_net_from_arrays', 'xb_net_free',
+           'xb_net_int', 'xb_net_itable', 'xb_net_dtable', 'xb_read_thermo', 'xb_read_inab', 'xb_zone_start',
+           'xb_ctx_create', 'xb_ctx_destroy', 'xb_cross_sect', 'xb_get_csect', 'xb_yderiv', 'xb_jacobian_build',
+           'xb_get_jac', 'xb_set_jac', 'xb_jacobian_decomp', 'xb_get_indx', 'xb_jacobian_bksub',
+           'xb_jacobian_solve', 'xb_evolve', 'xb_zones_upload', 'xb_evolve_resident', 'xb_results_download',
+           'xb_phase_cycles', 'xb_last_copy_bytes', 'xb_launch_config', 'xb_measure_fp64_peak']
+
+
+def lib():
+    """Loads libxnet_b200.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            raise XnetB200Error('libxnet_b200.so is not built (run __graft_entry__.build()); no CPU fallback exists')
+        l = C.CDLL(p)
+        l.xb_last_error.restype = C.c_char_p
+        l.xb_launch_count.restype = C.c_longlong
+        l.xb_launch_count.argtypes = [C.c_int]
+        l.xb_net_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+        l.xb_net_free.argtypes = [C.c_void_p]
+        l.xb_net_int.argtypes = [C.c_void_p, C.c_char_p, c_ip]
+        l.xb_net_itable.argtypes = [C.c_void_p, C.c_char_p, c_ip, C.c_int64, C.POINTER(C.c_int64)]
+        l.xb_net_dtable.argtypes = [C.c_void_p, C.c_char_p, c_dp, C.c_int64, C.POINTER(C.c_int64)]
+        l.xb_read_thermo.argtypes = [C.c_char_p, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, c_dp]
+        l.xb_read_inab.argtypes = [C.c_void_p, C.c_char_p, c_dp, c_dp]
+        l.xb_zone_start.argtypes = [C.c_void_p, C.c_int32, c_dp, c_dp, c_dp, c_dp, C.c_double, c_dp, c_dp, c_ip, c_dp]
+        l.xb_ctx_create.argtypes = [C.c_void_p, C.POINTER(XbCtl), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        l.xb_ctx_destroy.argtypes = [C.c_void_p]
+        l.xb_cross_sect.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
+        l.xb_get_csect.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_dp]
+        l.xb_yderiv.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_ip, c_dp, c_dp]
+        l.xb_jacobian_build.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_ip, c_dp, c_dp]
+        l.xb_get_jac.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_dp]
+        l.xb_set_jac.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_dp]
+        l.xb_jacobian_decomp.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_ip, c_ip]
+        l.xb_get_indx.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_ip]
+        l.xb_jacobian_bksub.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp]
+        l.xb_jacobian_solve.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, c_ip]
+        l.xb_evolve.argtypes = [C.c_void_p, C.POINTER(XbZones), C.POINTER(XbOut)]
+        l.xb_zones_upload.argtypes = [C.c_void_p, C.POINTER(XbZones), C.c_int32]
+        l.xb_evolve_resident.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        l.xb_results_download.argtypes = [C.c_void_p, C.POINTER(XbOut)]
+        l.xb_phase_cycles.argtypes = [C.c_void_p, c_dp]
+        l.xb_last_copy_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        l.xb_launch_config.argtypes = [C.c_void_p, c_ip]
+        l.xb_measure_fp64_peak.argtypes = [C.c_int32, c_dp]
+        _lib = l
+    return _lib
+
+
+def _chk(rc):
+    if rc != 0:
+        raise XnetB200Error('xnet_b200 error %d: %s' % (rc, lib().xb_last_error().decode()))
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _pd(a):
+    return None if a is None else a.ctypes.data_as(c_dp)
+
+
+def _pi(a):
+    return None if a is None else a.ctypes.data_as(c_ip)
+
+
+# --------------------------------------------------------------------------------------------------
+class Controls(dict):
+    """Parsed `control` file (keys named as the xnet_controls module variables)."""
+    def to_struct(self, arith=0, **override):
+        c = XbCtl()
+        for nm, _ in XbCtl._fields_:
+            if nm in ('arith', 'reserved'):
+                continue
+            setattr(c, nm, override.get(nm, self[nm]))
+        c.arith = arith
+        return c
+
+
+def _block(lines, key):
+    for i, ln in enumerate(lines[:1000]):
+        if ln.startswith('##') and key in ln[2:82]:
+            return i + 1
+    return None
+
+
+def _tok(line):
+    return line.replace(',', ' ').split()[0]
+
+
+def _f(s):
+    return float(s.replace('D', 'E').replace('d', 'e'))
+
+
+def read_controls(text):
+    """Host mirror of read_controls (xnet_controls.F90:164-396): `## <Block>` markers located by
+    substring search, values list-directed one per line in fixed order, optional blocks defaulted."""
+    ln = text.split('\n')
+    c = Controls()
+    p = _block(ln, 'Job Controls')
+    for k, nm in enumerate(('szone', 'nzone', 'iweak0', 'iscrn', 'iprocess')):
+        c[nm] = int(_tok(ln[p + k]))
+    p = _block(ln, 'Zone Batching Controls')
+    c['nzbatchmx'] = int(_tok(ln[p])) if p is not None else 1
+    p = _block(ln, 'Integration Controls')
+    for k, nm in enumerate(('isolv', 'kstmx', 'kitmx', 'ijac', 'iconvc')):
+        c[nm] = int(_tok(ln[p + k]))
+    for k, nm in enumerate(('changemx', 'yacc', 'tolm', 'tolc', 'ymin', 'tdel_maxmult')):
+        c[nm] = _f(_tok(ln[p + 5 + k]))
+    p = _block(ln, 'Self-heating Controls')
+    if p is not None:
+        c['iheat'] = int(_tok(ln[p])); c['changemxt'] = _f(_tok(ln[p + 1])); c['tolt9'] = _f(_tok(ln[p + 2]))
+    else:
+        c['iheat'] = 0; c['changemxt'] = 1.0e-2; c['tolt9'] = 1.0e-4
+    if c['isolv'] == 3:
+        c['changemx'] = 1.0e+10; c['changemxt'] = 1.0e+10
+    p = _block(ln, 'NSE Initial Conditions')
+    c['t9nse'] = _f(_tok(ln[p])) if p is not None else 8.0
+    p = _block(ln, 'Neutrinos')
+    c['ineutrino'] = int(_tok(ln[p])) if p is not None else 0
+    p = _block(ln, 'Output Controls')
+    c['idiag'] = int(_tok(ln[p])); c['itsout'] = int(_tok(ln[p + 1]))
+    c['ev_file_base'] = ln[p + 3][:80].strip(); c['bin_file_base'] = ln[p + 5][:80].strip()
+    p = _block(ln, 'Input Controls')
+    c['data_dir'] = ln[p + 1][:80].strip()
+    files = [x[:80].strip() for x in ln[p + 3:p + 3 + 2 * c['nzone']] if x.strip()]
+    inab, th = files[0::2], files[1::2]
+    n = min(len(inab), len(th))
+    inab, th = inab[:n], th[:n]
+    if n == 1 and c['nzone'] > 1:  # base name + zero padded zone number (xnet_util.F90:341-370)
+        w = len(str(c['nzone']))
+        inab = [inab[0] + str(k + 1).zfill(w) for k in range(c['nzone'])]
+        th = [th[0] + str(k + 1).zfill(w) for k in range(c['nzone'])]
+    c['inab_file'] = inab; c['thermo_file'] = th
+    return c
+
+
+class Network:
+    """Zone-invariant tables (nuclear_data + reaction_data), loaded and pre-processed by the C++
+    host side of the library (xb_net_load)."""
+    def __init__(self, data_dir, iweak0=1):
+        self.h = C.c_void_p()
+        _chk(lib().xb_net_load(data_dir.encode(), iweak0, C.byref(self.h)))
+        self.data_dir = data_dir
+        self.ny = self.int('ny')
+        self.nreac = [self.int('nreac%d' % k) for k in (1, 2, 3, 4)]
+        self.nan = [self.int('nan%d' % k) for k in (1, 2, 3, 4)]
+        self.nffn = self.int('nffn'); self.nnnu = self.int('nnnu')
+
+    def int(self, what):
+        v = C.c_int32()
+        _chk(lib().xb_net_int(self.h, what.encode(), C.byref(v)))
+        return v.value
+
+    def itable(self, what):
+        n = C.c_int64()
+        _chk(lib().xb_net_itable(self.h, what.encode(), None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 1), np.int32)
+        _chk(lib().xb_net_itable(self.h, what.encode(), _pi(out), out.size, C.byref(n)))
+        return out[:n.value]
+
+    def dtable(self, what):
+        n = C.c_int64()
+        _chk(lib().xb_net_dtable(self.h, what.encode(), None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 1))
+        _chk(lib().xb_net_dtable(self.h, what.encode(), _pd(out), out.size, C.byref(n)))
+        return out[:n.value]
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().xb_net_free(self.h); self.h = None
+        except Exception:
+            pass
+
+
+class Fixture(dict):
+    """One (trajectory, initial abundance) input pair with its start-of-run conditions."""
+
+
+def load_fixture(net, inab_path, th_path):
+    """read_thermo_file + load_initial_abundances + t9rhofind(tstart) through the C ABI."""
+    l = lib()
+    nh = C.c_int32(); hdr = np.zeros(3)
+    _chk(l.xb_read_thermo(th_path.encode(), 0, C.byref(nh), None, None, None, None, _pd(hdr)))
+    th = np.zeros(nh.value); t9h = np.zeros(nh.value); rhoh = np.zeros(nh.value); yeh = np.zeros(nh.value)
+    _chk(l.xb_read_thermo(th_path.encode(), nh.value, C.byref(nh), _pd(th), _pd(t9h), _pd(rhoh), _pd(yeh), _pd(hdr)))
+    y = np.zeros(net.ny); scal = np.zeros(4)
+    _chk(l.xb_read_inab(net.h, inab_path.encode(), _pd(y), _pd(scal)))
+    nstart = C.c_int32(); out4 = np.zeros(4)
+    _chk(l.xb_zone_start(net.h, nh.value, _pd(th), _pd(t9h), _pd(rhoh), _pd(yeh), hdr[0], _pd(y), _pd(scal),
+                         C.byref(nstart), _pd(out4)))
+    return Fixture(nh=nh.value, th=th, t9h=t9h, rhoh=rhoh, yeh=yeh, tstart=hdr[0], tstop=hdr[1], tdelstart=hdr[2],
+                   nstart=nstart.value, t9start=out4[0], rhostart=out4[1], yestart=out4[2], ystart=y,
+                   xext=scal[1], aext=scal[2], zext=scal[3])
+
+
+def build_zone_set(fixtures, nzone=None, zfix=None, rho_scale=None, restart=None):
+    """Packs fixtures into the xb_zones layout; zone z uses fixture z mod K unless zfix is given."""
+    K = len(fixtures)
+    nzone = nzone or K
+    a = dict(
+        nh=_i([f['nh'] for f in fixtures]),
+        off=_i(np.concatenate([[0], np.cumsum([f['nh'] for f in fixtures])[:-1]])),
+        th=_d(np.concatenate([f['th'] for f in fixtures])), t9h=_d(np.concatenate([f['t9h'] for f in fixtures])),
+        rhoh=_d(np.concatenate([f['rhoh'] for f in fixtures])),
+        tstart=_d([f['tstart'] for f in fixtures]), tstop=_d([f['tstop'] for f in fixtures]),
+        tdelstart=_d([f['tdelstart'] for f in fixtures]), nstart=_i([f['nstart'] for f in fixtures]),
+        t9start=_d([f['t9start'] for f in fixtures]), rhostart=_d([f['rhostart'] for f in fixtures]),
+        yestart=_d([f['yestart'] for f in fixtures]), ystart=_d(np.stack([f['ystart'] for f in fixtures])),
+        xext=_d([f['xext'] for f in fixtures]), aext=_d([f['aext'] for f in fixtures]),
+        zext=_d([f['zext'] for f in fixtures]),
+        zfix=_i(np.arange(nzone) % K) if zfix is None else _i(zfix))
+    if rho_scale is not None:
+        a['rho_scale'] = _d(rho_scale)
+    if restart is not None:
+        for nm in ('t', 'tdel', 't9', 'rho', 't9o', 'y', 'yo'):
+            a['rs_' + nm] = _d(restart[nm])
+        a['rs_kstep0'] = _i(restart['kstep0'])
+    z = XbZones()
+    z.nfix = K; z.nzone = nzone
+    for nm, tp in XbZones._fields_:
+        if nm in a:
+            setattr(z, nm, _pi(a[nm]) if tp is c_ip else _pd(a[nm]))
+    z._keep = a
+    return z
+
+
+def _alloc_out(nzone, ny, hist_cap, pinned=False):
+    def arr(shape, dt):
+        if pinned:
+            import torch
+            t = torch.zeros(shape, dtype=torch.float64 if dt == np.float64 else torch.int32).pin_memory()
+            return t.numpy()
+        return np.zeros(shape, dt)
+    r = dict(y=arr((nzone, ny), np.float64), t=arr(nzone, np.float64), t9=arr(nzone, np.float64),
+             rho=arr(nzone, np.float64), tdel=arr(nzone, np.float64), kstep=arr(nzone, np.int32),
+             ktot=arr((nzone, 5), np.int32), status=arr(nzone, np.int32))
+    if hist_cap > 0:
+        r.update(hist_n=np.zeros(nzone, np.int32), hist_kstep=np.zeros((nzone, hist_cap), np.int32),
+                 hist_kmon=np.zeros((nzone, hist_cap, 2), np.int32))
+        for nm in ('hist_t', 'hist_t9', 'hist_rho', 'hist_tdel', 'hist_edot', 'hist_sqnu'):
+            r[nm] = np.zeros((nzone, hist_cap))
+        r['hist_y'] = np.zeros((nzone, hist_cap, ny))
+    o = XbOut()
+    o.hist_cap = hist_cap
+    for nm, tp in XbOut._fields_:
+        if nm in r:
+            setattr(o, nm, _pi(r[nm]) if tp is c_ip else _pd(r[nm]))
+    return r, o
+
+
+class Context:
+    """Device-resident state for `nzevolve` zones (what read_jacobian_data + be_init allocate)."""
+    def __init__(self, net, controls, nzevolve=1, device=0, arith=0, **override):
+        self.net = net
+        self.ctl = controls.to_struct(arith=arith, **override)
+        self.h = C.c_void_p()
+        self.nzevolve = nzevolve
+        _chk(lib().xb_ctx_create(net.h, C.byref(self.ctl), nzevolve, device, C.byref(self.h)))
+        cfg = np.zeros(6, np.int32)
+        _chk(lib().xb_launch_config(self.h, _pi(cfg)))
+        self.launch_config = dict(grid=int(cfg[0]), threads=int(cfg[1]), smem_bytes=int(cfg[2]),
+                                  jac_in_smem=int(cfg[3]), nsm=int(cfg[4]), msize=int(cfg[5]))
+        self.msize = int(cfg[5])
+
+    def close(self):
+        if self.h:
+            lib().xb_ctx_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- module procedures (host arrays in, host arrays out) ----
+    def cross_sect(self, yt, t9t, rhot, mask=None, xext=None, aext=None, zext=None):
+        yt = _d(yt); nz = yt.shape[0]
+        t9t = _d(t9t); rhot = _d(rhot); yet = np.zeros(nz)
+        m = None if mask is None else _i(mask)
+        ex = [None if v is None else _d(v) for v in (xext, aext, zext)]
+        _chk(lib().xb_cross_sect(self.h, 1, nz, _pi(m), _pd(yt), _pd(t9t), _pd(rhot), _pd(ex[0]), _pd(ex[1]), _pd(ex[2]), _pd(yet)))
+        return yet
+
+    def csect(self, nz):
+        out = np.zeros((nz, sum(self.net.nreac)))
+        _chk(lib().xb_get_csect(self.h, 1, nz, _pd(out)))
+        return out
+
+    def yderiv(self, yt, mask=None):
+        yt = _d(yt); nz = yt.shape[0]; ydot = np.zeros_like(yt)
+        m = None if mask is None else _i(mask)
+        _chk(lib().xb_yderiv(self.h, 1, nz, _pi(m), _pd(yt), _pd(ydot)))
+        return ydot
+
+    def jacobian_build(self, nz, diag=None, mult=None, mask=None):
+        d = None if diag is None else _d(diag); mu = None if mult is None else _d(mult)
+        m = None if mask is None else _i(mask)
+        _chk(lib().xb_jacobian_build(self.h, 1, nz, _pi(m), _pd(d), _pd(mu)))
+
+    def jac(self, nz):
+        """jac[z, col, row] as it lies in memory (column-major per zone)."""
+        out = np.zeros((nz, self.msize, self.msize))
+        _chk(lib().xb_get_jac(self.h, 1, nz, _pd(out)))
+        return out
+
+    def set_jac(self, jac_colmajor):
+        j = _d(jac_colmajor)
+        _chk(lib().xb_set_jac(self.h, 1, j.shape[0], _pd(j)))
+
+    def jacobian_decomp(self, nz, mask=None):
+        info = np.zeros(nz, np.int32)
+        m = None if mask is None else _i(mask)
+        _chk(lib().xb_jacobian_decomp(self.h, 1, nz, _pi(m), _pi(info)))
+        return info
+
+    def indx(self, nz):
+        out = np.zeros((nz, self.msize), np.int32)
+        _chk(lib().xb_get_indx(self.h, 1, nz, _pi(out)))
+        return out
+
+    def jacobian_bksub(self, yrhs, mask=None):
+        yrhs = _d(yrhs); nz = yrhs.shape[0]; dy = np.zeros_like(yrhs)
+        m = None if mask is None else _i(mask)
+        _chk(lib().xb_jacobian_bksub(self.h, 1, nz, _pi(m), _pd(yrhs), None, _pd(dy), None))
+        return dy
+
+    # ---- fused evolve ----
+    def full_net(self, zones, hist_cap=0, pinned=False):
+        """xb_evolve: host buffers in, host buffers out (H2D + kernel + D2H)."""
+        res, o = _alloc_out(zones.nzone, self.net.ny, hist_cap, pinned)
+        _chk(lib().xb_evolve(self.h, C.byref(zones), C.byref(o)))
+        return res
+
+    def upload(self, zones, hist_cap=0):
+        self._nzone = zones.nzone; self._hist_cap = hist_cap
+        _chk(lib().xb_zones_upload(self.h, C.byref(zones), hist_cap))
+
+    def run_resident(self):
+        ms = C.c_float()
+        _chk(lib().xb_evolve_resident(self.h, C.byref(ms)))
+        return ms.value
+
+    def download(self, pinned=False):
+        res, o = _alloc_out(self._nzone, self.net.ny, self._hist_cap, pinned)
+        _chk(lib().xb_results_download(self.h, C.byref(o)))
+        return res
+
+    def phase_cycles(self):
+        c = np.zeros(8)
+        _chk(lib().xb_phase_cycles(self.h, _pd(c)))
+        return dict(zip(('rates', 'yderiv', 'jac', 'lu', 'bksub', 'other', 'total', 'zones'), c))
+
+    def copy_bytes(self):
+        a = C.c_int64(); b = C.c_int64()
+        _chk(lib().xb_last_copy_bytes(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+def measure_fp64_peak(device=0):
+    v = C.c_double()
+    _chk(lib().xb_measure_fp64_peak(device, C.byref(v)))
+    return v.value

@@ -1,0 +1,860 @@
+// xnet_b200 C ABI implementation: device context, kernels, evolve driver.  See include/xnet_b200.h.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/xnet_b200.h"
+#include "xb_host.h"
+#include "xb_zone.cuh"
+
+using namespace xb;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static long long g_launches = 0;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess)                                                                      \
+      return fail(XB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));             \
+  } while (0)
+
+struct xb_net { Network h; };
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr; size_t n = 0;
+  cudaError_t put(const T *src, size_t count) {
+    cudaError_t e = resize(count);
+    if (e != cudaSuccess) return e;
+    if (count == 0) return cudaSuccess;
+    return cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice);
+  }
+  cudaError_t put(const std::vector<T> &v) { return put(v.data(), v.size()); }
+  cudaError_t resize(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) n = std::max<size_t>(count, 1);
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct xb_ctx {
+  const xb_net *net = nullptr;
+  xb_ctl ctl{};
+  int device = 0, nzevolve = 0, nsm = 0;
+  DevNet dn{};
+  DevCtl dc{};
+  // network tables
+  DevBuf<double> rcT, a[4], aa, zz, mex, be, g, lng, dlng, t9i, ffnsum, ffnenu;
+  DevBuf<int> ni, iwk, irev, iffn, la, le, mu[4], nn[4][4];
+  // launch configuration
+  int threads = 256, grid = 0, jac_in_smem = 1;
+  size_t smem_bytes = 0;
+  DevScratch scr{};
+  DevBuf<double> scratch;
+  DevBuf<unsigned long long> phase;
+  DevBuf<int> counter;
+  // module-level per-zone state (HBM)
+  DevBuf<double> m_yt, m_t9t, m_rhot, m_ext, m_yet, m_csect, m_qk, m_ydot, m_jac, m_rhs, m_diag, m_mult;
+  DevBuf<int> m_indx, m_info, m_mask;
+  // evolve: zones + outputs
+  DevZones dz{};
+  DevOut dout{};
+  int nzone = 0, hist_cap = 0;
+  DevBuf<int> z_nh, z_off, z_nstart, z_zfix, z_kstep0;
+  DevBuf<double> z_th, z_t9h, z_rhoh, z_tstart, z_tstop, z_tdelstart, z_t9start, z_rhostart, z_yestart, z_ystart,
+      z_xext, z_aext, z_zext, z_rho_scale, z_rs_t, z_rs_tdel, z_rs_t9, z_rs_rho, z_rs_t9o, z_rs_y, z_rs_yo;
+  DevBuf<double> o_y, o_t, o_t9, o_rho, o_tdel, o_ht, o_ht9, o_hrho, o_htdel, o_hedot, o_hsqnu, o_hy;
+  DevBuf<int> o_kstep, o_ktot, o_status, o_hn, o_hkstep, o_hkmon;
+  int64_t h2d = 0, d2h = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory carve-up of one zone
+struct SmemLayout { size_t scal, jac, y, yo, yt, ydot, rhs, gg, indx, total; };
+static __host__ __device__ SmemLayout smem_layout(int ny, int N, bool jac_in_smem) {
+  SmemLayout L;
+  size_t o = 0;
+  L.scal = o; o += (sizeof(ZoneScalars) + 15) / 16 * 16;
+  L.jac = o; if (jac_in_smem) o += (size_t)N * N * 8;
+  L.y = o; o += (size_t)ny * 8;
+  L.yo = o; o += (size_t)ny * 8;
+  L.yt = o; o += (size_t)ny * 8;
+  L.ydot = o; o += (size_t)ny * 8;
+  L.rhs = o; o += (size_t)N * 8;
+  L.gg = o; o += (size_t)(ny + 1) * 8;
+  L.indx = o; o += (size_t)N * 4;
+  L.total = (o + 15) / 16 * 16;
+  return L;
+}
+
+static __device__ void carve(ZoneMem &zm, unsigned char *sm, const DevNet &net, const DevScratch &scr, bool jac_in_smem) {
+  SmemLayout L = smem_layout(net.ny, net.msize, jac_in_smem);
+  double *g = scr.base + (size_t)blockIdx.x * scr.stride;
+  zm.s = reinterpret_cast<ZoneScalars *>(sm + L.scal);
+  zm.jac = jac_in_smem ? reinterpret_cast<double *>(sm + L.jac) : g + scr.off_jac;
+  zm.y = reinterpret_cast<double *>(sm + L.y);
+  zm.yo = reinterpret_cast<double *>(sm + L.yo);
+  zm.yt = reinterpret_cast<double *>(sm + L.yt);
+  zm.ydot = reinterpret_cast<double *>(sm + L.ydot);
+  zm.rhs = reinterpret_cast<double *>(sm + L.rhs);
+  zm.gg = reinterpret_cast<double *>(sm + L.gg);
+  zm.indx = reinterpret_cast<int *>(sm + L.indx);
+  zm.csect = g + scr.off_csect;
+  zm.rffn = g + scr.off_rffn;
+  zm.qkffn = g + scr.off_qkffn;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent evolve kernel: each CTA pulls zones from a global counter and runs full_net on them.
+template <bool STRICT>
+__global__ void evolve_kernel(DevNet net, DevCtl ctl, DevZones zn, DevOut out, DevScratch scr, int *counter,
+                              int jac_in_smem) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  __shared__ int s_zone;
+  ZoneMem zm;
+  carve(zm, sm, net, scr, jac_in_smem != 0);
+  for (;;) {
+    if (threadIdx.x == 0) s_zone = atomicAdd(counter, 1);
+    __syncthreads();
+    const int iz = s_zone;
+    __syncthreads();
+    if (iz >= zn.nzone) break;
+    full_net_cta<STRICT>(net, ctl, zn, out, zm, iz);
+    if (threadIdx.x == 0) {
+      for (int k = 0; k < 7; ++k) atomicAdd(&scr.phase[k], (unsigned long long)zm.s->ph[k]);
+      atomicAdd(&scr.phase[PH_ZONES], 1ULL);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Module-level kernels (drop-ins for cross_sect / yderiv / jacobian_*): one CTA per zone of the
+// slice, state in HBM between calls as in the reference's OpenACC build.
+enum ModOp { OP_CSECT = 0, OP_YDERIV, OP_JBUILD, OP_DECOMP, OP_BKSUB };
+struct ModArgs {
+  int z0, nz;            // first zone (0-based) and count
+  const int *mask;       // [nzevolve] or null
+  double *yt, *t9t, *rhot, *ext, *yet, *csect, *qk, *ydot, *jac, *rhs, *diag, *mult;
+  int *indx, *info;
+};
+
+template <bool STRICT, int OP>
+__global__ void module_kernel(DevNet net, DevCtl ctl, ModArgs ma, DevScratch scr, int jac_in_smem) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  const int iz = ma.z0 + blockIdx.x;
+  if (ma.mask && ma.mask[iz] == 0) return;
+  ZoneMem zm;
+  carve(zm, sm, net, scr, jac_in_smem != 0);
+  const int tid = threadIdx.x, nt = blockDim.x, ny = net.ny, N = net.msize;
+  zm.csect = ma.csect + (size_t)iz * net.nrtot;
+  zm.qkffn = ma.qk + (size_t)iz * (net.nffn + 1);
+  ZoneScalars *s = zm.s;
+  if (OP == OP_CSECT || OP == OP_YDERIV || OP == OP_JBUILD)
+    for (int k = tid; k < ny; k += nt) zm.yt[k] = ma.yt[(size_t)iz * ny + k];
+  if (tid == 0) {
+    for (int k = 0; k < 5; ++k) s->ktot[k] = 0;
+    s->t9t = ma.t9t[iz]; s->rhot = ma.rhot[iz];
+    s->xext = ma.ext[3 * iz]; s->aext = ma.ext[3 * iz + 1]; s->zext = ma.ext[3 * iz + 2];
+    s->rdt = ma.diag[iz]; s->mult = ma.mult[iz];
+  }
+  __syncthreads();
+  if (OP == OP_CSECT) {
+    cross_sect_cta<STRICT>(net, ctl, zm);
+    if (tid == 0) ma.yet[iz] = s->yet;
+  } else if (OP == OP_YDERIV) {
+    yderiv_cta<STRICT>(net, zm);
+    for (int k = tid; k < ny; k += nt) ma.ydot[(size_t)iz * ny + k] = zm.ydot[k];
+  } else if (OP == OP_JBUILD) {
+    double *gj = ma.jac + (size_t)iz * N * N;
+    double *keep = zm.jac;
+    if (!jac_in_smem) zm.jac = gj;
+    jacobian_build_cta<STRICT>(net, zm, N);
+    if (jac_in_smem) for (int e = tid; e < N * N; e += nt) gj[e] = keep[e];
+  } else if (OP == OP_DECOMP) {
+    double *gj = ma.jac + (size_t)iz * N * N;
+    if (jac_in_smem) { for (int e = tid; e < N * N; e += nt) zm.jac[e] = gj[e]; __syncthreads(); }
+    else zm.jac = gj;
+    lu_cta<STRICT>(zm, N);
+    if (jac_in_smem) for (int e = tid; e < N * N; e += nt) gj[e] = zm.jac[e];
+    for (int k = tid; k < N; k += nt) ma.indx[(size_t)iz * N + k] = zm.indx[k] + 1;  // LAPACK 1-based ipiv
+    if (tid == 0) ma.info[iz] = s->info;
+  } else if (OP == OP_BKSUB) {
+    zm.jac = ma.jac + (size_t)iz * N * N;  // read straight from HBM/L2: each element is used once
+    for (int k = tid; k < N; k += nt) { zm.indx[k] = ma.indx[(size_t)iz * N + k] - 1; zm.rhs[k] = ma.rhs[(size_t)iz * N + k]; }
+    __syncthreads();
+    bksub_cta<STRICT>(zm, N);
+    for (int k = tid; k < N; k += nt) ma.rhs[(size_t)iz * N + k] = zm.rhs[k];
+  }
+}
+
+// FP64 FMA peak microbenchmark (bench.py roofline denominator for the LU)
+__global__ void fp64_peak_kernel(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *xb_last_error(void) { return g_err.c_str(); }
+int xb_version(void) { return 1; }
+long long xb_launch_count(int reset) { long long v = g_launches; if (reset) g_launches = 0; return v; }
+
+int xb_net_load(const char *data_dir, int iweak0, xb_net **net) {
+  if (!data_dir || !net) return fail(XB_ERR_ARG, "xb_net_load: null argument");
+  try {
+    xb_net *n = new xb_net();
+    load_network(data_dir, iweak0, n->h);
+    *net = n;
+  } catch (const std::exception &e) { return fail(XB_ERR_IO, e.what()); }
+  return XB_OK;
+}
+
+int xb_net_from_arrays(const xb_net_arrays *A, xb_net **net) {
+  if (!A || !net) return fail(XB_ERR_ARG, "xb_net_from_arrays: null argument");
+  xb_net *n = new xb_net();
+  Network &h = n->h;
+  h.ny = A->ny; h.nffn = A->nffn; h.nnnu = A->nnnu;
+  const int ny = h.ny;
+  h.aa.assign(A->aa, A->aa + ny); h.zz.assign(A->zz, A->zz + ny); h.mex.assign(A->mex, A->mex + ny);
+  h.be.assign(A->be, A->be + ny); h.mex_n = A->mex_n; h.mex_p = A->mex_p;
+  h.g.assign(A->g, A->g + (size_t)ny * kNG); h.t9i.assign(A->t9i, A->t9i + kNG);
+  h.iz.resize(ny); h.in.resize(ny); h.nn.resize(ny); h.nname.assign(ny, "     ");
+  for (int i = 0; i < ny; ++i) { h.iz[i] = (int)std::lrint(h.zz[i]); h.in[i] = (int)std::lrint(h.aa[i]) - h.iz[i]; h.nn[i] = h.in[i]; }
+  h.izmax = ny ? *std::max_element(h.iz.begin(), h.iz.end()) : 0;
+  h.la.resize((size_t)4 * ny); h.le.resize((size_t)4 * ny);
+  for (int c = 0; c < 4; ++c)
+    for (int i = 0; i < ny; ++i) { h.la[(size_t)c * ny + i] = A->la[4 * i + c]; h.le[(size_t)c * ny + i] = A->le[4 * i + c]; }
+  for (int c = 0; c < 4; ++c) {
+    const int nr = A->nreac[c], na = A->nan[c], ld = A->ni_ld[c];
+    h.nreac[c] = nr; h.nan[c] = na;
+    h.rc[c].assign(A->rc[c], A->rc[c] + (size_t)nr * 7);
+    h.ni[c].assign((size_t)nr * 6, 0);
+    for (int k = 0; k < nr; ++k) for (int s = 0; s < ld && s < 6; ++s) h.ni[c][(size_t)k * 6 + s] = A->ni[c][(size_t)k * ld + s];
+    h.iwk[c].assign(A->iwk[c], A->iwk[c] + nr); h.irev[c].assign(A->irev[c], A->irev[c] + nr);
+    h.ires[c].assign(nr, 0); h.q[c].assign(nr, 0.0);
+    h.mu[c].assign(A->mu[c], A->mu[c] + na); h.a[c].assign(A->a[c], A->a[c] + na);
+  }
+  h.iffn.assign(h.nreac[0], 0);
+  for (int k = 0; k < h.nreac[0]; ++k)
+    if (h.iwk[0][k] == 2 || h.iwk[0][k] == 3) h.iffn[k] = (int)std::lrint(h.rc[0][(size_t)k * 7]);
+  const int nf = std::max(h.nffn, 1);
+  h.ffnsum.assign((size_t)nf * kNGrid, 0.0); h.ffnenu.assign((size_t)nf * kNGrid, 0.0);
+  h.ffn_ec.assign((size_t)nf * kNGrid, 0.0); h.ffn_beta.assign((size_t)nf * kNGrid, 0.0);
+  h.ffn_qval.assign(nf, 0.0); h.has_logft.assign(nf, 0);
+  for (int k = 0; k < h.nffn; ++k)
+    for (int j = 0; j < kNGrid; ++j) {  // Fortran (nffn,143): rate index fastest
+      h.ffnsum[(size_t)k * kNGrid + j] = A->ffnsum[(size_t)j * h.nffn + k];
+      h.ffnenu[(size_t)k * kNGrid + j] = A->ffnenu[(size_t)j * h.nffn + k];
+    }
+  h.chap_la.assign(kNChap, 0); h.chap_le.assign(kNChap, 0);
+  *net = n;
+  return XB_OK;
+}
+
+void xb_net_free(xb_net *net) { delete net; }
+
+int xb_net_int(const xb_net *net, const char *what, int32_t *value) {
+  if (!net || !what || !value) return fail(XB_ERR_ARG, "xb_net_int: null argument");
+  const Network &h = net->h; std::string w(what);
+  if (w == "ny") *value = h.ny; else if (w == "nffn") *value = h.nffn; else if (w == "nnnu") *value = h.nnnu;
+  else if (w == "izmax") *value = h.izmax;
+  else if (w.size() == 6 && w.compare(0, 5, "nreac") == 0 && w[5] >= '1' && w[5] <= '4') *value = h.nreac[w[5] - '1'];
+  else if (w.size() == 4 && w.compare(0, 3, "nan") == 0 && w[3] >= '1' && w[3] <= '4') *value = h.nan[w[3] - '1'];
+  else return fail(XB_ERR_ARG, "xb_net_int: unknown key " + w);
+  return XB_OK;
+}
+
+}  // extern "C"
+template <class T>
+static int copy_out(const std::vector<T> &v, T *out, int64_t cap, int64_t *n) {
+  if (n) *n = (int64_t)v.size();
+  if (out) {
+    if (cap < (int64_t)v.size()) return fail(XB_ERR_ARG, "output buffer too small");
+    std::copy(v.begin(), v.end(), out);
+  }
+  return XB_OK;
+}
+
+extern "C" {
+int xb_net_itable(const xb_net *net, const char *what, int32_t *out, int64_t cap, int64_t *n) {
+  if (!net || !what) return fail(XB_ERR_ARG, "xb_net_itable: null argument");
+  const Network &h = net->h; std::string w(what);
+  if (w == "la") return copy_out(h.la, out, cap, n);
+  if (w == "le") return copy_out(h.le, out, cap, n);
+  if (w == "iffn") return copy_out(h.iffn, out, cap, n);
+  if (w == "chap_la") return copy_out(h.chap_la, out, cap, n);
+  if (w == "chap_le") return copy_out(h.chap_le, out, cap, n);
+  if (w == "has_logft") return copy_out(h.has_logft, out, cap, n);
+  if (w.size() >= 3) {
+    const int c = w.back() - '1';
+    std::string stem = w.substr(0, w.size() - 1);
+    if (w.size() == 3 && w[0] == 'n' && w[2] == 'i' && w[1] >= '1' && w[1] <= '4') return copy_out(h.ni[w[1] - '1'], out, cap, n);
+    if (c >= 0 && c < 4) {
+      if (stem == "mu") return copy_out(h.mu[c], out, cap, n);
+      if (stem == "iwk") return copy_out(h.iwk[c], out, cap, n);
+      if (stem == "irev") return copy_out(h.irev[c], out, cap, n);
+      if (stem == "ires") return copy_out(h.ires[c], out, cap, n);
+    }
+  }
+  return fail(XB_ERR_ARG, "xb_net_itable: unknown key " + w);
+}
+
+int xb_net_dtable(const xb_net *net, const char *what, double *out, int64_t cap, int64_t *n) {
+  if (!net || !what) return fail(XB_ERR_ARG, "xb_net_dtable: null argument");
+  const Network &h = net->h; std::string w(what);
+  if (w == "aa") return copy_out(h.aa, out, cap, n);
+  if (w == "zz") return copy_out(h.zz, out, cap, n);
+  if (w == "mex") return copy_out(h.mex, out, cap, n);
+  if (w == "be") return copy_out(h.be, out, cap, n);
+  if (w == "g") return copy_out(h.g, out, cap, n);
+  if (w == "t9i") return copy_out(h.t9i, out, cap, n);
+  if (w == "ffnsum") return copy_out(h.ffnsum, out, cap, n);
+  if (w == "ffnenu") return copy_out(h.ffnenu, out, cap, n);
+  if (w == "ffn_ec") return copy_out(h.ffn_ec, out, cap, n);
+  if (w == "ffn_beta") return copy_out(h.ffn_beta, out, cap, n);
+  if (w == "ffn_qval") return copy_out(h.ffn_qval, out, cap, n);
+  if (w == "mex_np") { std::vector<double> v{h.mex_n, h.mex_p}; return copy_out(v, out, cap, n); }
+  if (w.size() >= 2) {
+    const int c = w.back() - '1';
+    std::string stem = w.substr(0, w.size() - 1);
+    if (c >= 0 && c < 4) {
+      if (stem == "a") return copy_out(h.a[c], out, cap, n);
+      if (stem == "rc") return copy_out(h.rc[c], out, cap, n);
+      if (stem == "q") return copy_out(h.q[c], out, cap, n);
+    }
+  }
+  return fail(XB_ERR_ARG, "xb_net_dtable: unknown key " + w);
+}
+
+int xb_read_thermo(const char *path, int32_t cap, int32_t *nh, double *th, double *t9h, double *rhoh, double *yeh,
+                   double *hdr) {
+  if (!path || !nh) return fail(XB_ERR_ARG, "xb_read_thermo: null argument");
+  try {
+    Thermo t; read_thermo_file(path, t);
+    *nh = (int32_t)t.th.size();
+    if (hdr) { hdr[0] = t.tstart; hdr[1] = t.tstop; hdr[2] = t.tdelstart; }
+    if (th) {
+      if (cap < *nh) return fail(XB_ERR_ARG, "xb_read_thermo: buffer too small");
+      std::copy(t.th.begin(), t.th.end(), th); std::copy(t.t9h.begin(), t.t9h.end(), t9h);
+      std::copy(t.rhoh.begin(), t.rhoh.end(), rhoh); if (yeh) std::copy(t.yeh.begin(), t.yeh.end(), yeh);
+    }
+  } catch (const std::exception &e) { return fail(XB_ERR_IO, e.what()); }
+  return XB_OK;
+}
+
+int xb_read_inab(const xb_net *net, const char *path, double *y, double *scal) {
+  if (!net || !path || !y || !scal) return fail(XB_ERR_ARG, "xb_read_inab: null argument");
+  try {
+    InAb ab; read_inab_file(net->h, path, ab);
+    std::copy(ab.y.begin(), ab.y.end(), y);
+    scal[0] = ab.yein; scal[1] = ab.xext; scal[2] = ab.aext; scal[3] = ab.zext;
+  } catch (const std::exception &e) { return fail(XB_ERR_IO, e.what()); }
+  return XB_OK;
+}
+
+// Start-of-run conditions of one fixture (net.F90:249-268, model_input_ascii.F90:166-198):
+// nstart/t9start/rhostart from the trajectory at tstart, Ye from the abundance file or, if absent,
+// from the composition moments.  out4 = t9start, rhostart, yestart, (unused)
+int xb_zone_start(const xb_net *net, int32_t nh, const double *th, const double *t9h, const double *rhoh,
+                  const double *yeh, double tstart, const double *y, const double *scal, int32_t *nstart, double *out4) {
+  if (!net || !th || !t9h || !rhoh || !y || !scal || !nstart || !out4 || nh < 1) return fail(XB_ERR_ARG, "xb_zone_start: bad argument");
+  const Network &h = net->h;
+  int n = 1;
+  double t9s, rhos;
+  if (nh == 1) { t9s = t9h[0]; rhos = rhoh[0]; n = 1; }
+  else {
+    for (n = 1; n <= nh; ++n) if (tstart <= th[n - 1]) break;
+    if (n > 1 && n <= nh) {
+      const double rdt = 1.0 / (th[n - 1] - th[n - 2]), dt = tstart - th[n - 2];
+      t9s = dt * rdt * (t9h[n - 1] - t9h[n - 2]) + t9h[n - 2];
+      rhos = dt * rdt * (rhoh[n - 1] - rhoh[n - 2]) + rhoh[n - 2];
+    } else if (n == 1) { t9s = t9h[0]; rhos = rhoh[0]; }
+    else { t9s = t9h[nh - 1]; rhos = rhoh[nh - 1]; }
+  }
+  (void)yeh;
+  double yein = scal[0];
+  if (yein <= 0.0 || yein >= 1.0) {  // y_moment (xnet_abundances.F90:137-166): only Ye is needed here
+    const double xext = scal[1], aext = scal[2], zext = scal[3];
+    const double yext = xext / aext;
+    double atot = 0.0, ztot = 0.0;
+    for (int k = 0; k < h.ny; ++k) { atot = atot + y[k] * h.aa[k]; ztot = ztot + y[k] * h.zz[k]; }
+    atot = atot + xext; ztot = ztot + yext * zext;
+    yein = ztot / atot;
+  }
+  *nstart = n; out4[0] = t9s; out4[1] = rhos; out4[2] = yein; out4[3] = 0.0;
+  return XB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int upload_network(xb_ctx *c) {
+  const Network &h = c->net->h;
+  DevNet &d = c->dn;
+  const int ny = h.ny;
+  d.ny = ny; d.nffn = h.nffn; d.msize = ny + (c->ctl.iheat > 0 ? 1 : 0);
+  d.mex_n = h.mex_n; d.mex_p = h.mex_p;
+  int off = 0;
+  for (int k = 0; k < 4; ++k) { d.nr[k] = h.nreac[k]; d.roff[k] = off; off += h.nreac[k]; d.nan[k] = h.nan[k]; }
+  d.nrtot = off;
+  const int nrt = std::max(off, 1);
+  std::vector<double> rcT((size_t)7 * nrt, 0.0);
+  std::vector<int> ni((size_t)nrt * 6, 0), iwk(nrt, 0), irev(nrt, 0), iffn(nrt, 0);
+  for (int cI = 0; cI < 4; ++cI)
+    for (int k = 0; k < h.nreac[cI]; ++k) {
+      const int gk = d.roff[cI] + k;
+      for (int j = 0; j < 7; ++j) rcT[(size_t)j * d.nrtot + gk] = h.rc[cI][(size_t)k * 7 + j];
+      for (int s = 0; s < 6; ++s) ni[(size_t)gk * 6 + s] = h.ni[cI][(size_t)k * 6 + s];
+      iwk[gk] = h.iwk[cI][k]; irev[gk] = h.irev[cI][k];
+      if (cI == 0) iffn[gk] = h.iffn[k];
+    }
+  CUDA_TRY(c->rcT.put(rcT)); CUDA_TRY(c->ni.put(ni)); CUDA_TRY(c->iwk.put(iwk)); CUDA_TRY(c->irev.put(irev));
+  CUDA_TRY(c->iffn.put(iffn));
+  d.rcT = c->rcT.p; d.ni = c->ni.p; d.iwk = c->iwk.p; d.irev = c->irev.p; d.iffn = c->iffn.p;
+  CUDA_TRY(c->la.put(h.la)); CUDA_TRY(c->le.put(h.le));
+  d.la = c->la.p; d.le = c->le.p;
+  for (int cI = 0; cI < 4; ++cI) {
+    const int na = h.nan[cI];
+    std::vector<int> mu(std::max(na, 1), 0);
+    for (int j = 0; j < na; ++j) mu[j] = d.roff[cI] + h.mu[cI][j] - 1;
+    CUDA_TRY(c->mu[cI].put(mu));
+    std::vector<double> av(h.a[cI]); if (av.empty()) av.push_back(0.0);
+    CUDA_TRY(c->a[cI].put(av));
+    d.mu[cI] = c->mu[cI].p; d.a[cI] = c->a[cI].p;
+    for (int r = 0; r < 4; ++r) {
+      std::vector<int> nn(std::max(na, 1), 0);
+      if (r <= cI)
+        for (int j = 0; j < na; ++j) nn[j] = h.ni[cI][(size_t)(h.mu[cI][j] - 1) * 6 + r] - 1;  // xnet_data.F90:901-924
+      CUDA_TRY(c->nn[cI][r].put(nn));
+      d.nn[cI][r] = c->nn[cI][r].p;
+    }
+  }
+  CUDA_TRY(c->aa.put(h.aa)); CUDA_TRY(c->zz.put(h.zz)); CUDA_TRY(c->mex.put(h.mex)); CUDA_TRY(c->be.put(h.be));
+  CUDA_TRY(c->g.put(h.g)); CUDA_TRY(c->t9i.put(h.t9i));
+  std::vector<double> lng(h.g.size()), dlng(h.g.size(), 0.0);
+  for (size_t i = 0; i < h.g.size(); ++i) lng[i] = std::log(h.g[i]);
+  for (int k = 0; k < ny; ++k)
+    for (int i = 1; i < kNG; ++i) dlng[(size_t)k * kNG + i] = std::log(h.g[(size_t)k * kNG + i] / h.g[(size_t)k * kNG + i - 1]);
+  CUDA_TRY(c->lng.put(lng)); CUDA_TRY(c->dlng.put(dlng));
+  CUDA_TRY(c->ffnsum.put(h.ffnsum)); CUDA_TRY(c->ffnenu.put(h.ffnenu));
+  d.aa = c->aa.p; d.zz = c->zz.p; d.mex = c->mex.p; d.be = c->be.p; d.g = c->g.p; d.lng = c->lng.p; d.dlng = c->dlng.p;
+  d.t9i = c->t9i.p; d.ffnsum = c->ffnsum.p; d.ffnenu = c->ffnenu.p;
+  return XB_OK;
+}
+
+}  // extern "C"
+template <bool STRICT>
+static const void *evolve_fn() { return (const void *)evolve_kernel<STRICT>; }
+
+extern "C" {
+static int configure_launch(xb_ctx *c) {
+  const int ny = c->dn.ny, N = c->dn.msize;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, c->device));
+  c->nsm = prop.multiProcessorCount;
+  const size_t max_smem = prop.sharedMemPerBlockOptin;
+  SmemLayout L = smem_layout(ny, N, true);
+  c->jac_in_smem = (L.total + 64 <= max_smem) ? 1 : 0;
+  if (!c->jac_in_smem) L = smem_layout(ny, N, false);
+  c->smem_bytes = L.total;
+  c->threads = N <= 24 ? 64 : (N <= 64 ? 128 : 256);
+  const void *fn = c->ctl.arith ? evolve_fn<true>() : evolve_fn<false>();
+  CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+  int per_sm = 0;
+  if (c->ctl.arith) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, evolve_kernel<true>, c->threads, c->smem_bytes));
+  else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, evolve_kernel<false>, c->threads, c->smem_bytes));
+  if (per_sm < 1) return fail(XB_ERR_CUDA, "evolve kernel does not fit on an SM");
+  per_sm = std::min(per_sm, 8);
+  c->grid = c->nsm * per_sm;
+  // per-CTA scratch (also sized for the module kernels, which index by blockIdx.x < nzevolve)
+  DevScratch &s = c->scr;
+  size_t o = 0;
+  s.off_csect = o; o += c->dn.nrtot;
+  s.off_rffn = o; o += std::max(c->dn.nffn, 1);
+  s.off_qkffn = o; o += c->dn.nffn + 1;
+  o = (o + 15) / 16 * 16;
+  s.off_jac = o; if (!c->jac_in_smem) o += (size_t)N * N;
+  s.stride = (o + 15) / 16 * 16;
+  const size_t nblocks = std::max<size_t>(c->grid, c->nzevolve);
+  CUDA_TRY(c->scratch.resize(nblocks * s.stride));
+  CUDA_TRY(cudaMemset(c->scratch.p, 0, nblocks * s.stride * sizeof(double)));
+  CUDA_TRY(c->phase.resize(8));
+  CUDA_TRY(cudaMemset(c->phase.p, 0, 8 * sizeof(unsigned long long)));
+  CUDA_TRY(c->counter.resize(1));
+  s.base = c->scratch.p; s.phase = c->phase.p;
+  return XB_OK;
+}
+
+int xb_ctx_create(const xb_net *net, const xb_ctl *ctl, int32_t nzevolve, int32_t device, xb_ctx **ctx) {
+  if (!net || !ctl || !ctx || nzevolve < 1) return fail(XB_ERR_ARG, "xb_ctx_create: bad argument");
+  if (ctl->iscrn > 0 || ctl->iheat > 0)
+    return fail(XB_ERR_UNSUPPORTED, "screening / self-heating are not built yet (iscrn, iheat must be 0)");
+  if (ctl->isolv != 1) return fail(XB_ERR_UNSUPPORTED, "only isolv=1 (backward Euler) is built");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(XB_ERR_CUDA, "no such CUDA device");
+  CUDA_TRY(cudaSetDevice(device));
+  xb_ctx *c = new xb_ctx();
+  c->net = net; c->ctl = *ctl; c->device = device; c->nzevolve = nzevolve;
+  DevCtl &dc = c->dc;
+  dc.iweak0 = ctl->iweak0; dc.iscrn = ctl->iscrn; dc.iheat = ctl->iheat; dc.isolv = ctl->isolv; dc.kstmx = ctl->kstmx;
+  dc.kitmx = ctl->kitmx; dc.ijac = ctl->ijac; dc.iconvc = ctl->iconvc; dc.changemx = ctl->changemx;
+  dc.changemxt = ctl->changemxt; dc.yacc = ctl->yacc; dc.tolm = ctl->tolm; dc.tolc = ctl->tolc; dc.tolt9 = ctl->tolt9;
+  dc.ymin = ctl->ymin; dc.tdel_maxmult = ctl->tdel_maxmult;
+  int rc = upload_network(c);
+  if (rc == XB_OK) rc = configure_launch(c);
+  if (rc != XB_OK) { delete c; return rc; }
+  cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+  *ctx = c;
+  return XB_OK;
+}
+
+void xb_ctx_destroy(xb_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  // DevBuf members are plain pointers: release explicitly
+  c->rcT.release(); c->aa.release(); c->zz.release(); c->mex.release(); c->be.release(); c->g.release(); c->lng.release();
+  c->dlng.release(); c->t9i.release(); c->ffnsum.release(); c->ffnenu.release(); c->ni.release(); c->iwk.release();
+  c->irev.release(); c->iffn.release(); c->la.release(); c->le.release();
+  for (int k = 0; k < 4; ++k) { c->a[k].release(); c->mu[k].release(); for (int r = 0; r < 4; ++r) c->nn[k][r].release(); }
+  c->scratch.release(); c->phase.release(); c->counter.release();
+  DevBuf<double> *db[] = {&c->m_yt, &c->m_t9t, &c->m_rhot, &c->m_ext, &c->m_yet, &c->m_csect, &c->m_qk, &c->m_ydot, &c->m_jac,
+                          &c->m_rhs, &c->m_diag, &c->m_mult, &c->z_th, &c->z_t9h, &c->z_rhoh, &c->z_tstart, &c->z_tstop,
+                          &c->z_tdelstart, &c->z_t9start, &c->z_rhostart, &c->z_yestart, &c->z_ystart, &c->z_xext, &c->z_aext,
+                          &c->z_zext, &c->z_rho_scale, &c->z_rs_t, &c->z_rs_tdel, &c->z_rs_t9, &c->z_rs_rho, &c->z_rs_t9o,
+                          &c->z_rs_y, &c->z_rs_yo, &c->o_y, &c->o_t, &c->o_t9, &c->o_rho, &c->o_tdel, &c->o_ht, &c->o_ht9,
+                          &c->o_hrho, &c->o_htdel, &c->o_hedot, &c->o_hsqnu, &c->o_hy};
+  for (auto *b : db) b->release();
+  DevBuf<int> *ib[] = {&c->m_indx, &c->m_info, &c->m_mask, &c->z_nh, &c->z_off, &c->z_nstart, &c->z_zfix, &c->z_kstep0,
+                       &c->o_kstep, &c->o_ktot, &c->o_status, &c->o_hn, &c->o_hkstep, &c->o_hkmon};
+  for (auto *b : ib) b->release();
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  delete c;
+}
+
+// ---- module-level drop-ins ------------------------------------------------------------------------
+static int module_state(xb_ctx *c) {
+  const int nz = c->nzevolve, ny = c->dn.ny, N = c->dn.msize;
+  if (c->m_yt.p) return XB_OK;
+  CUDA_TRY(c->m_yt.resize((size_t)nz * ny)); CUDA_TRY(c->m_t9t.resize(nz)); CUDA_TRY(c->m_rhot.resize(nz));
+  CUDA_TRY(c->m_ext.resize((size_t)3 * nz)); CUDA_TRY(c->m_yet.resize(nz));
+  CUDA_TRY(c->m_csect.resize((size_t)nz * std::max(c->dn.nrtot, 1))); CUDA_TRY(c->m_qk.resize((size_t)nz * (c->dn.nffn + 1)));
+  CUDA_TRY(c->m_ydot.resize((size_t)nz * ny)); CUDA_TRY(c->m_jac.resize((size_t)nz * N * N));
+  CUDA_TRY(c->m_rhs.resize((size_t)nz * N)); CUDA_TRY(c->m_diag.resize(nz)); CUDA_TRY(c->m_mult.resize(nz));
+  CUDA_TRY(c->m_indx.resize((size_t)nz * N)); CUDA_TRY(c->m_info.resize(nz)); CUDA_TRY(c->m_mask.resize(nz));
+  CUDA_TRY(cudaMemset(c->m_yt.p, 0, (size_t)nz * ny * 8)); CUDA_TRY(cudaMemset(c->m_csect.p, 0, (size_t)nz * std::max(c->dn.nrtot, 1) * 8));
+  CUDA_TRY(cudaMemset(c->m_qk.p, 0, (size_t)nz * (c->dn.nffn + 1) * 8));
+  CUDA_TRY(cudaMemset(c->m_t9t.p, 0, nz * 8)); CUDA_TRY(cudaMemset(c->m_rhot.p, 0, nz * 8));
+  CUDA_TRY(cudaMemset(c->m_diag.p, 0, nz * 8)); CUDA_TRY(cudaMemset(c->m_mult.p, 0, nz * 8));
+  std::vector<double> ext((size_t)3 * nz, 0.0);
+  for (int i = 0; i < nz; ++i) ext[3 * i + 1] = 1.0;
+  CUDA_TRY(c->m_ext.put(ext));
+  return XB_OK;
+}
+
+static int check_slice(xb_ctx *c, int zlo, int zhi) {
+  if (!c) return fail(XB_ERR_ARG, "null context");
+  if (zlo < 1 || zhi < zlo || zhi > c->nzevolve) return fail(XB_ERR_ARG, "zone slice outside 1..nzevolve");
+  CUDA_TRY(cudaSetDevice(c->device));
+  return module_state(c);
+}
+
+}  // extern "C"
+template <int OP>
+static int launch_module(xb_ctx *c, int zlo, int zhi, const int32_t *mask) {
+  const int nz = zhi - zlo + 1;
+  ModArgs ma{};
+  ma.z0 = zlo - 1; ma.nz = nz; ma.mask = nullptr;
+  if (mask) {
+    CUDA_TRY(cudaMemcpy(c->m_mask.p + (zlo - 1), mask, nz * sizeof(int), cudaMemcpyHostToDevice));
+    ma.mask = c->m_mask.p;
+  }
+  ma.yt = c->m_yt.p; ma.t9t = c->m_t9t.p; ma.rhot = c->m_rhot.p; ma.ext = c->m_ext.p; ma.yet = c->m_yet.p;
+  ma.csect = c->m_csect.p; ma.qk = c->m_qk.p; ma.ydot = c->m_ydot.p; ma.jac = c->m_jac.p; ma.rhs = c->m_rhs.p;
+  ma.diag = c->m_diag.p; ma.mult = c->m_mult.p; ma.indx = c->m_indx.p; ma.info = c->m_info.p;
+  if (c->ctl.arith) {
+    CUDA_TRY(cudaFuncSetAttribute(module_kernel<true, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    module_kernel<true, OP><<<nz, c->threads, c->smem_bytes>>>(c->dn, c->dc, ma, c->scr, c->jac_in_smem);
+  } else {
+    CUDA_TRY(cudaFuncSetAttribute(module_kernel<false, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    module_kernel<false, OP><<<nz, c->threads, c->smem_bytes>>>(c->dn, c->dc, ma, c->scr, c->jac_in_smem);
+  }
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return XB_OK;
+}
+
+extern "C" {
+int xb_cross_sect(xb_ctx *c, int32_t zlo, int32_t zhi, const int32_t *mask, const double *yt, const double *t9t,
+                  const double *rhot, const double *xext, const double *aext, const double *zext, double *yet) {
+  int rc = check_slice(c, zlo, zhi); if (rc) return rc;
+  if (!yt || !t9t || !rhot) return fail(XB_ERR_ARG, "xb_cross_sect: null input");
+  const int nz = zhi - zlo + 1, ny = c->dn.ny, z0 = zlo - 1;
+  CUDA_TRY(cudaMemcpy(c->m_yt.p + (size_t)z0 * ny, yt, (size_t)nz * ny * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->m_t9t.p + z0, t9t, nz * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->m_rhot.p + z0, rhot, nz * 8, cudaMemcpyHostToDevice));
+  if (xext && aext && zext) {
+    std::vector<double> ext((size_t)3 * nz);
+    for (int i = 0; i < nz; ++i) { ext[3 * i] = xext[i]; ext[3 * i + 1] = aext[i]; ext[3 * i + 2] = zext[i]; }
+    CUDA_TRY(cudaMemcpy(c->m_ext.p + (size_t)3 * z0, ext.data(), ext.size() * 8, cudaMemcpyHostToDevice));
+  }
+  rc = launch_module<OP_CSECT>(c, zlo, zhi, mask); if (rc) return rc;
+  if (yet) CUDA_TRY(cudaMemcpy(yet, c->m_yet.p + z0, nz * 8, cudaMemcpyDeviceToHost));
+  else CUDA_TRY(cudaDeviceSynchronize());
+  return XB_OK;
+}
+
+int xb_get_csect(xb_ctx *c, int32_t zlo, int32_t zhi, double *csect) {
+  int rc = check_slice(c, zlo, zhi); if (rc) return rc;
+  CUDA_TRY(cudaMemcpy(csect, c->m_csect.p + (size_t)(zlo - 1) * c->dn.nrtot, (size_t)(zhi - zlo + 1) * c->dn.nrtot * 8,
+                      cudaMemcpyDeviceToHost));
+  return XB_OK;
+}
+
+int xb_yderiv(xb_ctx *c, int32_t zlo, int32_t zhi, const int32_t *mask, const double *yt, double *ydot) {
+  int rc = check_slice(c, zlo, zhi); if (rc) return rc;
+  const int nz = zhi - zlo + 1, ny = c->dn.ny, z0 = zlo - 1;
+  if (yt) CUDA_TRY(cudaMemcpy(c->m_yt.p + (size_t)z0 * ny, yt, (size_t)nz * ny * 8, cudaMemcpyHostToDevice));
+  rc = launch_module<OP_YDERIV>(c, zlo, zhi, mask); if (rc) return rc;
+  if (ydot) CUDA_TRY(cudaMemcpy(ydot, c->m_ydot.p + (size_t)z0 * ny, (size_t)nz * ny * 8, cudaMemcpyDeviceToHost));
+  else CUDA_TRY(cudaDeviceSynchronize());
+  return XB_OK;
+}
+
+int xb_jacobian_build(xb_ctx *c, int32_t zlo, int32_t zhi, const int32_t *mask, const double *diag, const double *mult) {
+  int rc = check_slice(c, zlo, zhi); if (rc) return rc;
+  const int nz = zhi - zlo + 1, z0 = zlo - 1;
+  std::vector<double> one(nz, 1.0), zero(nz, 0.0);
+  CUDA_TRY(cudaMemcpy(c->m_diag.p + z0, diag ? diag : zero.data(), nz * 8, cudaMemcpyHostToDevice));  // diag0 = 0
+  CUDA_TRY(cudaMemcpy(c->m_mult.p + z0, mult ? mult : one.data(), nz * 8, cudaMemcpyHostToDevice));   // mult1 = 1
+  rc = launch_module<OP_JBUILD>(c, zlo, zhi, mask); if (rc) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());
+  return XB_OK;
+}
+
+int xb_get_jac(xb_ctx *c, int32_t zlo, int32_t zhi, double *jac) {
+  int rc = check_slice(c, zlo, zhi); if (rc) return rc;
+  const size_t nn = (size_t)c->dn.msize * c->dn.msize;
+  CUDA_TRY(cudaMemcpy(jac, c->m_jac.p + (size_t)(zlo - 1) * nn, (size_t)(zhi - zlo + 1) * nn * 8, cudaMemcpyDeviceToHost));
+  return XB_OK;
+}
+int xb_set_jac(xb_ctx *c, int32_t zlo, int32_t zhi, const double *jac) {
+  int rc = check_slice(c, zlo, zhi); if (rc) return rc;
+  const size_t nn = (size_t)c->dn.msize * c->dn.msize;
+  CUDA_TRY(cudaMemcpy(c->m_jac.p + (size_t)(zlo - 1) * nn, jac, (size_t)(zhi - zlo + 1) * nn * 8, cudaMemcpyHostToDevice));
+  return XB_OK;
+}
+
+int xb_jacobian_decomp(xb_ctx *c, int32_t zlo, int32_t zhi, const int32_t *mask, int32_t *info) {
+  int rc = check_slice(c, zlo, zhi); if (rc) return rc;
+  rc = launch_module<OP_DECOMP>(c, zlo, zhi, mask); if (rc) return rc;
+  if (info) CUDA_TRY(cudaMemcpy(info, c->m_info.p + (zlo - 1), (zhi - zlo + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+  else CUDA_TRY(cudaDeviceSynchronize());
+  return XB_OK;
+}
+
+int xb_get_indx(xb_ctx *c, int32_t zlo, int32_t zhi, int32_t *indx) {
+  int rc = check_slice(c, zlo, zhi); if (rc) return rc;
+  const int N = c->dn.msize;
+  CUDA_TRY(cudaMemcpy(indx, c->m_indx.p + (size_t)(zlo - 1) * N, (size_t)(zhi - zlo + 1) * N * sizeof(int), cudaMemcpyDeviceToHost));
+  return XB_OK;
+}
+
+int xb_jacobian_bksub(xb_ctx *c, int32_t zlo, int32_t zhi, const int32_t *mask, const double *yrhs, const double *t9rhs,
+                      double *dy, double *dt9) {
+  int rc = check_slice(c, zlo, zhi); if (rc) return rc;
+  if (!yrhs || !dy) return fail(XB_ERR_ARG, "xb_jacobian_bksub: null argument");
+  (void)t9rhs; (void)dt9;  // msize == ny in this build (iheat = 0)
+  const int nz = zhi - zlo + 1, N = c->dn.msize, z0 = zlo - 1;
+  CUDA_TRY(cudaMemcpy(c->m_rhs.p + (size_t)z0 * N, yrhs, (size_t)nz * N * 8, cudaMemcpyHostToDevice));
+  rc = launch_module<OP_BKSUB>(c, zlo, zhi, mask); if (rc) return rc;
+  if (!mask) {
+    CUDA_TRY(cudaMemcpy(dy, c->m_rhs.p + (size_t)z0 * N, (size_t)nz * N * 8, cudaMemcpyDeviceToHost));
+  } else {  // masked-out zones keep the caller's dy (xnet_jacobian_dense.F90:700-708)
+    std::vector<double> tmp((size_t)nz * N);
+    CUDA_TRY(cudaMemcpy(tmp.data(), c->m_rhs.p + (size_t)z0 * N, tmp.size() * 8, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < nz; ++i)
+      if (mask[i]) std::copy(tmp.begin() + (size_t)i * N, tmp.begin() + (size_t)(i + 1) * N, dy + (size_t)i * N);
+  }
+  return XB_OK;
+}
+
+int xb_jacobian_solve(xb_ctx *c, int32_t zlo, int32_t zhi, const int32_t *mask, const double *yrhs, const double *t9rhs,
+                      double *dy, double *dt9, int32_t *info) {
+  int rc = xb_jacobian_decomp(c, zlo, zhi, mask, info);
+  if (rc) return rc;
+  return xb_jacobian_bksub(c, zlo, zhi, mask, yrhs, t9rhs, dy, dt9);
+}
+
+// ---- evolve ---------------------------------------------------------------------------------------
+#define PUT(buf, src, count)                                                            \
+  do {                                                                                  \
+    CUDA_TRY((buf).put((src), (size_t)(count)));                                        \
+    c->h2d += (int64_t)((size_t)(count) * sizeof(*(src)));                              \
+  } while (0)
+
+int xb_zones_upload(xb_ctx *c, const xb_zones *z, int32_t hist_cap) {
+  if (!c || !z) return fail(XB_ERR_ARG, "xb_zones_upload: null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const int ny = c->dn.ny, K = z->nfix, nz = z->nzone;
+  if (K < 1 || nz < 1) return fail(XB_ERR_ARG, "xb_zones_upload: empty zone set");
+  size_t ntraj = 0;
+  for (int k = 0; k < K; ++k) ntraj = std::max<size_t>(ntraj, (size_t)z->off[k] + z->nh[k]);
+  c->h2d = 0;
+  PUT(c->z_nh, z->nh, K); PUT(c->z_off, z->off, K); PUT(c->z_nstart, z->nstart, K); PUT(c->z_zfix, z->zfix, nz);
+  PUT(c->z_th, z->th, ntraj); PUT(c->z_t9h, z->t9h, ntraj); PUT(c->z_rhoh, z->rhoh, ntraj);
+  PUT(c->z_tstart, z->tstart, K); PUT(c->z_tstop, z->tstop, K); PUT(c->z_tdelstart, z->tdelstart, K);
+  PUT(c->z_t9start, z->t9start, K); PUT(c->z_rhostart, z->rhostart, K); PUT(c->z_yestart, z->yestart, K);
+  PUT(c->z_ystart, z->ystart, (size_t)K * ny); PUT(c->z_xext, z->xext, K); PUT(c->z_aext, z->aext, K); PUT(c->z_zext, z->zext, K);
+  DevZones &d = c->dz;
+  d = DevZones{};
+  d.nfix = K; d.nzone = nz; d.nh = c->z_nh.p; d.off = c->z_off.p; d.nstart = c->z_nstart.p; d.zfix = c->z_zfix.p;
+  d.th = c->z_th.p; d.t9h = c->z_t9h.p; d.rhoh = c->z_rhoh.p; d.tstart = c->z_tstart.p; d.tstop = c->z_tstop.p;
+  d.tdelstart = c->z_tdelstart.p; d.t9start = c->z_t9start.p; d.rhostart = c->z_rhostart.p; d.yestart = c->z_yestart.p;
+  d.ystart = c->z_ystart.p; d.xext = c->z_xext.p; d.aext = c->z_aext.p; d.zext = c->z_zext.p;
+  if (z->rho_scale) { PUT(c->z_rho_scale, z->rho_scale, nz); d.rho_scale = c->z_rho_scale.p; }
+  if (z->rs_t) {
+    if (!z->rs_tdel || !z->rs_t9 || !z->rs_rho || !z->rs_t9o || !z->rs_y || !z->rs_yo || !z->rs_kstep0)
+      return fail(XB_ERR_ARG, "xb_zones_upload: incomplete restart state");
+    PUT(c->z_rs_t, z->rs_t, nz); PUT(c->z_rs_tdel, z->rs_tdel, nz); PUT(c->z_rs_t9, z->rs_t9, nz);
+    PUT(c->z_rs_rho, z->rs_rho, nz); PUT(c->z_rs_t9o, z->rs_t9o, nz); PUT(c->z_rs_y, z->rs_y, (size_t)nz * ny);
+    PUT(c->z_rs_yo, z->rs_yo, (size_t)nz * ny); PUT(c->z_kstep0, z->rs_kstep0, nz);
+    d.rs_t = c->z_rs_t.p; d.rs_tdel = c->z_rs_tdel.p; d.rs_t9 = c->z_rs_t9.p; d.rs_rho = c->z_rs_rho.p;
+    d.rs_t9o = c->z_rs_t9o.p; d.rs_y = c->z_rs_y.p; d.rs_yo = c->z_rs_yo.p; d.rs_kstep0 = c->z_kstep0.p;
+  }
+  c->nzone = nz; c->hist_cap = hist_cap;
+  CUDA_TRY(c->o_y.resize((size_t)nz * ny)); CUDA_TRY(c->o_t.resize(nz)); CUDA_TRY(c->o_t9.resize(nz));
+  CUDA_TRY(c->o_rho.resize(nz)); CUDA_TRY(c->o_tdel.resize(nz)); CUDA_TRY(c->o_kstep.resize(nz));
+  CUDA_TRY(c->o_ktot.resize((size_t)nz * 5)); CUDA_TRY(c->o_status.resize(nz));
+  DevOut &o = c->dout;
+  o = DevOut{};
+  o.y = c->o_y.p; o.t = c->o_t.p; o.t9 = c->o_t9.p; o.rho = c->o_rho.p; o.tdel = c->o_tdel.p; o.kstep = c->o_kstep.p;
+  o.ktot = c->o_ktot.p; o.status = c->o_status.p; o.hist_cap = hist_cap;
+  if (hist_cap > 0) {
+    const size_t hn = (size_t)nz * hist_cap;
+    CUDA_TRY(c->o_hn.resize(nz)); CUDA_TRY(c->o_hkstep.resize(hn)); CUDA_TRY(c->o_hkmon.resize(2 * hn));
+    CUDA_TRY(c->o_ht.resize(hn)); CUDA_TRY(c->o_ht9.resize(hn)); CUDA_TRY(c->o_hrho.resize(hn)); CUDA_TRY(c->o_htdel.resize(hn));
+    CUDA_TRY(c->o_hedot.resize(hn)); CUDA_TRY(c->o_hsqnu.resize(hn)); CUDA_TRY(c->o_hy.resize(hn * ny));
+    o.hist_n = c->o_hn.p; o.hist_kstep = c->o_hkstep.p; o.hist_kmon = c->o_hkmon.p; o.hist_t = c->o_ht.p; o.hist_t9 = c->o_ht9.p;
+    o.hist_rho = c->o_hrho.p; o.hist_tdel = c->o_htdel.p; o.hist_edot = c->o_hedot.p; o.hist_sqnu = c->o_hsqnu.p; o.hist_y = c->o_hy.p;
+  }
+  return XB_OK;
+}
+
+int xb_evolve_resident(xb_ctx *c, float *kernel_ms) {
+  if (!c || c->nzone < 1) return fail(XB_ERR_ARG, "xb_evolve_resident: no zones uploaded");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMemsetAsync(c->counter.p, 0, sizeof(int)));
+  CUDA_TRY(cudaMemsetAsync(c->phase.p, 0, 8 * sizeof(unsigned long long)));
+  const int grid = std::min(c->grid, c->nzone);
+  CUDA_TRY(cudaEventRecord(c->ev0));
+  if (c->ctl.arith)
+    evolve_kernel<true><<<grid, c->threads, c->smem_bytes>>>(c->dn, c->dc, c->dz, c->dout, c->scr, c->counter.p, c->jac_in_smem);
+  else
+    evolve_kernel<false><<<grid, c->threads, c->smem_bytes>>>(c->dn, c->dc, c->dz, c->dout, c->scr, c->counter.p, c->jac_in_smem);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(c->ev1));
+  CUDA_TRY(cudaEventSynchronize(c->ev1));
+  if (kernel_ms) CUDA_TRY(cudaEventElapsedTime(kernel_ms, c->ev0, c->ev1));
+  return XB_OK;
+}
+
+#define GET(dst, buf, count)                                                                     \
+  do {                                                                                           \
+    if (dst) {                                                                                   \
+      CUDA_TRY(cudaMemcpy((dst), (buf).p, (size_t)(count) * sizeof(*(dst)), cudaMemcpyDeviceToHost)); \
+      c->d2h += (int64_t)((size_t)(count) * sizeof(*(dst)));                                     \
+    }                                                                                            \
+  } while (0)
+
+int xb_results_download(xb_ctx *c, xb_out *out) {
+  if (!c || !out) return fail(XB_ERR_ARG, "xb_results_download: null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const int nz = c->nzone, ny = c->dn.ny;
+  c->d2h = 0;
+  GET(out->y, c->o_y, (size_t)nz * ny); GET(out->t, c->o_t, nz); GET(out->t9, c->o_t9, nz); GET(out->rho, c->o_rho, nz);
+  GET(out->tdel, c->o_tdel, nz); GET(out->kstep, c->o_kstep, nz); GET(out->ktot, c->o_ktot, (size_t)nz * 5);
+  GET(out->status, c->o_status, nz);
+  if (c->hist_cap > 0 && out->hist_cap > 0) {
+    if (out->hist_cap != c->hist_cap) return fail(XB_ERR_ARG, "hist_cap differs from the uploaded one");
+    const size_t hn = (size_t)nz * c->hist_cap;
+    GET(out->hist_n, c->o_hn, nz); GET(out->hist_kstep, c->o_hkstep, hn); GET(out->hist_kmon, c->o_hkmon, 2 * hn);
+    GET(out->hist_t, c->o_ht, hn); GET(out->hist_t9, c->o_ht9, hn); GET(out->hist_rho, c->o_hrho, hn);
+    GET(out->hist_tdel, c->o_htdel, hn); GET(out->hist_edot, c->o_hedot, hn); GET(out->hist_sqnu, c->o_hsqnu, hn);
+    GET(out->hist_y, c->o_hy, hn * ny);
+  }
+  return XB_OK;
+}
+
+int xb_evolve(xb_ctx *c, const xb_zones *zones, xb_out *out) {
+  if (!out) return fail(XB_ERR_ARG, "xb_evolve: null output");
+  int rc = xb_zones_upload(c, zones, out->hist_cap); if (rc) return rc;
+  rc = xb_evolve_resident(c, nullptr); if (rc) return rc;
+  return xb_results_download(c, out);
+}
+
+int xb_phase_cycles(xb_ctx *c, double *cycles) {
+  if (!c || !cycles) return fail(XB_ERR_ARG, "xb_phase_cycles: null argument");
+  unsigned long long h[8];
+  CUDA_TRY(cudaMemcpy(h, c->phase.p, sizeof(h), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 8; ++k) cycles[k] = (double)h[k];
+  return XB_OK;
+}
+
+int xb_last_copy_bytes(xb_ctx *c, int64_t *h2d, int64_t *d2h) {
+  if (!c) return fail(XB_ERR_ARG, "null context");
+  if (h2d) *h2d = c->h2d; if (d2h) *d2h = c->d2h;
+  return XB_OK;
+}
+
+int xb_launch_config(xb_ctx *c, int32_t *cfg6) {
+  if (!c || !cfg6) return fail(XB_ERR_ARG, "null argument");
+  cfg6[0] = c->grid; cfg6[1] = c->threads; cfg6[2] = (int32_t)c->smem_bytes; cfg6[3] = c->jac_in_smem; cfg6[4] = c->nsm;
+  cfg6[5] = c->dn.msize;
+  return XB_OK;
+}
+
+int xb_measure_fp64_peak(int32_t device, double *flops) {
+  if (!flops) return fail(XB_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  const int grid = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+  double *d = nullptr; CUDA_TRY(cudaMalloc(&d, (size_t)grid * threads * 8));
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(a);
+    fp64_peak_kernel<<<grid, threads>>>(d, iters);
+    ++g_launches;
+    cudaEventRecord(b); cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    if (rep > 0) best = std::min(best, ms);
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+  CUDA_TRY(cudaGetLastError());
+  *flops = 2.0 * 8.0 * (double)iters * grid * threads / (best * 1e-3);
+  return XB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,57 @@
+// Host-side network model of xnet_b200 (C++17).  Mirrors the Fortran modules nuclear_data and
+// reaction_data (source/xnet_data.F90:8-52, 602-650 in the XNet tree) as plain vectors.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace xb {
+
+constexpr int kNG = 24;       // partition-function grid points (xnet_data.F90: ng)
+constexpr int kNGrid = 143;   // FFN grid 13 x 11 (xnet_ffn.F90:15-17)
+constexpr int kNChap = 11;
+
+struct Network {
+  int ny = 0, nffn = 0, nnnu = 0, izmax = 0;
+  int nreac[4] = {0, 0, 0, 0};
+  int nan[4] = {0, 0, 0, 0};
+  std::vector<std::string> nname;             // [ny] 5-char names
+  std::vector<double> aa, zz, nn, mex, be;    // [ny]
+  std::vector<int32_t> iz, in;
+  double mex_n = 0, mex_p = 0;
+  std::vector<double> g;                      // [ny][24]
+  std::vector<double> t9i;                    // [24]
+  std::vector<int32_t> chap_la, chap_le;      // [11]
+  // per reactant-count class c = 0..3
+  std::vector<int32_t> ni[4];                 // [nreac][6]
+  std::vector<double> rc[4];                  // [nreac][7]
+  std::vector<double> q[4];
+  std::vector<int32_t> iwk[4], ires[4], irev[4];
+  std::vector<int32_t> iffn;                  // [nreac1]
+  std::vector<int32_t> la, le;                // [4][ny] class-major
+  std::vector<int32_t> mu[4];                 // [nan]
+  std::vector<double> a[4];                   // [nan]
+  // FFN tables [nffn][143]
+  std::vector<double> ffnsum, ffnenu, ffn_ec, ffn_beta, ffn_qval;
+  std::vector<int32_t> has_logft;
+};
+
+// throws std::runtime_error on malformed input
+void load_network(const std::string &data_dir, int iweak0, Network &net);
+int index_from_name(const Network &net, const std::string &name);
+
+struct Thermo {
+  std::string desc;
+  double tstart = 0, tstop = 0, tdelstart = 0;
+  std::vector<double> th, t9h, rhoh, yeh;
+};
+void read_thermo_file(const std::string &path, Thermo &th);
+
+struct InAb {
+  std::string desc;
+  double yein = 0, xext = 0, aext = 1, zext = 0;
+  std::vector<double> y;
+};
+void read_inab_file(const Network &net, const std::string &path, InAb &ab);
+
+}  // namespace xb

@@ -1,0 +1,440 @@
+// Host-side loader and network pre-processing for xnet_b200.
+//
+// Host mirror of (XNet tree, /root/reference/source):
+//   read_sunet / read_netwinv / read_nuclear_data   xnet_data.F90:285-513
+//   net_preprocess                                   xnet_preprocess.F90:505-1011
+//   read_reaction_data (iffn pointers)               xnet_data.F90:855-866
+//   read_ffn_data_table / _logft                     xnet_ffn.F90:73-137
+//   read_thermo_file / read_inab_file                model_input_ascii.F90:5-110, 223-350
+// Integer outputs (reaction classification, species->reaction maps) are bit-exact scope; they are
+// checked against the shipped net_desc goldens and against the oracle's independent parser.
+#include "xb_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <fstream>
+#include <limits>
+#include <sstream>
+#include <stdexcept>
+
+namespace xb {
+namespace {
+
+const int kNnucr[kNChap] = {2, 3, 4, 3, 4, 5, 6, 4, 5, 6, 5};      // nuclei per chapter
+const int kNreactant[kNChap] = {1, 1, 1, 2, 2, 2, 2, 3, 3, 4, 1};  // reactants per chapter
+
+// REACLIB source labels in table order (xnet_preprocess.F90:534-556); position = idesc-1
+const char *const kDescKnown[171] = {
+    "  ec", "bet+", "betp", "bet-", "betm", "btyk", " bec", "bkmo", "mo92", " ffn", " lmp", "fkth",
+    "cf88", "wies", "laur", "bb92", "baka", "rolf", "wawo", "mafo", "ms01", " wag", "bb93", "ca85",
+    "ornl", " wfh", "rath", "rpsm", "hg94", "ro95", "wien", "iucf", "smwa", "smmo", "wi2p", "aexp",
+    "pexp", "bex+", "bex-", "bqa+", "bhi+", "bec ", "bklq", "nuba", "bede", "bqa+", "gamm", "ja01",
+    "nosm", "nacr", "tang", "ta04", "ch04", "ku02", "il04", "go00", "most", "il03", "de04", "da03",
+    "vanc", "il01", "ha00", "ku92", "ro04", "sc83", "he98", "po00", "il00", "he95", "sc98", "vo00",
+    "il99", "beau", "da04", "ca00", "da77", "bl03", "ch01", "fynb", "De99", "bu96", "ba00", "Ha96",
+    "sh03", "tr04", "sc05", "nfis", "GW95", "ch05", "re98", "nb03", "mo03", "wc07", "an06", "ka02",
+    "gl07", "GG90", "lg06", "im05", "GG92", "ct07", "ga00", "ww02", "wh87", "dh03", "ha01", "cb01",
+    "HF99", "hg95", "pg06", "jm06", "sb05", "SM93", "SM86", "thra", "fy05", "ha04", "pt05", "bk91",
+    "bk92", "kg91", "SM91", "iwam", " nen", "nebp", "lznu", "lzan", "ths8", "wc12", "nk06", "mb11",
+    "jz10", "cd08", "nw00", "il10", "li10", "chw0", "co10", "kd02", "st08", "pkrF", "br10", "hi09",
+    "ld11", "hd08", "ua08", "ol11", "ls09", "ia08", "dc11", "mb07", "wc17", "mo97", "ks03", "nac2",
+    "mp17", "cb09", "li12", "ma10", "mm11", "si13", "sa12", "ks12", "hg12", "rk12", "ac12", "gl12",
+    "mv09", "lhnn", "lhna"};
+
+// weak-reaction class from the label position (xnet_preprocess.F90:648-669)
+int weak_flag_from_label(int idesc, int z_first, int z_second) {
+  if (idesc == 1) return 1;
+  if (idesc == 10 || idesc == 11) return (z_first > z_second && z_first != 1) ? 3 : 2;
+  if ((idesc >= 2 && idesc <= 9) || (idesc >= 38 && idesc <= 45) || (idesc >= 92 && idesc <= 94) ||
+      idesc == 130 || idesc == 153 || idesc == 154 || idesc == 157)
+    return 4;
+  if (idesc == 125 || idesc == 127) return 7;
+  if (idesc == 126 || idesc == 128) return 8;
+  if (idesc == 170) return 9;
+  if (idesc == 171) return 10;
+  return 0;
+}
+
+std::vector<std::string> read_lines(const std::string &path) {
+  std::ifstream f(path);
+  if (!f) throw std::runtime_error("Failed to open input file: " + path);
+  std::vector<std::string> out;
+  std::string s;
+  while (std::getline(f, s)) {
+    if (!s.empty() && s.back() == '\r') s.pop_back();
+    out.push_back(s);
+  }
+  return out;
+}
+
+std::string field(const std::string &line, size_t pos, size_t len) {  // blank padded fixed field
+  std::string r(len, ' ');
+  for (size_t i = 0; i < len && pos + i < line.size(); ++i) r[i] = line[pos + i];
+  return r;
+}
+
+std::string trimmed(const std::string &s) {
+  size_t a = s.find_first_not_of(" \t");
+  if (a == std::string::npos) return "";
+  size_t b = s.find_last_not_of(" \t");
+  return s.substr(a, b - a + 1);
+}
+
+double fortran_real(const std::string &txt) {  // blank -> 0, D exponent accepted
+  std::string s = trimmed(txt);
+  if (s.empty()) return 0.0;
+  for (auto &c : s)
+    if (c == 'D' || c == 'd') c = 'E';
+  return std::strtod(s.c_str(), nullptr);
+}
+
+int fortran_int(const std::string &txt) {
+  std::string s = trimmed(txt);
+  return s.empty() ? 0 : std::atoi(s.c_str());
+}
+
+// list-directed token stream over a range of lines
+std::vector<std::string> tokens_from(const std::vector<std::string> &lines, size_t first) {
+  std::vector<std::string> tok;
+  for (size_t i = first; i < lines.size(); ++i) {
+    std::string s = lines[i];
+    for (auto &c : s)
+      if (c == ',' || c == '\t') c = ' ';
+    std::istringstream is(s);
+    std::string t;
+    while (is >> t) tok.push_back(t);
+  }
+  return tok;
+}
+
+void read_nuclear(const std::string &dir, Network &net) {
+  // sunet: one name per line
+  std::vector<std::string> sun = read_lines(dir + "/sunet");
+  while (!sun.empty() && sun.back().empty()) sun.pop_back();
+  // netwinv
+  std::vector<std::string> w = read_lines(dir + "/netwinv");
+  if (w.size() < 2) throw std::runtime_error("Error reading netwinv file");
+  net.ny = fortran_int(field(w[0], 0, 5));
+  const int ny = net.ny;
+  if ((int)sun.size() != ny) throw std::runtime_error("netwinv /= sunet");
+  net.t9i.assign(kNG, 0.0);
+  for (int j = 0; j < kNG; ++j) {
+    double v = (double)fortran_int(field(w[1], 3 * j, 3));
+    net.t9i[j] = (j < kNG - 1) ? 0.01 * v : 0.1 * v;
+  }
+  net.nname.resize(ny);
+  for (int i = 0; i < ny; ++i) {
+    net.nname[i] = field(w[2 + i], 0, 5);
+    if (trimmed(net.nname[i]) != trimmed(field(sun[i], 0, 5))) throw std::runtime_error("netwinv /= sunet");
+  }
+  std::vector<std::string> tok = tokens_from(w, 2 + ny);
+  if ((int)tok.size() < ny * (6 + kNG)) throw std::runtime_error("Error reading netwinv file");
+  net.aa.resize(ny); net.zz.resize(ny); net.nn.resize(ny); net.mex.resize(ny); net.be.resize(ny);
+  net.iz.resize(ny); net.in.resize(ny); net.g.resize((size_t)ny * kNG);
+  size_t p = 0;
+  for (int i = 0; i < ny; ++i) {
+    if (trimmed(tok[p]) != trimmed(net.nname[i]))
+      throw std::runtime_error("netwinv data entry name does not match header");
+    net.aa[i] = fortran_real(tok[p + 1]);
+    net.iz[i] = std::atoi(tok[p + 2].c_str());
+    net.in[i] = std::atoi(tok[p + 3].c_str());
+    net.mex[i] = fortran_real(tok[p + 5]);
+    p += 6;
+    for (int j = 0; j < kNG; ++j) net.g[(size_t)i * kNG + j] = fortran_real(tok[p + j]);
+    p += kNG;
+    net.zz[i] = (double)net.iz[i];
+    net.nn[i] = (double)net.in[i];
+  }
+  net.izmax = *std::max_element(net.iz.begin(), net.iz.end());
+  // binding energies from the n/p mass excesses of the table itself (xnet_data.F90:486-498)
+  const double avn = 6.022140857e+23, epmev = 1.6021766208e-06, clt = 2.99792458e+10;
+  const double m_e = 0.5109989461, m_n = 939.5654133, m_p = 938.2720813;
+  const double amu = 1.0 / (avn * epmev), m_u = amu * (clt * clt);
+  int ineut = -1, iprot = -1;
+  for (int i = 0; i < ny; ++i) {
+    if (net.iz[i] == 0 && net.in[i] == 1) ineut = i;
+    if (net.iz[i] == 1 && net.in[i] == 0) iprot = i;
+  }
+  net.mex_n = ineut >= 0 ? net.mex[ineut] : m_n - m_u;
+  net.mex_p = iprot >= 0 ? net.mex[iprot] : m_p + m_e - m_u;
+  for (int i = 0; i < ny; ++i) net.be[i] = net.mex_n * net.nn[i] + net.mex_p * net.zz[i] - net.mex[i];
+}
+
+struct RawReaction {
+  int32_t n[6];
+  double an[6];
+  double rc[7];
+  double q;
+  int32_t iwk, ires, irev;
+};
+
+void preprocess_reactions(const std::string &dir, Network &net) {
+  const int ny = net.ny;
+  std::vector<std::string> L = read_lines(dir + "/netsu");
+  if (L.empty()) throw std::runtime_error("Failed to read netsu");
+  net.nffn = fortran_int(field(L[0], 0, 5));
+  net.nnnu = fortran_int(field(L[0], 5, 6));
+  while (L.size() > 1 && trimmed(L.back()).empty()) L.pop_back();
+
+  int cla[kNChap + 1], cle[kNChap + 1];
+  for (int j = 0; j <= kNChap; ++j) { cla[j] = 1; cle[j] = 0; }
+  std::vector<RawReaction> store[4];  // slot n-1 of the class, overwritten like the Fortran arrays
+  int count[4] = {0, 0, 0, 0};
+  int n = 1, chapter = 1;
+
+  for (size_t pos = 1; pos + 3 <= L.size(); pos += 3) {
+    const std::string &hdr = L[pos];
+    const int k = fortran_int(field(hdr, 0, 2));
+    if (k != 0) {  // chapter marker: (re)position the running reaction index
+      if (k == 1) { chapter = k; cla[k] = 1; n = 1; }
+      else if (k == 4 || k == 8 || k == 10) { chapter = k; cla[k] = 1; cle[k - 1] = n - 1; n = 1; }
+      else if (k == 11) { chapter = k; cla[k] = cle[3] + 1; cle[k - 1] = n - 1; n = cle[3] + 1; }
+      else { chapter = k; cla[k] = n; cle[k - 1] = n - 1; }
+      continue;
+    }
+    std::string name[6];
+    int32_t idx[6];
+    bool outside = false;
+    for (int s = 0; s < 6; ++s) {
+      name[s] = field(hdr, 5 + 5 * s, 5);
+      idx[s] = index_from_name(net, name[s]);
+      if (idx[s] > ny) outside = true;
+    }
+    if (outside) continue;  // reaction involves a nucleus not in sunet: dropped
+    const std::string label = field(hdr, 43, 4);
+    const char resflag = field(hdr, 47, 1)[0], revflag = field(hdr, 48, 1)[0];
+    RawReaction r{};
+    for (int j = 0; j < 4; ++j) r.rc[j] = fortran_real(field(L[pos + 1], 13 * j, 13));
+    for (int j = 0; j < 3; ++j) r.rc[4 + j] = fortran_real(field(L[pos + 2], 13 * j, 13));
+    int idesc = 172;
+    for (int d = 0; d < 171; ++d)
+      if (label == kDescKnown[d]) { idesc = d + 1; break; }
+    r.iwk = weak_flag_from_label(idesc, idx[0] > 0 ? net.iz[idx[0] - 1] : 0, idx[1] > 0 ? net.iz[idx[1] - 1] : 0);
+    r.ires = (resflag == ' ' || resflag == 'w') ? 0 : (resflag == 'n' ? 1 : 2);
+    r.irev = (revflag == 'v') ? 1 : 0;
+    const int nreact = kNreactant[chapter - 1];
+    // reactants count -1, products +1, blanks 0; Q from the table masses
+    int ki[6];
+    double qv = 0.0;
+    for (int s = 0; s < 6; ++s) {
+      const bool blank = (name[s] == "     ");
+      if (s + 1 > nreact) {
+        ki[s] = blank ? 0 : 1;
+        if (!blank) { int j = idx[s] - 1; qv = qv + net.be[j] - net.mex_n * net.nn[j] - net.mex_p * net.zz[j]; }
+      } else {
+        ki[s] = -1;
+        int j = idx[s] - 1;
+        qv = qv - net.be[j] + net.mex_n * net.nn[j] + net.mex_p * net.zz[j];
+      }
+    }
+    r.q = qv;
+    // fold runs of identical names: reactants, then products (xnet_preprocess.F90:728-750)
+    {
+      int head = 0;
+      for (int s = 1; s < nreact; ++s) {
+        if (name[s - 1] != name[s]) head = s;
+        else { ki[head] += ki[s]; ki[s] = 0; }
+      }
+      head = nreact;
+      for (int s = nreact + 1; s < 6; ++s) {
+        if (name[s - 1] != name[s]) head = s;
+        else { ki[head] += ki[s]; ki[s] = 0; }
+      }
+    }
+    double fac = 1.0;
+    int nslots = 5;
+    if (nreact > 1) {
+      int lo = 0;
+      for (int s = 0; s < nreact; ++s) lo = std::min(lo, ki[s]);
+      int f = 1;
+      for (int i = 2; i <= -lo; ++i) f *= i;
+      fac = 1.0 / (double)f;
+      nslots = 6;
+    }
+    for (int s = 0; s < 6; ++s) {
+      r.n[s] = s < nslots ? idx[s] : 0;
+      r.an[s] = s < nslots ? (double)ki[s] * fac : 0.0;
+    }
+    auto &vec = store[nreact - 1];
+    if ((int)vec.size() < n) vec.resize(n);
+    vec[n - 1] = r;
+    ++count[nreact - 1];
+    ++n;
+  }
+  cle[chapter] = n - 1;
+  net.chap_la.assign(cla + 1, cla + 1 + kNChap);
+  net.chap_le.assign(cle + 1, cle + 1 + kNChap);
+
+  for (int c = 0; c < 4; ++c) {
+    const int nr = count[c];
+    net.nreac[c] = nr;
+    if ((int)store[c].size() < nr) throw std::runtime_error("netsu: inconsistent chapter markers");
+    net.ni[c].assign((size_t)nr * 6, 0); net.rc[c].assign((size_t)nr * 7, 0.0); net.q[c].assign(nr, 0.0);
+    net.iwk[c].assign(nr, 0); net.ires[c].assign(nr, 0); net.irev[c].assign(nr, 0);
+    for (int k = 0; k < nr; ++k) {
+      const RawReaction &r = store[c][k];
+      for (int s = 0; s < 6; ++s) net.ni[c][(size_t)k * 6 + s] = r.n[s];
+      for (int j = 0; j < 7; ++j) net.rc[c][(size_t)k * 7 + j] = r.rc[j];
+      net.q[c][k] = r.q; net.iwk[c][k] = r.iwk; net.ires[c][k] = r.ires; net.irev[c][k] = r.irev;
+    }
+  }
+
+  // species -> reaction registration: species outer, chapters of the class in order, reaction,
+  // slot (xnet_preprocess.F90:863-951).  Defines the summation order of ydot and the Jacobian.
+  const double tiny = std::numeric_limits<double>::min();
+  net.la.assign((size_t)4 * ny, 0); net.le.assign((size_t)4 * ny, 0);
+  for (int c = 0; c < 4; ++c) {
+    net.mu[c].clear(); net.a[c].clear();
+    int cnt = 0;
+    for (int i = 1; i <= ny; ++i) {
+      net.la[(size_t)c * ny + i - 1] = cnt + 1;
+      for (int j = 1; j <= kNChap; ++j) {
+        if (kNreactant[j - 1] != c + 1) continue;
+        for (int k = cla[j]; k <= cle[j]; ++k) {
+          if (k < 1 || k > (int)store[c].size()) continue;
+          const RawReaction &r = store[c][k - 1];
+          for (int l = 0; l < kNnucr[j - 1]; ++l) {
+            if (r.n[l] == i && std::fabs(r.an[l]) > tiny) {
+              ++cnt;
+              net.a[c].push_back(r.an[l]);
+              net.mu[c].push_back(k);
+            }
+          }
+        }
+      }
+      net.le[(size_t)c * ny + i - 1] = cnt;
+    }
+    net.nan[c] = cnt;
+  }
+
+  // FFN table pointer lives in REACLIB coefficient 1 (xnet_data.F90:857-866)
+  net.iffn.assign(net.nreac[0], 0);
+  for (int k = 0; k < net.nreac[0]; ++k)
+    if (net.iwk[0][k] == 2 || net.iwk[0][k] == 3) net.iffn[k] = (int32_t)std::lrint(net.rc[0][(size_t)k * 7]);
+}
+
+void read_ffn(const std::string &dir, int iweak0, Network &net) {
+  const int nf = std::max(net.nffn, 1);
+  net.ffnsum.assign((size_t)nf * kNGrid, 0.0); net.ffnenu.assign((size_t)nf * kNGrid, 0.0);
+  net.ffn_ec.assign((size_t)nf * kNGrid, 0.0); net.ffn_beta.assign((size_t)nf * kNGrid, 0.0);
+  net.ffn_qval.assign(nf, 0.0); net.has_logft.assign(nf, 0);
+  if (net.nffn <= 0) return;
+  std::vector<std::string> L = read_lines(dir + "/netweak");
+  size_t pos = 0;
+  const bool logft = std::abs(iweak0) == 2;
+  const int per = logft ? 4 : 2;
+  for (int i = 0; i < net.nffn; ++i) {
+    if (pos >= L.size()) throw std::runtime_error("netweak: unexpected end of file");
+    if (logft) {
+      std::istringstream is(L[pos]);
+      std::string n1, n2, d;
+      std::string qv;
+      is >> n1 >> n2 >> d >> qv;
+      net.ffn_qval[i] = fortran_real(qv);
+      std::string d3 = d.substr(0, 3);
+      net.has_logft[i] = d3 == "ft+" ? 2 : (d3 == "ft-" ? 1 : 0);
+    }
+    ++pos;
+    std::vector<double> v;
+    while ((int)v.size() < per * kNGrid) {
+      if (pos >= L.size()) throw std::runtime_error("netweak: unexpected end of file");
+      std::string s = L[pos++];
+      for (auto &c : s)
+        if (c == ',') c = ' ';
+      std::istringstream is(s);
+      std::string t;
+      while (is >> t) v.push_back(fortran_real(t));
+    }
+    for (int j = 0; j < kNGrid; ++j) {
+      if (logft) {
+        net.ffn_beta[(size_t)i * kNGrid + j] = v[4 * j];
+        double ec = v[4 * j + 1];
+        net.ffn_ec[(size_t)i * kNGrid + j] = ec < -30.0 ? 99.0 : ec;
+        net.ffnsum[(size_t)i * kNGrid + j] = v[4 * j + 2];
+        net.ffnenu[(size_t)i * kNGrid + j] = v[4 * j + 3];
+      } else {
+        net.ffnsum[(size_t)i * kNGrid + j] = v[2 * j];
+        net.ffnenu[(size_t)i * kNGrid + j] = v[2 * j + 1];
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int index_from_name(const Network &net, const std::string &name) {
+  // 0 = blank, ny+1 = not in the network (xnet_data.F90:54-82)
+  const std::string s = trimmed(name);
+  if (s.empty()) return 0;
+  for (int i = 0; i < net.ny; ++i)
+    if (trimmed(net.nname[i]) == s) return i + 1;
+  return net.ny + 1;
+}
+
+void load_network(const std::string &data_dir, int iweak0, Network &net) {
+  read_nuclear(data_dir, net);
+  preprocess_reactions(data_dir, net);
+  read_ffn(data_dir, iweak0, net);
+}
+
+void read_thermo_file(const std::string &path, Thermo &th) {
+  std::vector<std::string> L = read_lines(path);
+  if (L.size() < 5) throw std::runtime_error("Failed while trying to read input file: " + path);
+  th.desc = field(L[0], 0, 80);
+  auto first_tok = [](const std::string &s) { std::istringstream is(s); std::string t; is >> t; return t; };
+  th.tstart = fortran_real(first_tok(L[1]));
+  th.tstop = fortran_real(first_tok(L[2]));
+  th.tdelstart = std::min(0.0, fortran_real(first_tok(L[3])));  // file value is ignored unless negative
+  th.th.clear(); th.t9h.clear(); th.rhoh.clear(); th.yeh.clear();
+  size_t last = L.size();
+  while (last > 4 && L[last - 1].empty()) --last;
+  for (size_t i = 4; i < last && th.th.size() < 50000; ++i) {
+    std::string s = L[i];
+    for (auto &c : s)
+      if (c == '\t') c = ' ';
+    std::istringstream is(s);
+    std::vector<std::string> t;
+    std::string x;
+    while (is >> x) t.push_back(x);
+    if (t.size() < 3) throw std::runtime_error("Not enough columns in thermo file: " + path);
+    th.th.push_back(fortran_real(t[0])); th.t9h.push_back(fortran_real(t[1])); th.rhoh.push_back(fortran_real(t[2]));
+    th.yeh.push_back(t.size() > 3 ? fortran_real(t[3]) : 0.0);
+  }
+}
+
+void read_inab_file(const Network &net, const std::string &path, InAb &ab) {
+  std::vector<std::string> L = read_lines(path);
+  if (L.empty()) throw std::runtime_error("Failed to open input file: " + path);
+  ab.desc = field(L[0], 0, 80);
+  std::vector<std::string> tok = tokens_from(L, 1);
+  const int ny = net.ny;
+  ab.y.assign(ny, 0.0);
+  ab.yein = 0.0;
+  double yext = 0.0;
+  for (size_t i = 0; i + 1 < tok.size(); i += 2) {
+    std::string nm = tok[i];
+    nm.erase(std::remove(nm.begin(), nm.end(), '\''), nm.end());
+    nm = trimmed(nm.substr(0, 5));
+    const double v = fortran_real(tok[i + 1]);
+    if (nm.empty() || !(v > 0.0)) continue;
+    for (auto &c : nm)
+      if (c >= 'A' && c <= 'Z') c = (char)(c - 'A' + 'a');
+    if (nm == "ye") { ab.yein = v; continue; }
+    const int inuc = index_from_name(net, nm);
+    if (inuc < 1 || inuc > ny) yext += v; else ab.y[inuc - 1] = v;
+  }
+  // sum(yin*aa), sum(yin*zz): gfortran evaluates the array sums left to right
+  double xnet = 0.0, znet = 0.0;
+  for (int i = 0; i < ny; ++i) { xnet += ab.y[i] * net.aa[i]; znet += ab.y[i] * net.zz[i]; }
+  if (yext > 0.0 && xnet < 1.0 && znet < ab.yein) {
+    ab.xext = 1.0 - xnet;
+    ab.aext = ab.xext / yext;
+    ab.zext = (ab.yein <= 0.0 || ab.yein >= 1.0) ? 0.0 : (ab.yein - znet) * ab.aext / ab.xext;
+  } else {
+    ab.xext = 0.0; ab.aext = 1.0; ab.zext = 0.0;
+    for (int i = 0; i < ny; ++i) ab.y[i] = ab.y[i] / xnet;
+  }
+}
+
+}  // namespace xb
