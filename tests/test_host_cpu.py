@@ -1,0 +1,109 @@
+"""CPU tests of the product's host side: the C ABI library loads and exports every declared symbol,
+its C++ loader/pre-processor agrees bit for bit with the oracle's independent parser and with the
+reference's net_desc goldens.  No compute calls (no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import DATA, ROOT, control_text, PROBLEMS
+
+NETS = [('alpha', 1), ('torch47', 1), ('SN160', 1), ('SN231', 1), ('SN231_logft', 2), ('XRB304', 1)]
+
+
+def test_library_exports_every_declared_symbol(built):
+    import xnet_b200 as X
+    from xnet_b200 import api
+    hdr = open(os.path.join(ROOT, 'include', 'xnet_b200.h')).read()
+    declared = set(re.findall(r'\b(xb_[a-z0-9_]+)\s*\(', hdr))
+    declared -= {'xb_step_be'} if 'int xb_step_be' not in hdr else set()
+    lib = C.CDLL(X.lib_path())
+    for name in sorted(declared):
+        assert hasattr(lib, name), 'missing export ' + name
+    assert declared == set(api.EXPORTS)
+    assert X.lib().xb_version() == 1
+
+
+@pytest.mark.parametrize('net,iweak0', NETS)
+def test_loader_bit_exact_against_oracle(built, net, iweak0):
+    import xnet_b200 as X
+    from oracle import xnet_loader as L
+    d = os.path.join(DATA, 'Data_' + net)
+    n = X.Network(d, iweak0)
+    nuc, on, ffn = L.load_network(d, iweak0)
+    assert (n.ny, n.nreac, n.nan, n.nffn, n.nnnu) == (nuc['ny'], on['nreac'], on['nan'], on['nffn'], on['nnnu'])
+    assert np.array_equal(n.itable('la'), on['la'].ravel()) and np.array_equal(n.itable('le'), on['le'].ravel())
+    assert np.array_equal(n.itable('chap_la'), on['chap_la']) and np.array_equal(n.itable('chap_le'), on['chap_le'])
+    for c in range(1, 5):
+        for key, ref in (('mu%d', 'mu%d'), ('iwk%d', 'iwk%d'), ('irev%d', 'irev%d'), ('ires%d', 'ires%d')):
+            assert np.array_equal(n.itable(key % c), on[ref % c]), key % c
+        assert np.array_equal(n.itable('n%di' % c), on['n%d' % c].ravel())
+        assert np.array_equal(n.dtable('a%d' % c), on['a%d' % c])
+        assert np.array_equal(n.dtable('rc%d' % c), on['rc%d' % c].ravel())
+        assert np.array_equal(n.dtable('q%d' % c), on['q%d' % c])
+    assert np.array_equal(n.itable('iffn'), on['iffn'])
+    for nm in ('aa', 'zz', 'mex', 'be', 't9i'):
+        assert np.array_equal(n.dtable(nm), nuc[nm])
+    assert np.array_equal(n.dtable('g'), nuc['g'].ravel())
+    for nm in ('ffnsum', 'ffnenu', 'ffn_ec', 'ffn_beta'):
+        assert np.array_equal(n.dtable(nm), ffn[nm].ravel())
+
+
+@pytest.mark.parametrize('net', ['alpha', 'torch47', 'SN160', 'SN231', 'XRB304'])
+def test_loader_against_net_desc(built, net):
+    import xnet_b200 as X
+    n = X.Network(os.path.join(DATA, 'Data_' + net))
+    ref = open(os.path.join(ROOT, 'tests', 'golden', 'net_desc_%s.txt' % net)).read().split('\n')
+    assert int(ref[1].split('=')[1]) == n.ny
+    la, le = n.itable('chap_la'), n.itable('chap_le')
+    for j in range(11):
+        assert [int(v) for v in ref[3 + j].split()] == [j + 1, la[j], le[j]]
+    assert [int(v) for v in ref[15].split('=')[1].split()] == n.nreac
+    assert [int(v) for v in ref[16].split('=')[1].split()] == n.nan
+
+
+@pytest.mark.parametrize('name', list(PROBLEMS))
+def test_fixture_and_controls_against_oracle(built, name):
+    import xnet_b200 as X
+    from oracle import xnet_loader as L
+    txt = control_text(*PROBLEMS[name])
+    c, oc = X.read_controls(txt), L.read_controls(txt)
+    for k in c:
+        if k in oc:
+            assert c[k] == oc[k], k
+    net = X.Network(os.path.join(DATA, c['data_dir']), c['iweak0'])
+    nuc = L.read_nuclear_data(os.path.join(DATA, c['data_dir']))
+    f = X.load_fixture(net, os.path.join(DATA, c['inab_file'][0]), os.path.join(DATA, c['thermo_file'][0]))
+    z = L.load_zone(os.path.join(DATA, c['inab_file'][0]), os.path.join(DATA, c['thermo_file'][0]), nuc, c['t9nse'])
+    for k in ('nh', 'tstart', 'tstop', 'tdelstart', 'nstart', 't9start', 'rhostart', 'yestart', 'xext', 'aext', 'zext'):
+        assert f[k] == z[k], k
+    for k in ('th', 't9h', 'rhoh', 'ystart'):
+        assert np.array_equal(f[k], z[k]), k
+
+
+def test_missing_input_fails_loudly(built):
+    import xnet_b200 as X
+    with pytest.raises(X.XnetB200Error):
+        X.Network(os.path.join(DATA, 'Data_does_not_exist'))
+
+
+def test_no_cpu_fallback_without_gpu(built):
+    """On a box without a CUDA device every compute entry point must fail, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    import xnet_b200 as X
+    c = X.read_controls(control_text(*PROBLEMS['alpha']))
+    net = X.Network(os.path.join(DATA, c['data_dir']))
+    with pytest.raises(X.XnetB200Error):
+        X.Context(net, c, nzevolve=1)
+
+
+def test_product_never_imports_oracle():
+    for dp, _, files in os.walk(os.path.join(ROOT, 'xnet_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.cpp', '.h')):
+                s = open(os.path.join(dp, f)).read()
+                assert 'oracle' not in s.replace('the oracle', '').replace("oracle's", '').replace('CPU oracle', ''), f
