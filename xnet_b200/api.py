@@ -405,9 +405,10 @@ class Context:
         return res
 
     def phase_cycles(self):
-        c = np.zeros(8)
+        c = np.zeros(12)
         _chk(lib().xb_phase_cycles(self.h, _pd(c)))
-        return dict(zip(('rates', 'yderiv', 'jac', 'lu', 'bksub', 'other', 'total', 'zones'), c))
+        return dict(zip(('rates', 'yderiv', 'jac', 'lu', 'bksub', 'other', 'total', 'zones',
+                         'lu_panel', 'lu_swap_trsm', 'lu_gemm', 'spare'), c))
 
     def copy_bytes(self):
         a = C.c_int64(); b = C.c_int64()

@@ -5,12 +5,14 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "../../include/xnet_b200.h"
 #include "xb_host.h"
+#define XB_MAX_THREADS 256
 #include "xb_zone.cuh"
 
 using namespace xb;
@@ -57,7 +59,10 @@ struct xb_ctx {
   DevCtl dc{};
   // network tables
   DevBuf<double> rcT, a[4], aa, zz, mex, be, g, lng, dlng, t9i, ffnsum, ffnenu;
-  DevBuf<int> ni, iwk, irev, iffn, la, le, mu[4], nn[4][4];
+  DevBuf<int> ni, iwk, irev, iffn, la, le, mu[4], nn[4][4], ffr_n1, ffr_iffn;
+  // term plans (ydot, Jacobian)
+  struct PlanBufs { DevBuf<double> a; DevBuf<uint2> nn, mc; DevBuf<int> seg_start, seg_dest, multi_start, multi_dest; } pby, pbj;
+  int ld = 0, npart = 0;
   // launch configuration
   int threads = 256, grid = 0, jac_in_smem = 1;
   size_t smem_bytes = 0;
@@ -83,58 +88,62 @@ struct xb_ctx {
 
 // ------------------------------------------------------------------------------------------------
 // shared-memory carve-up of one zone
-struct SmemLayout { size_t scal, jac, y, yo, yt, ydot, rhs, gg, indx, total; };
-static __host__ __device__ SmemLayout smem_layout(int ny, int N, bool jac_in_smem) {
-  SmemLayout L;
+static SmemOff smem_layout(int ny, int N, int ld, int npart, bool jac_in_smem) {
+  SmemOff L{};
   size_t o = 0;
-  L.scal = o; o += (sizeof(ZoneScalars) + 15) / 16 * 16;
-  L.jac = o; if (jac_in_smem) o += (size_t)N * N * 8;
-  L.y = o; o += (size_t)ny * 8;
-  L.yo = o; o += (size_t)ny * 8;
-  L.yt = o; o += (size_t)ny * 8;
-  L.ydot = o; o += (size_t)ny * 8;
-  L.rhs = o; o += (size_t)N * 8;
-  L.gg = o; o += (size_t)(ny + 1) * 8;
-  L.indx = o; o += (size_t)N * 4;
-  L.total = (o + 15) / 16 * 16;
+  L.scal = (int)o; o += (sizeof(ZoneScalars) + 15) / 16 * 16;
+  L.jac = (int)o; if (jac_in_smem) o += ((size_t)N * ld * 8 + 15) / 16 * 16;
+  L.y = (int)o; o += (size_t)ny * 8;
+  L.yo = (int)o; o += (size_t)ny * 8;
+  L.yt = (int)o; o += (size_t)(ny + 1) * 8;
+  L.ydot = (int)o; o += (size_t)ny * 8;
+  L.rhs = (int)o; o += (size_t)N * 8;
+  L.gg = (int)o; o += (size_t)(ny + 1) * 8;
+  L.rdiag = (int)o; o += (size_t)N * 8;
+  o = (o + 15) / 16 * 16;
+  L.part = (int)o; o += (size_t)npart * 8;
+  o = (o + 15) / 16 * 16;
+  L.prow = (int)o; o += (size_t)2 * kPanelWarps * kPanelRec * 8;
+  L.indx = (int)o; o += (size_t)N * 4;
+  L.total = (int)((o + 15) / 16 * 16);
   return L;
 }
 
-static __device__ void carve(ZoneMem &zm, unsigned char *sm, const DevNet &net, const DevScratch &scr, bool jac_in_smem) {
-  SmemLayout L = smem_layout(net.ny, net.msize, jac_in_smem);
-  double *g = scr.base + (size_t)blockIdx.x * scr.stride;
-  zm.s = reinterpret_cast<ZoneScalars *>(sm + L.scal);
-  zm.jac = jac_in_smem ? reinterpret_cast<double *>(sm + L.jac) : g + scr.off_jac;
-  zm.y = reinterpret_cast<double *>(sm + L.y);
-  zm.yo = reinterpret_cast<double *>(sm + L.yo);
-  zm.yt = reinterpret_cast<double *>(sm + L.yt);
-  zm.ydot = reinterpret_cast<double *>(sm + L.ydot);
-  zm.rhs = reinterpret_cast<double *>(sm + L.rhs);
-  zm.gg = reinterpret_cast<double *>(sm + L.gg);
-  zm.indx = reinterpret_cast<int *>(sm + L.indx);
-  zm.csect = g + scr.off_csect;
-  zm.rffn = g + scr.off_rffn;
-  zm.qkffn = g + scr.off_qkffn;
+// Kernel prologue: per-CTA global scratch pointers into the zone scalars, yt[ny] = 1 (the factor that
+// stands in for absent reactants in the term plans).
+static __device__ void zone_prologue(const DevScratch &scr, double *csect, double *qkffn, double *jacg) {
+  ZoneScalars *s = reinterpret_cast<ZoneScalars *>(xb_smem + c_net.lay.scal);
+  if (threadIdx.x == 0) {
+    double *g = scr.base + (size_t)blockIdx.x * scr.stride;
+    s->g_csect = csect ? csect : g + scr.off_csect;
+    s->g_rffn = g + scr.off_rffn;
+    s->g_qkffn = qkffn ? qkffn : g + scr.off_qkffn;
+    s->g_prod = g + scr.off_prod;
+    s->g_jac = jacg ? jacg : g + scr.off_jac;
+    reinterpret_cast<double *>(xb_smem + c_net.lay.yt)[c_net.ny] = 1.0;
+  }
+  __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
 // Persistent evolve kernel: each CTA pulls zones from a global counter and runs full_net on them.
 template <bool STRICT>
-__global__ void evolve_kernel(DevNet net, DevCtl ctl, DevZones zn, DevOut out, DevScratch scr, int *counter,
-                              int jac_in_smem) {
-  extern __shared__ __align__(16) unsigned char sm[];
+__global__ void __launch_bounds__(XB_MAX_THREADS, 1)
+evolve_kernel(const __grid_constant__ DevZones zn, const __grid_constant__ DevOut out, const __grid_constant__ DevScratch scr,
+              int *counter) {
   __shared__ int s_zone;
-  ZoneMem zm;
-  carve(zm, sm, net, scr, jac_in_smem != 0);
+  zone_prologue(scr, nullptr, nullptr, nullptr);
+  ZoneScalars *zs = reinterpret_cast<ZoneScalars *>(xb_smem + c_net.lay.scal);
   for (;;) {
     if (threadIdx.x == 0) s_zone = atomicAdd(counter, 1);
     __syncthreads();
     const int iz = s_zone;
     __syncthreads();
     if (iz >= zn.nzone) break;
-    full_net_cta<STRICT>(net, ctl, zn, out, zm, iz);
+    full_net_cta<STRICT>(zn, out, iz);
     if (threadIdx.x == 0) {
-      for (int k = 0; k < 7; ++k) atomicAdd(&scr.phase[k], (unsigned long long)zm.s->ph[k]);
+      for (int k = 0; k < PH_COUNT; ++k)
+        if (k != PH_ZONES) atomicAdd(&scr.phase[k], (unsigned long long)zs->ph[k]);
       atomicAdd(&scr.phase[PH_ZONES], 1ULL);
     }
     __syncthreads();
@@ -153,50 +162,53 @@ struct ModArgs {
 };
 
 template <bool STRICT, int OP>
-__global__ void module_kernel(DevNet net, DevCtl ctl, ModArgs ma, DevScratch scr, int jac_in_smem) {
-  extern __shared__ __align__(16) unsigned char sm[];
+__global__ void __launch_bounds__(XB_MAX_THREADS, 1)
+module_kernel(const __grid_constant__ ModArgs ma, const __grid_constant__ DevScratch scr) {
   const int iz = ma.z0 + blockIdx.x;
   if (ma.mask && ma.mask[iz] == 0) return;
-  ZoneMem zm;
-  carve(zm, sm, net, scr, jac_in_smem != 0);
-  const int tid = threadIdx.x, nt = blockDim.x, ny = net.ny, N = net.msize;
-  zm.csect = ma.csect + (size_t)iz * net.nrtot;
-  zm.qkffn = ma.qk + (size_t)iz * (net.nffn + 1);
+  const DevNet &net = c_net;
+  const int tid = threadIdx.x, nt = blockDim.x, ny = net.ny, N = net.msize, ld = net.ld;
+  double *gj = ma.jac + (size_t)iz * N * N;   // caller-visible layout: msize x msize, column-major
+  // without the shared tile the kernels work in place on the caller-visible array (ld == N)
+  zone_prologue(scr, ma.csect + (size_t)iz * net.nrtot, ma.qk + (size_t)iz * (net.nffn + 1), gj);
+  ZoneMem zm = zone_mem();
   ZoneScalars *s = zm.s;
   if (OP == OP_CSECT || OP == OP_YDERIV || OP == OP_JBUILD)
     for (int k = tid; k < ny; k += nt) zm.yt[k] = ma.yt[(size_t)iz * ny + k];
   if (tid == 0) {
     for (int k = 0; k < 5; ++k) s->ktot[k] = 0;
+    for (int k = 0; k < PH_COUNT; ++k) s->ph[k] = 0;
     s->t9t = ma.t9t[iz]; s->rhot = ma.rhot[iz];
     s->xext = ma.ext[3 * iz]; s->aext = ma.ext[3 * iz + 1]; s->zext = ma.ext[3 * iz + 2];
     s->rdt = ma.diag[iz]; s->mult = ma.mult[iz];
   }
   __syncthreads();
   if (OP == OP_CSECT) {
-    cross_sect_cta<STRICT>(net, ctl, zm);
+    cross_sect_cta<STRICT>();
     if (tid == 0) ma.yet[iz] = s->yet;
   } else if (OP == OP_YDERIV) {
-    yderiv_cta<STRICT>(net, zm);
+    yderiv_cta<STRICT>();
     for (int k = tid; k < ny; k += nt) ma.ydot[(size_t)iz * ny + k] = zm.ydot[k];
   } else if (OP == OP_JBUILD) {
-    double *gj = ma.jac + (size_t)iz * N * N;
-    double *keep = zm.jac;
-    if (!jac_in_smem) zm.jac = gj;
-    jacobian_build_cta<STRICT>(net, zm, N);
-    if (jac_in_smem) for (int e = tid; e < N * N; e += nt) gj[e] = keep[e];
+    jacobian_build_cta<STRICT>();
+    if (net.tile)
+      for (int e = tid; e < N * N; e += nt) { const int j = e / N, i = e - j * N; gj[e] = zm.jac[j * ld + i]; }
   } else if (OP == OP_DECOMP) {
-    double *gj = ma.jac + (size_t)iz * N * N;
-    if (jac_in_smem) { for (int e = tid; e < N * N; e += nt) zm.jac[e] = gj[e]; __syncthreads(); }
-    else zm.jac = gj;
+    if (net.tile) {
+      for (int e = tid; e < N * N; e += nt) { const int j = e / N, i = e - j * N; zm.jac[j * ld + i] = gj[e]; }
+      __syncthreads();
+    }
     lu_cta<STRICT>(zm, N);
-    if (jac_in_smem) for (int e = tid; e < N * N; e += nt) gj[e] = zm.jac[e];
+    if (net.tile)
+      for (int e = tid; e < N * N; e += nt) { const int j = e / N, i = e - j * N; gj[e] = zm.jac[j * ld + i]; }
     for (int k = tid; k < N; k += nt) ma.indx[(size_t)iz * N + k] = zm.indx[k] + 1;  // LAPACK 1-based ipiv
     if (tid == 0) ma.info[iz] = s->info;
   } else if (OP == OP_BKSUB) {
-    zm.jac = ma.jac + (size_t)iz * N * N;  // read straight from HBM/L2: each element is used once
+    // factors are read straight from HBM/L2 (each element is used once); rdiag is not kept between calls
     for (int k = tid; k < N; k += nt) { zm.indx[k] = ma.indx[(size_t)iz * N + k] - 1; zm.rhs[k] = ma.rhs[(size_t)iz * N + k]; }
     __syncthreads();
-    bksub_cta<STRICT>(zm, N);
+    if (net.tile) bksub_block<STRICT, false>(gj, N, N, zm.indx, zm.rhs, nullptr, zm.prow);
+    else bksub_simple<STRICT>(gj, N, N, zm.indx, zm.rhs);
     for (int k = tid; k < N; k += nt) ma.rhs[(size_t)iz * N + k] = zm.rhs[k];
   }
 }
@@ -447,6 +459,15 @@ static int upload_network(xb_ctx *c) {
       d.nn[cI][r] = c->nn[cI][r].p;
     }
   }
+  {
+    std::vector<int> fn1, fif;
+    for (int k = 0; k < h.nreac[0]; ++k)
+      if (h.iffn[k] > 0) { fn1.push_back(h.ni[0][(size_t)k * 6] - 1); fif.push_back(h.iffn[k]); }
+    d.nffr = (int)fn1.size();
+    if (fn1.empty()) { fn1.push_back(0); fif.push_back(0); }
+    CUDA_TRY(c->ffr_n1.put(fn1)); CUDA_TRY(c->ffr_iffn.put(fif));
+    d.ffr_n1 = c->ffr_n1.p; d.ffr_iffn = c->ffr_iffn.p;
+  }
   CUDA_TRY(c->aa.put(h.aa)); CUDA_TRY(c->zz.put(h.zz)); CUDA_TRY(c->mex.put(h.mex)); CUDA_TRY(c->be.put(h.be));
   CUDA_TRY(c->g.put(h.g)); CUDA_TRY(c->t9i.put(h.t9i));
   std::vector<double> lng(h.g.size()), dlng(h.g.size(), 0.0);
@@ -464,6 +485,134 @@ static int upload_network(xb_ctx *c) {
 template <bool STRICT>
 static const void *evolve_fn() { return (const void *)evolve_kernel<STRICT>; }
 
+// ---- term plans ------------------------------------------------------------------------------------
+namespace {
+struct PlanRec { double a; int mu; int n[4]; int fseg; int fdest; int sseg; };
+struct PlanHost {
+  int nrec = 0, L = 0, nseg = 0, nmulti = 0, npart = 0;
+  std::vector<double> a; std::vector<uint2> nn, mc;
+  std::vector<int> seg_start, seg_dest, multi_start, multi_dest;
+};
+
+// recs sorted by segment (fseg non-decreasing, sseg non-decreasing); fdest = (destination<<1)|diag of
+// the record's fast segment; strict segments are [sseg_start[i], sseg_start[i+1]) with sseg_dest[i].
+PlanHost make_plan(const std::vector<PlanRec> &recs, int NT, int dummy, std::vector<int> sseg_start,
+                   std::vector<int> sseg_dest) {
+  PlanHost P;
+  P.nrec = (int)recs.size();
+  P.L = std::max(1, (P.nrec + NT - 1) / NT);
+  P.L = (P.L + kPlanU - 1) / kPlanU * kPlanU;
+  const size_t tot = (size_t)P.L * NT;
+  const unsigned dd = (unsigned)dummy | ((unsigned)dummy << 16);
+  P.a.assign(tot, 0.0); P.nn.assign(tot, make_uint2(dd, dd)); P.mc.assign(tot, make_uint2(0u, 0u));
+  P.nseg = (int)sseg_dest.size();
+  P.seg_start = std::move(sseg_start); P.seg_dest = std::move(sseg_dest);
+  // extent of every fast segment
+  std::vector<int> first, last;   // by fseg
+  for (int r = 0; r < P.nrec; ++r) {
+    const int g = recs[r].fseg;
+    if (g >= (int)first.size()) { first.resize(g + 1, -1); last.resize(g + 1, -1); }
+    if (first[g] < 0) first[g] = r;
+    last[g] = r;
+  }
+  int open_multi = -1;
+  for (int t = 0; t < NT; ++t) {
+    const int b = t * P.L, e = std::min(P.nrec, (t + 1) * P.L);
+    for (int r = b; r < e; ++r) {
+      const PlanRec &R = recs[r];
+      const size_t at = (size_t)(r - b) * NT + t;
+      P.a[at] = R.a;
+      P.nn[at] = make_uint2((unsigned)R.n[0] | ((unsigned)R.n[1] << 16), (unsigned)R.n[2] | ((unsigned)R.n[3] << 16));
+      unsigned ctl = 0;
+      const bool piece_end = (r + 1 == e) || recs[r + 1].fseg != R.fseg;
+      if (piece_end) {
+        int pb = r;
+        while (pb > b && recs[pb - 1].fseg == R.fseg) --pb;
+        const bool complete = (pb == first[R.fseg]) && (r == last[R.fseg]);
+        if (complete) ctl = 1u | ((unsigned)(R.fdest & 1) << 2) | ((unsigned)(R.fdest >> 1) << 3);
+        else {
+          if (open_multi != R.fseg) { P.multi_start.push_back(P.npart); P.multi_dest.push_back(R.fdest); open_multi = R.fseg; }
+          ctl = 2u | ((unsigned)P.npart << 3);
+          ++P.npart;
+        }
+      }
+      P.mc[at] = make_uint2((unsigned)R.mu, ctl);
+    }
+  }
+  P.nmulti = (int)P.multi_dest.size();
+  P.multi_start.push_back(P.npart);
+  return P;
+}
+}  // namespace
+
+static int upload_plan(xb_ctx::PlanBufs &B, DevPlan &D, const PlanHost &P) {
+  CUDA_TRY(B.a.put(P.a)); CUDA_TRY(B.nn.put(P.nn)); CUDA_TRY(B.mc.put(P.mc));
+  std::vector<int> ss(P.seg_start), sd(P.seg_dest), ms(P.multi_start), md(P.multi_dest);
+  if (sd.empty()) sd.push_back(0);
+  if (md.empty()) md.push_back(0);
+  CUDA_TRY(B.seg_start.put(ss)); CUDA_TRY(B.seg_dest.put(sd)); CUDA_TRY(B.multi_start.put(ms)); CUDA_TRY(B.multi_dest.put(md));
+  D.nrec = P.nrec; D.L = P.L; D.nseg = P.nseg; D.nmulti = P.nmulti; D.npart = P.npart;
+  D.a = B.a.p; D.nn = B.nn.p; D.mc = B.mc.p; D.seg_start = B.seg_start.p; D.seg_dest = B.seg_dest.p;
+  D.multi_start = B.multi_start.p; D.multi_dest = B.multi_dest.p;
+  return XB_OK;
+}
+
+// ydot plan: species-major, reaction class, ascending la..le (xnet_integrate.F90:409-469).
+// Jacobian plan: contributions generated in the order of the reference scatter loop
+// (xnet_jacobian_dense.F90:303-341), then grouped by element (stable): element (i0, col) of jac.
+static int build_plans(xb_ctx *c, int NT, int ld) {
+  const Network &h = c->net->h;
+  const DevNet &d = c->dn;
+  const int ny = h.ny, N = d.msize;
+  std::vector<PlanRec> ry, rj;
+  std::vector<int> ys_start, ys_dest;
+  for (int i = 0; i < ny; ++i)
+    for (int cI = 0; cI < 4; ++cI) {
+      ys_start.push_back((int)ry.size()); ys_dest.push_back(4 * i + cI);
+      for (int j = h.la[(size_t)cI * ny + i] - 1; j < h.le[(size_t)cI * ny + i]; ++j) {
+        const int k = h.mu[cI][j] - 1;
+        PlanRec R{}; R.a = h.a[cI][j]; R.mu = d.roff[cI] + k;
+        for (int r = 0; r < 4; ++r) R.n[r] = (r <= cI) ? h.ni[cI][(size_t)k * 6 + r] - 1 : ny;
+        R.fseg = i; R.fdest = i << 1; R.sseg = 4 * i + cI;
+        ry.push_back(R);
+        // Jacobian contributions of this term, slot by slot
+        for (int sl = 0; sl <= cI; ++sl) {
+          PlanRec Q{}; Q.a = R.a; Q.mu = R.mu;
+          for (int r = 0; r < 4; ++r) Q.n[r] = ny;
+          for (int r = 0; r < cI; ++r) Q.n[r] = R.n[(sl + 1 + r) % (cI + 1)];
+          const int col = R.n[sl];
+          Q.fseg = i * N + col;   // element key, replaced by a dense id below
+          rj.push_back(Q);
+        }
+      }
+    }
+  ys_start.push_back((int)ry.size());
+  for (int i = 0; i < ny; ++i) {   // every diagonal element exists (jac = mult*d + diag)
+    bool have = false;
+    for (const PlanRec &Q : rj) if (Q.fseg == i * N + i) { have = true; break; }
+    if (!have) { PlanRec Q{}; Q.a = 0.0; Q.mu = 0; for (int r = 0; r < 4; ++r) Q.n[r] = ny; Q.fseg = i * N + i; rj.push_back(Q); }
+  }
+  std::stable_sort(rj.begin(), rj.end(), [](const PlanRec &x, const PlanRec &y) { return x.fseg < y.fseg; });
+  std::vector<int> js_start, js_dest;
+  int id = -1, prev = -1;
+  for (size_t r = 0; r < rj.size(); ++r) {
+    const int key = rj[r].fseg;
+    if (key != prev) {
+      ++id; prev = key;
+      const int i0 = key / N, col = key % N;
+      js_start.push_back((int)r); js_dest.push_back(((i0 + col * ld) << 1) | (i0 == col ? 1 : 0));
+    }
+    rj[r].fseg = id; rj[r].sseg = id; rj[r].fdest = js_dest.back();
+  }
+  js_start.push_back((int)rj.size());
+  PlanHost py = make_plan(ry, NT, ny, ys_start, ys_dest), pj = make_plan(rj, NT, ny, js_start, js_dest);
+  int rc = upload_plan(c->pby, c->dn.py, py); if (rc) return rc;
+  rc = upload_plan(c->pbj, c->dn.pj, pj); if (rc) return rc;
+  c->ld = ld; c->dn.ld = ld;
+  c->npart = std::max(std::max(py.npart, pj.npart), std::max(2 * std::max(ny, c->dn.nffr), 128));
+  return XB_OK;
+}
+
 extern "C" {
 static int configure_launch(xb_ctx *c) {
   const int ny = c->dn.ny, N = c->dn.msize;
@@ -471,11 +620,17 @@ static int configure_launch(xb_ctx *c) {
   CUDA_TRY(cudaGetDeviceProperties(&prop, c->device));
   c->nsm = prop.multiProcessorCount;
   const size_t max_smem = prop.sharedMemPerBlockOptin;
-  SmemLayout L = smem_layout(ny, N, true);
-  c->jac_in_smem = (L.total + 64 <= max_smem) ? 1 : 0;
-  if (!c->jac_in_smem) L = smem_layout(ny, N, false);
-  c->smem_bytes = L.total;
-  c->threads = N <= 24 ? 64 : (N <= 64 ? 128 : 256);
+  c->threads = N <= 32 ? 64 : (N <= 64 ? 128 : XB_MAX_THREADS);
+  // Jacobian tile in shared memory (odd leading dimension) when it fits and the register-panel LU applies
+  int rc = build_plans(c, c->threads, N | 1); if (rc) return rc;
+  SmemOff L = smem_layout(ny, N, c->ld, c->npart, true);
+  c->jac_in_smem = (N <= 192 && c->threads >= ((N + 31) / 32) * 32 && (size_t)L.total + 64 <= max_smem) ? 1 : 0;
+  if (!c->jac_in_smem) {
+    rc = build_plans(c, c->threads, N); if (rc) return rc;
+    L = smem_layout(ny, N, c->ld, c->npart, false);
+  }
+  c->smem_bytes = (size_t)L.total;
+  c->dn.lay = L; c->dn.tile = c->jac_in_smem;
   const void *fn = c->ctl.arith ? evolve_fn<true>() : evolve_fn<false>();
   CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
   int per_sm = 0;
@@ -491,13 +646,15 @@ static int configure_launch(xb_ctx *c) {
   s.off_rffn = o; o += std::max(c->dn.nffn, 1);
   s.off_qkffn = o; o += c->dn.nffn + 1;
   o = (o + 15) / 16 * 16;
-  s.off_jac = o; if (!c->jac_in_smem) o += (size_t)N * N;
+  s.off_prod = o; if (c->ctl.arith) o += (size_t)std::max(c->dn.py.L, c->dn.pj.L) * c->threads;
+  o = (o + 15) / 16 * 16;
+  s.off_jac = o; if (!c->jac_in_smem) o += (size_t)N * c->ld;
   s.stride = (o + 15) / 16 * 16;
   const size_t nblocks = std::max<size_t>(c->grid, c->nzevolve);
   CUDA_TRY(c->scratch.resize(nblocks * s.stride));
   CUDA_TRY(cudaMemset(c->scratch.p, 0, nblocks * s.stride * sizeof(double)));
-  CUDA_TRY(c->phase.resize(8));
-  CUDA_TRY(cudaMemset(c->phase.p, 0, 8 * sizeof(unsigned long long)));
+  CUDA_TRY(c->phase.resize(PH_COUNT));
+  CUDA_TRY(cudaMemset(c->phase.p, 0, PH_COUNT * sizeof(unsigned long long)));
   CUDA_TRY(c->counter.resize(1));
   s.base = c->scratch.p; s.phase = c->phase.p;
   return XB_OK;
@@ -552,6 +709,15 @@ void xb_ctx_destroy(xb_ctx *c) {
   delete c;
 }
 
+// Uploads the context's zone-invariant state to constant memory.  Called, under g_launch_mu, right
+// before every launch; copy and launch are ordered on the same stream, so contexts can interleave.
+static std::mutex g_launch_mu;
+static int bind_constants(xb_ctx *c) {
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_net, &c->dn, sizeof(DevNet), 0, cudaMemcpyHostToDevice, 0));
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_ctl, &c->dc, sizeof(DevCtl), 0, cudaMemcpyHostToDevice, 0));
+  return XB_OK;
+}
+
 // ---- module-level drop-ins ------------------------------------------------------------------------
 static int module_state(xb_ctx *c) {
   const int nz = c->nzevolve, ny = c->dn.ny, N = c->dn.msize;
@@ -592,12 +758,14 @@ static int launch_module(xb_ctx *c, int zlo, int zhi, const int32_t *mask) {
   ma.yt = c->m_yt.p; ma.t9t = c->m_t9t.p; ma.rhot = c->m_rhot.p; ma.ext = c->m_ext.p; ma.yet = c->m_yet.p;
   ma.csect = c->m_csect.p; ma.qk = c->m_qk.p; ma.ydot = c->m_ydot.p; ma.jac = c->m_jac.p; ma.rhs = c->m_rhs.p;
   ma.diag = c->m_diag.p; ma.mult = c->m_mult.p; ma.indx = c->m_indx.p; ma.info = c->m_info.p;
+  std::lock_guard<std::mutex> lock(g_launch_mu);
+  { int rcb = bind_constants(c); if (rcb) return rcb; }
   if (c->ctl.arith) {
     CUDA_TRY(cudaFuncSetAttribute(module_kernel<true, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
-    module_kernel<true, OP><<<nz, c->threads, c->smem_bytes>>>(c->dn, c->dc, ma, c->scr, c->jac_in_smem);
+    module_kernel<true, OP><<<nz, c->threads, c->smem_bytes>>>(ma, c->scr);
   } else {
     CUDA_TRY(cudaFuncSetAttribute(module_kernel<false, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
-    module_kernel<false, OP><<<nz, c->threads, c->smem_bytes>>>(c->dn, c->dc, ma, c->scr, c->jac_in_smem);
+    module_kernel<false, OP><<<nz, c->threads, c->smem_bytes>>>(ma, c->scr);
   }
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
@@ -765,16 +933,19 @@ int xb_evolve_resident(xb_ctx *c, float *kernel_ms) {
   if (!c || c->nzone < 1) return fail(XB_ERR_ARG, "xb_evolve_resident: no zones uploaded");
   CUDA_TRY(cudaSetDevice(c->device));
   CUDA_TRY(cudaMemsetAsync(c->counter.p, 0, sizeof(int)));
-  CUDA_TRY(cudaMemsetAsync(c->phase.p, 0, 8 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemsetAsync(c->phase.p, 0, PH_COUNT * sizeof(unsigned long long)));
   const int grid = std::min(c->grid, c->nzone);
+  std::unique_lock<std::mutex> lock(g_launch_mu);
+  { int rcb = bind_constants(c); if (rcb) return rcb; }
   CUDA_TRY(cudaEventRecord(c->ev0));
   if (c->ctl.arith)
-    evolve_kernel<true><<<grid, c->threads, c->smem_bytes>>>(c->dn, c->dc, c->dz, c->dout, c->scr, c->counter.p, c->jac_in_smem);
+    evolve_kernel<true><<<grid, c->threads, c->smem_bytes>>>(c->dz, c->dout, c->scr, c->counter.p);
   else
-    evolve_kernel<false><<<grid, c->threads, c->smem_bytes>>>(c->dn, c->dc, c->dz, c->dout, c->scr, c->counter.p, c->jac_in_smem);
+    evolve_kernel<false><<<grid, c->threads, c->smem_bytes>>>(c->dz, c->dout, c->scr, c->counter.p);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(c->ev1));
+  lock.unlock();
   CUDA_TRY(cudaEventSynchronize(c->ev1));
   if (kernel_ms) CUDA_TRY(cudaEventElapsedTime(kernel_ms, c->ev0, c->ev1));
   return XB_OK;
@@ -816,9 +987,9 @@ int xb_evolve(xb_ctx *c, const xb_zones *zones, xb_out *out) {
 
 int xb_phase_cycles(xb_ctx *c, double *cycles) {
   if (!c || !cycles) return fail(XB_ERR_ARG, "xb_phase_cycles: null argument");
-  unsigned long long h[8];
+  unsigned long long h[PH_COUNT];
   CUDA_TRY(cudaMemcpy(h, c->phase.p, sizeof(h), cudaMemcpyDeviceToHost));
-  for (int k = 0; k < 8; ++k) cycles[k] = (double)h[k];
+  for (int k = 0; k < PH_COUNT; ++k) cycles[k] = (double)h[k];
   return XB_OK;
 }
 

@@ -12,8 +12,31 @@
 namespace xb {
 
 
+// Term plan of a segmented sum (ydot over species, Jacobian over non-zero elements).  Records are
+// sorted by (segment, reference summation order); thread t of an NT-thread CTA owns the contiguous
+// chunk [t*L, (t+1)*L) and record (t*L+k) is stored at k*NT+t, so every load is coalesced.
+//   product = (((a * csect[mu]) * y[n0]) * y[n1]) * y[n2]) * y[n3]     (missing factors: y[ny] = 1)
+//   ctl: bits 0-1 action after adding the product (0 none, 1 store to destination, 2 store partial),
+//        bit 2 = diagonal element (Jacobian), bits 3.. = destination / partial slot
+struct DevPlan {
+  int nrec, L, nseg, nmulti, npart;
+  const double *a;           // [L*NT]
+  const uint2 *nn;           // [L*NT]  4 x u16 species indices
+  const uint2 *mc;           // [L*NT]  x = csect index, y = ctl
+  const int *seg_start;      // [nseg+1] sorted-order record ranges (strict path)
+  const int *seg_dest;       // [nseg]   ydot: 4*species+class;  Jacobian: (offset<<1)|diag
+  const int *multi_start;    // [nmulti+1] partial-slot ranges of segments split over chunks
+  const int *multi_dest;     // [nmulti]  destination as in ctl>>2 (bit 0 = diag)
+};
+
+// byte offsets of the zone working set inside the CTA's dynamic shared memory
+struct SmemOff { int scal, jac, y, yo, yt, ydot, rhs, gg, rdiag, part, prow, indx, total; };
+
 struct DevNet {
-  int ny, nrtot, nffn, msize;
+  int ny, nrtot, nffn, msize, ld, nffr, tile;
+  SmemOff lay;
+  DevPlan py, pj;            // ydot and Jacobian plans
+  const int *ffr_n1, *ffr_iffn;  // [nffr] FFN reactions in reaction order: first reactant (0-based), table row (1-based)
   int nr[4], roff[4], nan[4];
   const double *rcT;         // [7][nrtot]  REACLIB coefficients, coefficient-major (coalesced)
   const int *ni;             // [nrtot][6]  nuclei of each reaction, 1-based, 0 = blank
@@ -58,11 +81,18 @@ struct DevOut {
 struct DevScratch {
   double *base;            // [ncta][stride]
   size_t stride;           // doubles per CTA
-  size_t off_csect, off_rffn, off_qkffn, off_jac;  // offsets (doubles)
-  unsigned long long *phase;  // [8] cycle counters (rates,yderiv,jac,lu,bksub,other,total,zones)
+  size_t off_csect, off_rffn, off_qkffn, off_jac, off_prod;  // offsets (doubles)
+  unsigned long long *phase;  // [PH_COUNT] cycle counters, see enum Phase
 };
 
-enum Phase { PH_RATES = 0, PH_YDERIV, PH_JAC, PH_LU, PH_BKSUB, PH_OTHER, PH_TOTAL, PH_ZONES };
+// Zone-invariant state lives in constant memory (uploaded before every launch of a context): device
+// code reads it through the constant bank instead of chasing kernel-parameter pointers.
+__constant__ DevNet c_net;
+__constant__ DevCtl c_ctl;
+extern __shared__ __align__(16) unsigned char xb_smem[];
+
+enum Phase { PH_RATES = 0, PH_YDERIV, PH_JAC, PH_LU, PH_BKSUB, PH_OTHER, PH_TOTAL, PH_ZONES,
+             PH_LU_PANEL, PH_LU_SWAP, PH_LU_GEMM, PH_SPARE, PH_COUNT };
 
 // ---------------------------------------------------------------------------------------------
 // Arithmetic policy.  STRICT: every product and sum individually rounded (no FMA contraction), so

@@ -21,20 +21,16 @@ struct Math {
   }
   static __device__ __forceinline__ double log10(double x) { return STRICT ? pm_log10(x) : ::log10(x); }
   static __device__ __forceinline__ double pow10(double x) { return STRICT ? pm_pow10(x) : pow(10.0, x); }
-  // t09(3,4,6,7) = T9^(-1/3), T9^(1/3), T9^(5/3), ln T9   (xnet_integrate.F90:650-656)
-  static __device__ __forceinline__ void t9_powers(double t9, double *t09) {
+  // t09(3,4,6,7) = T9^(-1/3), T9^(1/3), T9^(5/3), ln T9   (xnet_integrate.F90:650-656); which = 0..3
+  static __device__ __noinline__ double t9_power(double t9, int which) {
     if (STRICT) {
       const double l = pm_log(t9);
-      t09[2] = pm_exp(__dmul_rn(-1.0 / 3.0, l));
-      t09[3] = pm_exp(__dmul_rn(1.0 / 3.0, l));
-      t09[5] = pm_exp(__dmul_rn(5.0 / 3.0, l));
-      t09[6] = l;
-    } else {
-      t09[2] = pow(t9, -1.0 / 3.0);
-      t09[3] = pow(t9, 1.0 / 3.0);
-      t09[5] = pow(t9, 5.0 / 3.0);
-      t09[6] = log(t9);
+      if (which == 3) return l;
+      const double e = (which == 0) ? -1.0 / 3.0 : (which == 1) ? 1.0 / 3.0 : 5.0 / 3.0;
+      return pm_exp(__dmul_rn(e, l));
     }
+    if (which == 3) return log(t9);
+    return pow(t9, (which == 0) ? -1.0 / 3.0 : (which == 1) ? 1.0 / 3.0 : 5.0 / 3.0);
   }
 };
 

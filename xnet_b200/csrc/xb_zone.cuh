@@ -4,6 +4,7 @@
 #pragma once
 #include "xb_device.cuh"
 #include "xb_math.cuh"
+#include "xb_lu.cuh"
 
 namespace xb {
 
@@ -14,25 +15,60 @@ struct ZoneScalars {
   double xext, aext, zext, rho_scale;
   double rdt, mult, xtot_init, enm, enold, edot, sqnu;
   double t9rhs, dt9, relt9;
+  double red[4];             // results of block-wide reductions
+  double t09[4];             // T9^(-1/3), T9^(1/3), T9^(5/3), ln T9 of the current rate evaluation
   const double *th, *t9h, *rhoh;
+  double *g_csect, *g_rffn, *g_qkffn, *g_prod, *g_jac;  // per-CTA global scratch (set in the kernel prologue)
   int nh, has_scale, nt, ntt, nto, ints, iweak;
   int kmon[5], ktot[5];
   int inr, its, flag, piv, info;
-  long long ph[8];
+  long long ph[12];          // see enum Phase
   long long tmark;
 };
 
 // Views of the zone working set
 struct ZoneMem {
   ZoneScalars *s;
-  double *jac;      // [N][N] column-major (shared or global scratch)
-  double *y, *yo, *yt, *ydot, *rhs;  // [ny] ... rhs [N]
+  double *jac;      // [N columns][ld] column-major (shared tile, or global scratch for large N)
+  int ld, tile;     // leading dimension (odd); tile = 1 when the Jacobian is the shared-memory tile
+  double *y, *yo, *yt, *ydot, *rhs;  // [ny]; yt has ny+1 entries (yt[ny] = 1); rhs [N]
+  double *part;     // partial sums of the term plans / scratch of block reductions
+  double *prow;     // [2][6][12] published pivot candidates of the LU panel; [2][32] block values of the solve
+  double *rdiag;    // [N] reciprocal diagonal of U (fast arithmetic only)
+  double *prod;     // per-CTA global scratch for the strict term products
   double *gg;       // [ny+1]
   double *csect;    // [nrtot] (global scratch)
   double *rffn;     // [nffn]
   double *qkffn;    // [nffn+1]
   int *indx;        // [N] 0-based pivot rows
 };
+
+// The zone working set is addressed from the dynamic shared-memory symbol with offsets that the host
+// placed in constant memory, so every access compiles to LDS/STS with 32-bit addressing.
+__device__ __forceinline__ ZoneMem zone_mem() {
+  const SmemOff &L = c_net.lay;
+  ZoneMem zm;
+  zm.s = reinterpret_cast<ZoneScalars *>(xb_smem + L.scal);
+  zm.ld = c_net.ld; zm.tile = c_net.tile;
+  zm.jac = c_net.tile ? reinterpret_cast<double *>(xb_smem + L.jac) : zm.s->g_jac;
+  zm.y = reinterpret_cast<double *>(xb_smem + L.y);
+  zm.yo = reinterpret_cast<double *>(xb_smem + L.yo);
+  zm.yt = reinterpret_cast<double *>(xb_smem + L.yt);
+  zm.ydot = reinterpret_cast<double *>(xb_smem + L.ydot);
+  zm.rhs = reinterpret_cast<double *>(xb_smem + L.rhs);
+  zm.gg = reinterpret_cast<double *>(xb_smem + L.gg);
+  zm.rdiag = reinterpret_cast<double *>(xb_smem + L.rdiag);
+  zm.part = reinterpret_cast<double *>(xb_smem + L.part);
+  zm.prow = reinterpret_cast<double *>(xb_smem + L.prow);
+  zm.indx = reinterpret_cast<int *>(xb_smem + L.indx);
+  zm.csect = zm.s->g_csect; zm.rffn = zm.s->g_rffn; zm.qkffn = zm.s->g_qkffn; zm.prod = zm.s->g_prod;
+  return zm;
+}
+#define XB_ZONE_PROLOGUE                \
+  const DevNet &net = c_net;            \
+  const DevCtl &ctl = c_ctl;            \
+  ZoneMem zm = zone_mem();              \
+  (void)net; (void)ctl;
 
 #define XB_PHASE_BEGIN(zm) \
   if (threadIdx.x == 0) (zm).s->tmark = clock64();
@@ -74,31 +110,103 @@ __device__ void t9rhofind(const ZoneScalars *s, double tf, int *nf, double *t9f,
   }
 }
 
+// --- block-wide helpers ----------------------------------------------------------------------------
+// Two sums over k < n of terms produced by f(k, ta, tb).  STRICT: terms are formed in parallel and
+// added by one thread in ascending k from 0.0 (the reference's sequential accumulation, bit for bit);
+// FAST: shuffle tree.  Results land in out2[0..1] (shared) and are visible to every thread on return.
+template <bool STRICT, class F>
+__device__ __forceinline__ void block_sum2(const int n, F f, double *buf, double *out2) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (STRICT) {
+    for (int k = tid; k < n; k += nt) { double ta, tb; f(k, ta, tb); buf[k] = ta; buf[n + k] = tb; }
+    __syncthreads();
+    if (tid < 2) {
+      const double *b = buf + tid * n;
+      double s = 0.0;
+      for (int k = 0; k < n; ++k) s = __dadd_rn(s, b[k]);
+      out2[tid] = s;
+    }
+    __syncthreads();
+  } else {
+    double sa = 0.0, sb = 0.0;
+    for (int k = tid; k < n; k += nt) { double ta, tb; f(k, ta, tb); sa += ta; sb += tb; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      sa += __shfl_xor_sync(kFull, sa, off);
+      sb += __shfl_xor_sync(kFull, sb, off);
+    }
+    const int w = tid >> 5, nw = nt >> 5;
+    if ((tid & 31) == 0) { buf[w] = sa; buf[32 + w] = sb; }
+    __syncthreads();
+    if (tid < 32) {
+      double va = (tid < nw) ? buf[tid] : 0.0, vb = (tid < nw) ? buf[32 + tid] : 0.0;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        va += __shfl_xor_sync(kFull, va, off);
+        vb += __shfl_xor_sync(kFull, vb, off);
+      }
+      if (tid == 0) { out2[0] = va; out2[1] = vb; }
+    }
+    __syncthreads();
+  }
+}
+
+// First index of the maximum of f(k), k < n (Fortran maxloc).  Result in out[0] (value) and *iout.
+template <class F>
+__device__ __forceinline__ void block_argmax_first(const int n, F f, double *buf, double *out, int *iout) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double bv = -1.0; int bi = 0x7fffffff;
+  for (int k = tid; k < n; k += nt) { const double v = f(k); if (v > bv) { bv = v; bi = k; } }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double ov = __shfl_xor_sync(kFull, bv, off);
+    const int oi = __shfl_xor_sync(kFull, bi, off);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  const int w = tid >> 5, nw = nt >> 5;
+  if ((tid & 31) == 0) { buf[w] = bv; reinterpret_cast<int *>(buf + 32)[2 * w] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    double v = buf[0]; int i = reinterpret_cast<int *>(buf + 32)[0];
+    for (int q = 1; q < nw; ++q) {
+      const double ov = buf[q]; const int oi = reinterpret_cast<int *>(buf + 32)[2 * q];
+      if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+    out[0] = v; *iout = i;
+  }
+  __syncthreads();
+}
+
 // --- cross_sect (xnet_integrate.F90:569-927) incl. update_eos' Ye (xnet_abundances.F90:137-166),
 //     update_iweak (:300-311), partf (xnet_data.F90:217-245), ffn_rate (xnet_ffn.F90:199-299) ------
 template <bool STRICT>
-__device__ void cross_sect_cta(const DevNet &net, const DevCtl &ctl, ZoneMem &zm) {
+__device__ __noinline__ void cross_sect_cta() {
   using A = Ar<STRICT>;
   using Mx = Math<STRICT>;
+  XB_ZONE_PROLOGUE
   ZoneScalars *s = zm.s;
   const int tid = threadIdx.x, nt = blockDim.x, ny = net.ny;
   const double t9t = s->t9t, rhot = s->rhot;
 
+  {
+    // Ye from the composition moments (xnet_abundances.F90:137-166); sums in the reference order
+    const double *aa = net.aa, *zz = net.zz, *yt = zm.yt;
+    block_sum2<STRICT>(ny, [&](int k, double &ta, double &tb) { ta = A::mul(yt[k], aa[k]); tb = A::mul(yt[k], zz[k]); },
+                       zm.part, s->red);
+  }
   if (tid == 0) {
-    // Ye from the composition moments; sequential sums as in the reference
-    double yext = A::div(s->xext, s->aext), atot = 0.0, ztot = 0.0;
-    for (int k = 0; k < ny; ++k) {
-      double yk = zm.yt[k];
-      atot = A::mad(yk, net.aa[k], atot);
-      ztot = A::mad(yk, net.zz[k], ztot);
-    }
-    atot = A::add(atot, s->xext);
-    ztot = A::mad(yext, s->zext, ztot);
+    const double yext = A::div(s->xext, s->aext);
+    const double atot = A::add(s->red[0], s->xext);
+    const double ztot = A::mad(yext, s->zext, s->red[1]);
     s->yet = A::div(ztot, atot);
     s->cv = 0.0; s->etae = 0.0; s->detaedt9 = 0.0;
     s->iweak = (t9t < 0.01 && ctl.iweak0 != 0) ? -abs(ctl.iweak0) : ctl.iweak0;
     s->ktot[4] += 1;
   }
+  // temperature powers: four threads of different warps evaluate one transcendental each
+  // t09(3,4,6,7) = T9^(-1/3), T9^(1/3), T9^(5/3), ln T9   (xnet_integrate.F90:650-656)
+  if ((tid & 31) == 0)
+    for (int which = tid >> 5; which < 4; which += nt >> 5) s->t09[which] = Mx::t9_power(t9t, which);
   // partition functions
   {
     int ii = 1;
@@ -153,7 +261,7 @@ __device__ void cross_sect_cta(const DevNet &net, const DevCtl &ctl, ZoneMem &zm
   double t09[7];
   t09[0] = 1.0;
   t09[1] = A::div(1.0, t9t);
-  Mx::t9_powers(t9t, t09);  // fills [2]=t9^-1/3, [3]=t9^1/3, [5]=t9^5/3, [6]=ln t9
+  t09[2] = s->t09[0]; t09[3] = s->t09[1]; t09[5] = s->t09[2]; t09[6] = s->t09[3];
   t09[4] = t9t;
   const double rho2 = A::mul(rhot, rhot), rho3 = A::mul(rho2, rhot);
   for (int k = tid; k < net.nrtot; k += nt) {
@@ -195,230 +303,196 @@ __device__ void cross_sect_cta(const DevNet &net, const DevCtl &ctl, ZoneMem &zm
   __syncthreads();
 }
 
-// --- yderiv (xnet_integrate.F90:409-469): one thread per species, ascending la..le order --------
+// --- term plans -------------------------------------------------------------------------------------
+// product of one record:  (((a*csect[mu])*y[n0])*y[n1])*y[n2])*y[n3]   (absent factors are y[ny]=1)
+constexpr int kPlanU = 8;   // records in flight per thread (host pads L to a multiple)
+
 template <bool STRICT>
-__device__ void yderiv_cta(const DevNet &net, ZoneMem &zm) {
+__device__ __forceinline__ double plan_mul(const double a, const double c, const uint2 nn, const double *y) {
   using A = Ar<STRICT>;
-  const int ny = net.ny;
-  const double *yt = zm.yt, *cs = zm.csect;
-  for (int i0 = threadIdx.x; i0 < ny; i0 += blockDim.x) {
-    double s[4];
+  double v = A::mul(a, c);
+  v = A::mul(v, y[nn.x & 0xffffu]);
+  v = A::mul(v, y[nn.x >> 16]);
+  v = A::mul(v, y[nn.y & 0xffffu]);
+  v = A::mul(v, y[nn.y >> 16]);
+  return v;
+}
+
+// FAST: every thread reduces its chunk; `flush(ctl, acc)` is called at the end of each piece.  Loads of
+// kPlanU records are issued together (two L2 round trips per batch instead of per record).
+template <class Flush>
+__device__ __forceinline__ void plan_run_fast(const DevPlan &P, const double *cs, const double *y, Flush flush) {
+  const double *__restrict__ pa = P.a;
+  const uint2 *__restrict__ pn = P.nn;
+  const uint2 *__restrict__ pm = P.mc;
+  const int L = P.L, nt = blockDim.x;
+  int idx = threadIdx.x;
+  double acc = 0.0;
+  for (int k0 = 0; k0 < L; k0 += kPlanU) {
+    double a[kPlanU], c[kPlanU];
+    uint2 nn[kPlanU], mc[kPlanU];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int la = net.la[c * ny + i0] - 1, le = net.le[c * ny + i0];
-      double sc = 0.0;
-      for (int j = la; j < le; ++j) {
-        double t = A::mul(A::mul(net.a[c][j], cs[net.mu[c][j]]), yt[net.nn[c][0][j]]);
-        if (c >= 1) t = A::mul(t, yt[net.nn[c][1][j]]);
-        if (c >= 2) t = A::mul(t, yt[net.nn[c][2][j]]);
-        if (c >= 3) t = A::mul(t, yt[net.nn[c][3][j]]);
-        sc = A::add(sc, t);
-      }
-      s[c] = sc;
+    for (int u = 0; u < kPlanU; ++u) { a[u] = __ldg(pa + idx + u * nt); nn[u] = __ldg(pn + idx + u * nt); mc[u] = __ldg(pm + idx + u * nt); }
+#pragma unroll
+    for (int u = 0; u < kPlanU; ++u) c[u] = __ldcg(cs + mc[u].x);
+#pragma unroll
+    for (int u = 0; u < kPlanU; ++u) {
+      acc += plan_mul<false>(a[u], c[u], nn[u], y);
+      if (mc[u].y & 3u) { flush(mc[u].y, acc); acc = 0.0; }
     }
-    zm.ydot[i0] = A::add(A::add(A::add(s[0], s[1]), s[2]), s[3]);
+    idx += kPlanU * nt;
   }
-  if (threadIdx.x == 0) zm.s->ktot[3] += 1;
+}
+
+// STRICT: products of all records to the per-CTA scratch in sorted order (thread t owns [t*L, (t+1)*L))
+__device__ __forceinline__ void plan_products_strict(const DevPlan &P, const double *cs, const double *y, double *prod) {
+  const double *__restrict__ pa = P.a;
+  const uint2 *__restrict__ pn = P.nn;
+  const uint2 *__restrict__ pm = P.mc;
+  const int L = P.L, nt = blockDim.x, tid = threadIdx.x;
+  double *out = prod + (size_t)tid * L;
+  for (int k0 = 0; k0 < L; k0 += kPlanU) {
+    double a[kPlanU], c[kPlanU];
+    uint2 nn[kPlanU], mc[kPlanU];
+#pragma unroll
+    for (int u = 0; u < kPlanU; ++u) { const int idx = (k0 + u) * nt + tid; a[u] = __ldg(pa + idx); nn[u] = __ldg(pn + idx); mc[u] = __ldg(pm + idx); }
+#pragma unroll
+    for (int u = 0; u < kPlanU; ++u) c[u] = __ldcg(cs + mc[u].x);
+#pragma unroll
+    for (int u = 0; u < kPlanU; ++u) out[k0 + u] = plan_mul<true>(a[u], c[u], nn[u], y);
+  }
+}
+
+// --- yderiv (xnet_integrate.F90:409-469): ydot_i = sum over the species' terms -----------------------
+// FAST: chunked segmented reduction; segments cut by a chunk boundary are finished from per-chunk
+// partials in chunk order (deterministic).  STRICT: products in parallel, then one thread per species
+// adds them in the reference order, per reaction class, ((s1+s2)+s3)+s4.
+template <bool STRICT>
+__device__ __noinline__ void yderiv_cta() {
+  XB_ZONE_PROLOGUE
+  const DevPlan &P = net.py;
+  const int tid = threadIdx.x, nt = blockDim.x, ny = net.ny;
+  double *ydot = zm.ydot, *part = zm.part;
+  if (STRICT) {
+    plan_products_strict(P, zm.csect, zm.yt, zm.prod);
+    __syncthreads();
+    const double *prod = zm.prod;
+    for (int i = tid; i < ny; i += nt) {
+      double s[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        double sc = 0.0;
+        for (int q = P.seg_start[4 * i + c]; q < P.seg_start[4 * i + c + 1]; ++q) sc = __dadd_rn(sc, __ldcg(prod + q));
+        s[c] = sc;
+      }
+      ydot[i] = __dadd_rn(__dadd_rn(__dadd_rn(s[0], s[1]), s[2]), s[3]);
+    }
+  } else {
+    plan_run_fast(P, zm.csect, zm.yt, [&](unsigned ctl, double acc) {
+      if ((ctl & 3u) == 1u) ydot[ctl >> 3] = acc; else part[ctl >> 3] = acc;
+    });
+    __syncthreads();
+    for (int m = tid; m < P.nmulti; m += nt) {
+      double sm = 0.0;
+      for (int q = P.multi_start[m]; q < P.multi_start[m + 1]; ++q) sm += part[q];
+      ydot[P.multi_dest[m] >> 1] = sm;
+    }
+  }
+  if (tid == 0) zm.s->ktot[3] += 1;
   __syncthreads();
 }
 
-// --- jacobian_build + jacobian_scale (xnet_jacobian_dense.F90:183-200, 303-341) ----------------
-// Thread i0 owns row i0 of J (= column i0 of dydotdy), accumulates its terms in reference order,
-// then applies jac = mult*dydotdy^T + diag*I in place.  No atomics.
-template <bool STRICT>
-__device__ void jacobian_build_cta(const DevNet &net, ZoneMem &zm, int N) {
-  using A = Ar<STRICT>;
-  const int ny = net.ny;
-  double *J = zm.jac;
-  const double *yt = zm.yt, *cs = zm.csect;
+// --- jacobian_build + jacobian_scale (xnet_jacobian_dense.F90:183-200, 303-341) ----------------------
+// jac(i,j) = mult * sum_of_contributions(d ydot_i / d y_j) [+ diag on the diagonal], written once per
+// non-zero element straight into the tile; no atomics, contributions added in the reference order.
+template <bool STRICT, bool TILE>
+__device__ __forceinline__ void jacobian_build_impl(const DevNet &net, const ZoneMem &zm, double *J) {
+  if (TILE) XB_ASSUME_SHARED(J);
+  const DevPlan &P = net.pj;
+  const int tid = threadIdx.x, nt = blockDim.x, N = net.msize, ld = zm.ld;
   const double diag = zm.s->rdt, mult = zm.s->mult;
-  for (int e = threadIdx.x; e < N * N; e += blockDim.x) J[e] = 0.0;
-  __syncthreads();
-  for (int i0 = threadIdx.x; i0 < ny; i0 += blockDim.x) {
-    {
-      const int la = net.la[0 * ny + i0] - 1, le = net.le[0 * ny + i0];
-      for (int j = la; j < le; ++j) {
-        const double b = A::mul(net.a[0][j], cs[net.mu[0][j]]);
-        double *p = &J[(size_t)net.nn[0][0][j] * N + i0];
-        *p = A::add(*p, b);
-      }
+  double *part = zm.part;
+  {
+    const int n2 = (N * ld) >> 1;
+    double2 *J2 = reinterpret_cast<double2 *>(J);
+    for (int e = tid; e < n2; e += nt) J2[e] = make_double2(0.0, 0.0);
+    if (tid == 0 && ((N * ld) & 1)) J[N * ld - 1] = 0.0;
+  }
+  if (STRICT) {
+    plan_products_strict(P, zm.csect, zm.yt, zm.prod);
+    __syncthreads();
+    const double *prod = zm.prod;
+    for (int e = tid; e < P.nseg; e += nt) {
+      double sc = 0.0;
+      for (int q = P.seg_start[e]; q < P.seg_start[e + 1]; ++q) sc = __dadd_rn(sc, __ldcg(prod + q));
+      const int d = P.seg_dest[e];
+      double v = __dmul_rn(mult, sc);
+      if (d & 1) v = __dadd_rn(v, diag);
+      J[d >> 1] = v;
     }
-    {
-      const int la = net.la[1 * ny + i0] - 1, le = net.le[1 * ny + i0];
-      for (int j = la; j < le; ++j) {
-        const double b = A::mul(net.a[1][j], cs[net.mu[1][j]]);
-        const int n1 = net.nn[1][0][j], n2 = net.nn[1][1][j];
-        double *p1 = &J[(size_t)n1 * N + i0];
-        *p1 = A::add(*p1, A::mul(b, yt[n2]));
-        double *p2 = &J[(size_t)n2 * N + i0];
-        *p2 = A::add(*p2, A::mul(b, yt[n1]));
-      }
-    }
-    {
-      const int la = net.la[2 * ny + i0] - 1, le = net.le[2 * ny + i0];
-      for (int j = la; j < le; ++j) {
-        const double b = A::mul(net.a[2][j], cs[net.mu[2][j]]);
-        const int n1 = net.nn[2][0][j], n2 = net.nn[2][1][j], n3 = net.nn[2][2][j];
-        double *p1 = &J[(size_t)n1 * N + i0];
-        *p1 = A::add(*p1, A::mul(A::mul(b, yt[n2]), yt[n3]));
-        double *p2 = &J[(size_t)n2 * N + i0];
-        *p2 = A::add(*p2, A::mul(A::mul(b, yt[n3]), yt[n1]));
-        double *p3 = &J[(size_t)n3 * N + i0];
-        *p3 = A::add(*p3, A::mul(A::mul(b, yt[n1]), yt[n2]));
-      }
-    }
-    {
-      const int la = net.la[3 * ny + i0] - 1, le = net.le[3 * ny + i0];
-      for (int j = la; j < le; ++j) {
-        const double b = A::mul(net.a[3][j], cs[net.mu[3][j]]);
-        const int n1 = net.nn[3][0][j], n2 = net.nn[3][1][j], n3 = net.nn[3][2][j], n4 = net.nn[3][3][j];
-        double *p1 = &J[(size_t)n1 * N + i0];
-        *p1 = A::add(*p1, A::mul(A::mul(A::mul(b, yt[n2]), yt[n3]), yt[n4]));
-        double *p2 = &J[(size_t)n2 * N + i0];
-        *p2 = A::add(*p2, A::mul(A::mul(A::mul(b, yt[n3]), yt[n4]), yt[n1]));
-        double *p3 = &J[(size_t)n3 * N + i0];
-        *p3 = A::add(*p3, A::mul(A::mul(A::mul(b, yt[n4]), yt[n1]), yt[n2]));
-        double *p4 = &J[(size_t)n4 * N + i0];
-        *p4 = A::add(*p4, A::mul(A::mul(A::mul(b, yt[n1]), yt[n2]), yt[n3]));
-      }
-    }
-    // scale row i0:  J(i0,j) = mult*d(j,i0) (+ diag on the diagonal)
-    for (int j = 0; j < N; ++j) {
-      double v = A::mul(mult, J[(size_t)j * N + i0]);
-      if (j == i0) v = A::add(v, diag);
-      J[(size_t)j * N + i0] = v;
+  } else {
+    __syncthreads();  // zero fill complete before the scattered stores
+    plan_run_fast(P, zm.csect, zm.yt, [&](unsigned ctl, double acc) {
+      if ((ctl & 3u) == 1u) J[ctl >> 3] = fma(mult, acc, (ctl & 4u) ? diag : 0.0);
+      else part[ctl >> 3] = acc;
+    });
+    __syncthreads();
+    for (int m = tid; m < P.nmulti; m += nt) {
+      double sm = 0.0;
+      for (int q = P.multi_start[m]; q < P.multi_start[m + 1]; ++q) sm += part[q];
+      const int d = P.multi_dest[m];
+      J[d >> 1] = fma(mult, sm, (d & 1) ? diag : 0.0);
     }
   }
-  if (threadIdx.x == 0) zm.s->ktot[2] += 1;
+  if (tid == 0) zm.s->ktot[2] += 1;
   __syncthreads();
 }
-
-// --- LU with row partial pivoting (jacobian_decomp -> DGETRF, tools/LAPACK/dgetrf2.f) -----------
-// Right-looking, column at a time.  Every element receives its updates a(i,j) -= l(i,k)*u(k,j) in
-// ascending k and L is scaled by the reciprocal of the pivot, exactly the operation sequence of
-// the recursive LAPACK algorithm, so STRICT mode reproduces DGETRF bit for bit (pivot = first
-// largest |a|, IDAMAX semantics).
 template <bool STRICT>
-__device__ void lu_cta(ZoneMem &zm, int N) {
-  using A = Ar<STRICT>;
-  double *J = zm.jac;
-  ZoneScalars *s = zm.s;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  if (tid == 0) s->info = 0;
-  for (int k = 0; k < N; ++k) {
-    // pivot search by warp 0
-    if (tid < 32) {
-      double best = -1.0; int bi = k;
-      for (int i = k + tid; i < N; i += 32) {
-        double v = fabs(J[(size_t)k * N + i]);
-        if (v > best) { best = v; bi = i; }
-      }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        double ob = __shfl_down_sync(0xffffffffu, best, off);
-        int oi = __shfl_down_sync(0xffffffffu, bi, off);
-        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-      }
-      if (tid == 0) {
-        s->piv = bi;
-        zm.indx[k] = bi;
-        if (best == 0.0 && s->info == 0) s->info = k + 1;
-      }
-    }
-    __syncthreads();
-    const int p = s->piv;
-    const double pv = J[(size_t)k * N + p];
-    // row interchange over all columns
-    if (p != k) {
-      for (int j = tid; j < N; j += nt) {
-        double a = J[(size_t)j * N + k], b = J[(size_t)j * N + p];
-        J[(size_t)j * N + k] = b; J[(size_t)j * N + p] = a;
-      }
-    }
-    __syncthreads();
-    if (pv != 0.0) {
-      // scale the column below the diagonal
-      if (fabs(pv) >= 2.2250738585072014e-308) {
-        const double r = A::div(1.0, pv);
-        for (int i = k + 1 + tid; i < N; i += nt) J[(size_t)k * N + i] = A::mul(r, J[(size_t)k * N + i]);
-      } else {
-        for (int i = k + 1 + tid; i < N; i += nt) J[(size_t)k * N + i] = A::div(J[(size_t)k * N + i], pv);
-      }
-    }
-    __syncthreads();
-    // rank-1 update of the trailing block
-    const int m = N - k - 1;
-    if (m > 0) {
-      const double *lcol = &J[(size_t)k * N + k + 1];
-      for (int e = tid; e < m * m; e += nt) {
-        const int jj = e / m, ii = e - jj * m;
-        double *a = &J[(size_t)(k + 1 + jj) * N + k + 1 + ii];
-        *a = A::nmad(lcol[ii], J[(size_t)(k + 1 + jj) * N + k], *a);
-      }
-    }
-    __syncthreads();
-  }
+__device__ __noinline__ void jacobian_build_cta() {
+  XB_ZONE_PROLOGUE
+  if (net.tile) jacobian_build_impl<STRICT, true>(net, zm, zm.jac);
+  else jacobian_build_impl<STRICT, false>(net, zm, zm.jac);
 }
 
-// --- back-substitution (jacobian_bksub -> DGETRS, tools/LAPACK/dgetrs.f) ------------------------
 template <bool STRICT>
-__device__ void bksub_cta(ZoneMem &zm, int N) {
-  using A = Ar<STRICT>;
-  const double *J = zm.jac;
-  double *b = zm.rhs;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  if (tid == 0) {
-    for (int i = 0; i < N; ++i) {
-      const int p = zm.indx[i];
-      if (p != i) { double t = b[i]; b[i] = b[p]; b[p] = t; }
-    }
-  }
-  __syncthreads();
-  for (int k = 0; k < N; ++k) {  // L, unit diagonal
-    const double bk = b[k];
-    if (bk != 0.0)
-      for (int i = k + 1 + tid; i < N; i += nt) b[i] = A::nmad(bk, J[(size_t)k * N + i], b[i]);
-    __syncthreads();
-  }
-  for (int k = N - 1; k >= 0; --k) {  // U
-    double bk = b[k];
-    if (bk != 0.0) {
-      bk = A::div(bk, J[(size_t)k * N + k]);
-      __syncthreads();
-      if (tid == 0) b[k] = bk;
-      for (int i = tid; i < k; i += nt) b[i] = A::nmad(bk, J[(size_t)k * N + i], b[i]);
-    } else {
-      __syncthreads();
-    }
-    __syncthreads();
-  }
+__device__ __forceinline__ void lu_cta(const ZoneMem &zm, const int N) {
+  if (zm.tile) lu_tile<STRICT>(zm.jac, zm.ld, N, zm.indx, &zm.s->info, zm.prow, zm.rdiag, zm.s->ph + PH_LU_PANEL);
+  else { lu_simple<STRICT>(zm.jac, zm.ld, N, zm.indx, &zm.s->info, &zm.s->piv); }
+}
+template <bool STRICT>
+__device__ __forceinline__ void bksub_cta(const ZoneMem &zm, const int N) {
+  if (zm.tile) bksub_block<STRICT, true>(zm.jac, zm.ld, N, zm.indx, zm.rhs, zm.rdiag, zm.prow);
+  else bksub_simple<STRICT>(zm.jac, zm.ld, N, zm.indx, zm.rhs);
 }
 
 // --- step_be: Newton-Raphson loop (xnet_integrate_be.F90:233-482) -------------------------------
 template <bool STRICT>
-__device__ void step_be_cta(const DevNet &net, const DevCtl &ctl, ZoneMem &zm) {
+__device__ __noinline__ void step_be_cta() {
   using A = Ar<STRICT>;
+  XB_ZONE_PROLOGUE
   ZoneScalars *s = zm.s;
   const int tid = threadIdx.x, nt = blockDim.x, ny = net.ny, N = net.msize;
   if (s->inr != 0) return;
-  if (tid == 0) {
-    double s1 = 0.0;
-    for (int k = 0; k < ny; ++k) s1 = A::mad(net.aa[k], zm.y[k], s1);
-    s->xtot_init = A::sub(A::add(s1, s->xext), 1.0);
-    s->rdt = A::div(1.0, s->tdel);
-    s->mult = -1.0;
+  {
+    const double *aa = net.aa, *y = zm.y;
+    block_sum2<STRICT>(ny, [&](int k, double &ta, double &tb) { ta = A::mul(aa[k], y[k]); tb = 0.0; }, zm.part, s->red);
+    if (tid == 0) {
+      s->xtot_init = A::sub(A::add(s->red[0], s->xext), 1.0);
+      s->rdt = A::div(1.0, s->tdel);
+      s->mult = -1.0;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   for (int kit = 1; kit <= ctl.kitmx; ++kit) {
     const bool rebuild = ((kit - 1) % ctl.ijac) == 0;
     const bool eval_rates = (ctl.iheat > 0) ? true : (kit == 1 && s->nh > 1);
     XB_PHASE_BEGIN(zm);
-    if (eval_rates) cross_sect_cta<STRICT>(net, ctl, zm);
+    if (eval_rates) cross_sect_cta<STRICT>();
     XB_PHASE_END(zm, PH_RATES);
-    yderiv_cta<STRICT>(net, zm);
+    yderiv_cta<STRICT>();
     XB_PHASE_END(zm, PH_YDERIV);
     if (rebuild) {
-      jacobian_build_cta<STRICT>(net, zm, N);
+      jacobian_build_cta<STRICT>();
       XB_PHASE_END(zm, PH_JAC);
       lu_cta<STRICT>(zm, N);
       XB_PHASE_END(zm, PH_LU);
@@ -432,20 +506,26 @@ __device__ void step_be_cta(const DevNet &net, const DevCtl &ctl, ZoneMem &zm) {
     __syncthreads();
     bksub_cta<STRICT>(zm, N);
     XB_PHASE_END(zm, PH_BKSUB);
+    {
+      const double *aa = net.aa;
+      const double ymin = ctl.ymin;
+      double *yt = zm.yt;
+      const double *rhs = zm.rhs;
+      block_sum2<STRICT>(ny, [&](int k, double &ta, double &tb) {
+        const double dy = rhs[k];
+        const double ytmp = A::add(yt[k], dy);
+        double rel, ynew;
+        if (ytmp < ymin) { ynew = 0.0; rel = 0.0; }
+        else { ynew = ytmp; rel = fabs(A::div(dy, ytmp)); }
+        yt[k] = ynew;
+        ta = rel;
+        tb = A::mul(aa[k], ynew);
+      }, zm.part, s->red);
+    }
     if (tid == 0) {
-      double s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      for (int k = 0; k < ny; ++k) {
-        double dy = zm.rhs[k];
-        double ytmp = A::add(zm.yt[k], dy), rel;
-        if (ytmp < ctl.ymin) { dy = -zm.yt[k]; zm.yt[k] = 0.0; rel = 0.0; }
-        else { zm.yt[k] = ytmp; rel = fabs(A::div(dy, ytmp)); }
-        s1 = A::add(s1, rel);
-        s2 = A::mad(net.aa[k], dy, s2);
-        s3 = A::mad(net.aa[k], zm.yt[k], s3);
-      }
-      const double xtot = A::sub(A::add(s3, s->xext), 1.0);
+      const double xtot = A::sub(A::add(s->red[1], s->xext), 1.0);
       const double testm = A::sub(xtot, s->xtot_init);
-      const double testn = (ctl.iconvc != 0) ? s1 : testm;
+      const double testn = (ctl.iconvc != 0) ? s->red[0] : testm;
       const double toln = (ctl.iconvc != 0) ? ctl.tolc : ctl.tolm;
       s->relt9 = 0.0;
       s->flag = (fabs(testn) <= toln && s->relt9 < ctl.tolt9) ? 1 : 0;
@@ -459,8 +539,9 @@ __device__ void step_be_cta(const DevNet &net, const DevCtl &ctl, ZoneMem &zm) {
 
 // --- timestep (xnet_integrate.F90:13-268), executed by thread 0 after the optional rate pass ---
 template <bool STRICT>
-__device__ void timestep_cta(const DevNet &net, const DevCtl &ctl, ZoneMem &zm) {
+__device__ __noinline__ void timestep_cta() {
   using A = Ar<STRICT>;
+  XB_ZONE_PROLOGUE
   ZoneScalars *s = zm.s;
   const int ny = net.ny;
   if (threadIdx.x == 0) {
@@ -471,12 +552,28 @@ __device__ void timestep_cta(const DevNet &net, const DevCtl &ctl, ZoneMem &zm) 
   const bool mask_init = s->flag != 0;
   if (mask_init) {
     XB_PHASE_BEGIN(zm);
-    cross_sect_cta<STRICT>(net, ctl, zm);
+    cross_sect_cta<STRICT>();
     XB_PHASE_END(zm, PH_RATES);
-    yderiv_cta<STRICT>(net, zm);
+    yderiv_cta<STRICT>();
     XB_PHASE_END(zm, PH_YDERIV);
   }
   XB_PHASE_BEGIN(zm);
+  const bool fwd = s->tdel_old >= 0.0;
+  if (fwd) {
+    // controlling species: first maximum of |dY/Y| per unit time (xnet_integrate.F90:118-139)
+    const double *y = zm.y, *yo = zm.yo, *ydot = zm.ydot;
+    const double ymin = ctl.ymin, yacc = ctl.yacc, tdo = s->tdel_old;
+    block_argmax_first(ny, [&](int k) {
+      double r = 0.0;
+      const double yk = y[k];
+      if (yk > ymin) {
+        const double yfloor = fmax(yk, yacc);
+        if (mask_init) r = fabs(A::div(ydot[k], yfloor));
+        else r = A::div(fabs(A::div(A::sub(yk, yo[k]), yfloor)), tdo);
+      }
+      return r;
+    }, zm.part, s->red, &s->ints);
+  }
   if (threadIdx.x == 0) {
     const double changeth = 0.1;
     double changey, tdel_init, tdel_dy, tdel_dt9;
@@ -487,19 +584,9 @@ __device__ void timestep_cta(const DevNet &net, const DevCtl &ctl, ZoneMem &zm) 
       tdel_init = fmin(A::mul(changest, fabs(s->tdelstart)), tdel_stop);
       s->tdel_next = (s->nh > 2) ? A::mul(1.0e-4, tdel_stop) : tdel_stop;
     } else { changey = ctl.changemx; tdel_init = 0.0; }
-    if (s->tdel_old >= 0.0) {
-      int imax = 0; double vmax = -1.0;
-      for (int k = 0; k < ny; ++k) {
-        double r = 0.0;
-        const double yk = zm.y[k];
-        if (yk > ctl.ymin) {
-          const double yfloor = fmax(yk, ctl.yacc);
-          if (mask_init) r = fabs(A::div(zm.ydot[k], yfloor));
-          else r = A::div(fabs(A::div(A::sub(yk, zm.yo[k]), yfloor)), s->tdel_old);
-        }
-        if (r > vmax) { vmax = r; imax = k; }
-      }
-      s->ints = imax + 1;
+    if (fwd) {
+      const double vmax = s->red[0];
+      s->ints += 1;
       tdel_dy = (fabs(vmax) > 0.0) ? A::div(changey, vmax) : s->tdel_next;
       tdel_dt9 = s->tdel_next;  // rtau_t9 = 0 without self-heating
       s->tdel = fmax(tdel_init, fmin(fmin(tdel_stop, s->tdel_next), fmin(tdel_dy, tdel_dt9)));
@@ -538,8 +625,9 @@ __device__ void timestep_cta(const DevNet &net, const DevCtl &ctl, ZoneMem &zm) 
 
 // --- solve_be: retry ladder + accept (xnet_integrate_be.F90:32-231) -----------------------------
 template <bool STRICT>
-__device__ void solve_be_cta(const DevNet &net, const DevCtl &ctl, ZoneMem &zm) {
+__device__ __noinline__ void solve_be_cta() {
   using A = Ar<STRICT>;
+  XB_ZONE_PROLOGUE
   ZoneScalars *s = zm.s;
   const int tid = threadIdx.x, nt = blockDim.x, ny = net.ny;
   const int ktsmx = 10;
@@ -548,7 +636,7 @@ __device__ void solve_be_cta(const DevNet &net, const DevCtl &ctl, ZoneMem &zm) 
   __syncthreads();
   int mykts = 0;
   for (int kts = 1; kts <= ktsmx; ++kts) {
-    step_be_cta<STRICT>(net, ctl, zm);
+    step_be_cta<STRICT>();
     const int inr = s->inr;
     __syncthreads();
     if (inr == 0) {
@@ -563,7 +651,7 @@ __device__ void solve_be_cta(const DevNet &net, const DevCtl &ctl, ZoneMem &zm) 
         if (kts == ktsmx - 1) { s->tdel = 0.0; s->tdelstart = 0.0; }
       }
       __syncthreads();
-      if (kts == ktsmx - 1) timestep_cta<STRICT>(net, ctl, zm);
+      if (kts == ktsmx - 1) timestep_cta<STRICT>();
     } else {
       mykts = kts;
       if (tid == 0) { s->kmon[1] = inr; s->ktot[1] += inr; }
@@ -589,25 +677,33 @@ __device__ void solve_be_cta(const DevNet &net, const DevCtl &ctl, ZoneMem &zm) 
   __syncthreads();
 }
 
-// benuc (xnet_data.F90:157-175) and enudot (:990-1020), thread 0
+// benuc (xnet_data.F90:157-175) and enudot (:990-1020); all threads call
 template <bool STRICT>
-__device__ void benuc_t0(const DevNet &net, const double *y, double *enm) {
+__device__ __forceinline__ void benuc_cta(const ZoneMem &zm, const double *y, double *enm) {
   using A = Ar<STRICT>;
-  double ztot = 0.0, btot = 0.0;
-  for (int k = 0; k < net.ny; ++k) { ztot = A::mad(y[k], net.zz[k], ztot); btot = A::mad(y[k], net.be[k], btot); }
-  double e = A::sub(A::add(A::mul(net.mex_p, ztot), A::mul(net.mex_n, A::sub(1.0, ztot))), btot);
-  *enm = A::mul(A::mul(1.6021766208e-06, 6.022140857e+23), e);
+  const DevNet &net = c_net;
+  const double *zz = net.zz, *be = net.be;
+  block_sum2<STRICT>(net.ny, [&](int k, double &ta, double &tb) { ta = A::mul(y[k], zz[k]); tb = A::mul(y[k], be[k]); },
+                     zm.part, zm.s->red);
+  if (threadIdx.x == 0) {
+    const double ztot = zm.s->red[0], btot = zm.s->red[1];
+    const double e = A::sub(A::add(A::mul(net.mex_p, ztot), A::mul(net.mex_n, A::sub(1.0, ztot))), btot);
+    *enm = A::mul(A::mul(1.6021766208e-06, 6.022140857e+23), e);
+  }
+  __syncthreads();
 }
+// sum over the FFN reactions in reaction order (all other reactions contribute +0 in the reference loop)
 template <bool STRICT>
-__device__ void enudot_t0(const DevNet &net, const ZoneMem &zm, const double *y, double *sqnu) {
+__device__ __forceinline__ void enudot_cta(const ZoneMem &zm, const double *y, double *sqnu) {
   using A = Ar<STRICT>;
+  const DevNet &net = c_net;
   if (net.nffn > 0) {
-    double sv = 0.0;
-    for (int k = 0; k < net.nr[0]; ++k) {
-      const int f = net.iffn[k];
-      sv = A::mad(y[net.ni[(size_t)k * 6] - 1], zm.qkffn[f], sv);
-    }
-    *sqnu = A::mul(A::mul(1.6021766208e-06, 6.022140857e+23), sv);
+    const int *n1 = net.ffr_n1, *ff = net.ffr_iffn;
+    const double *qk = zm.qkffn;
+    block_sum2<STRICT>(net.nffr, [&](int k, double &ta, double &tb) { ta = A::mul(y[n1[k]], qk[ff[k]]); tb = 0.0; },
+                       zm.part, zm.s->red);
+    if (threadIdx.x == 0) *sqnu = A::mul(A::mul(1.6021766208e-06, 6.022140857e+23), zm.s->red[0]);
+    __syncthreads();
   }
 }
 
@@ -631,9 +727,9 @@ __device__ inline void hist_put(const DevOut &out, int iz, int ny, int kstep, co
 
 // --- full_net for one zone (xnet_evolve.F90:19-269; zone load net.F90:246-272) ------------------
 template <bool STRICT>
-__device__ void full_net_cta(const DevNet &net, const DevCtl &ctl, const DevZones &zn, const DevOut &out,
-                             ZoneMem &zm, int iz) {
+__device__ __forceinline__ void full_net_cta(const DevZones &zn, const DevOut &out, int iz) {
   using A = Ar<STRICT>;
+  XB_ZONE_PROLOGUE
   ZoneScalars *s = zm.s;
   const int tid = threadIdx.x, nt = blockDim.x, ny = net.ny;
   const int fx = zn.zfix[iz];
@@ -647,7 +743,7 @@ __device__ void full_net_cta(const DevNet &net, const DevCtl &ctl, const DevZone
     s->ye = zn.yestart[fx];
     s->cv = s->etae = s->detaedt9 = s->t9dot = 0.0;
     for (int k = 0; k < 5; ++k) { s->kmon[k] = 0; s->ktot[k] = 0; }
-    for (int k = 0; k < 8; ++k) s->ph[k] = 0;
+    for (int k = 0; k < 12; ++k) s->ph[k] = 0;
     s->ints = 0; s->its = 0; s->edot = 0.0; s->sqnu = 0.0;
     if (out.hist_cap > 0) out.hist_n[iz] = 0;
     if (restart) {
@@ -677,18 +773,19 @@ __device__ void full_net_cta(const DevNet &net, const DevCtl &ctl, const DevZone
     if (restart) { double t9x, rhox; t9rhofind<STRICT>(s, s->t, &s->nt, &t9x, &rhox); }
     s->tdel_old = s->tdel; s->nto = s->nt; s->ntt = s->nt; s->to = s->t; s->tt = s->t;
     s->t9t = s->t9; s->rhoo = s->rho; s->rhot = s->rho; s->yeo = s->ye; s->yet = s->ye;
-    benuc_t0<STRICT>(net, zm.y, &s->enm);
-    s->enold = restart ? s->enm : 0.0;
     s->tmark = clock64();
     s->ph[PH_TOTAL] = -s->tmark;
   }
+  __syncthreads();
+  benuc_cta<STRICT>(zm, zm.y, &s->enm);
+  if (tid == 0) s->enold = restart ? s->enm : 0.0;
   __syncthreads();
   if (!restart) hist_put(out, iz, ny, 0, zm);
   int mykstep = 0;
   bool lzsolve = true;
   for (int kstep = kstep0 + 1; kstep <= kstep0 + ctl.kstmx; ++kstep) {
-    timestep_cta<STRICT>(net, ctl, zm);
-    solve_be_cta<STRICT>(net, ctl, zm);
+    timestep_cta<STRICT>();
+    solve_be_cta<STRICT>();
     bool lzoutput = true;
     const int its = s->its;
     __syncthreads();
@@ -698,11 +795,9 @@ __device__ void full_net_cta(const DevNet &net, const DevCtl &ctl, const DevZone
     } else { lzsolve = false; lzoutput = false; if (tid == 0 && its == 1) s->its = 2; }
     __syncthreads();
     if (lzoutput) {
-      if (tid == 0) {
-        benuc_t0<STRICT>(net, zm.yt, &s->enm);
-        enudot_t0<STRICT>(net, zm, zm.yt, &s->sqnu);
-        s->edot = -A::div(A::sub(s->enm, s->enold), s->tdel);
-      }
+      benuc_cta<STRICT>(zm, zm.yt, &s->enm);
+      enudot_cta<STRICT>(zm, zm.yt, &s->sqnu);
+      if (tid == 0) s->edot = -A::div(A::sub(s->enm, s->enold), s->tdel);
       __syncthreads();
       hist_put(out, iz, ny, kstep, zm);
     }
