@@ -21,7 +21,7 @@ struct ZoneScalars {
   double *g_csect, *g_rffn, *g_qkffn, *g_prod, *g_jac;  // per-CTA global scratch (set in the kernel prologue)
   int nh, has_scale, nt, ntt, nto, ints, iweak;
   int kmon[5], ktot[5];
-  int inr, its, flag, piv, info;
+  int inr, its, flag, piv, info, tile_ctr;
   long long ph[12];          // see enum Phase
   long long tmark;
 };
@@ -456,7 +456,7 @@ __device__ __noinline__ void jacobian_build_cta() {
 
 template <bool STRICT>
 __device__ __forceinline__ void lu_cta(const ZoneMem &zm, const int N) {
-  if (zm.tile) lu_tile<STRICT>(zm.jac, zm.ld, N, zm.indx, &zm.s->info, zm.prow, zm.rdiag, zm.s->ph + PH_LU_PANEL);
+  if (zm.tile) lu_tile<STRICT>(zm.jac, zm.ld, N, zm.indx, &zm.s->info, zm.prow, zm.rdiag, &zm.s->tile_ctr, zm.s->ph + PH_LU_PANEL);
   else { lu_simple<STRICT>(zm.jac, zm.ld, N, zm.indx, &zm.s->info, &zm.s->piv); }
 }
 template <bool STRICT>
