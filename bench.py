@@ -241,6 +241,7 @@ def main():
                      'phase_share': {k: round(ph[k] / phase_tot, 4) for k in ('rates', 'yderiv', 'jac', 'lu', 'bksub', 'other', 'lu_panel', 'lu_swap_trsm', 'lu_gemm')},
                      'cycles_per_newton_iter': phase_tot / max(newton, 1.0),
                      'pivoting_panel_fallbacks_per_lu': ph['spare'] / max(nlu, 1.0),
+                     'dbg_cycles_per_newton_iter': [round(ph['dbg%d' % k] / max(newton, 1.0)) for k in range(12)],
                      'hbm_note': 'Jacobian/csect/state never touch HBM (shared memory / L2 scratch); HBM traffic per launch is '
                                  'inputs+outputs only: %.3g GB/s of measured %.0f GB/s' % (
                                      (h2d + d2h) / (ms_launch * 1e-3) / 1e9, peaks.get('hbm_gbs', 6650.0))},

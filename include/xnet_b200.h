@@ -167,9 +167,10 @@ int xb_evolve(xb_ctx *ctx, const xb_zones *zones, xb_out *out);
 int xb_zones_upload(xb_ctx *ctx, const xb_zones *zones, int32_t hist_cap);
 int xb_evolve_resident(xb_ctx *ctx, float *kernel_ms);   /* runs on the uploaded zones */
 int xb_results_download(xb_ctx *ctx, xb_out *out);
-/* per-phase cycle counters of the last resident run (sum over CTAs), 12 values:
- * rates,yderiv,jac,lu,bksub,other,total,zones, lu_panel,lu_swap_trsm,lu_gemm,spare */
-int xb_phase_cycles(xb_ctx *ctx, double *cycles12);
+/* per-phase cycle counters of the last resident run (sum over CTAs), 24 values:
+ * rates,yderiv,jac,lu,bksub,other,total,zones, lu_panel,lu_swap_trsm,lu_gemm,pivoting-panel fallbacks,
+ * then 12 fine-grained development timers */
+int xb_phase_cycles(xb_ctx *ctx, double *cycles24);
 /* bytes moved host->device / device->host by the last xb_evolve call */
 int xb_last_copy_bytes(xb_ctx *ctx, int64_t *h2d, int64_t *d2h);
 /* cfg6 = grid, threads per CTA, dynamic smem bytes, jacobian-in-smem flag, SM count, msize */

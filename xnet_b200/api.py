@@ -405,10 +405,11 @@ class Context:
         return res
 
     def phase_cycles(self):
-        c = np.zeros(12)
+        c = np.zeros(24)
         _chk(lib().xb_phase_cycles(self.h, _pd(c)))
-        return dict(zip(('rates', 'yderiv', 'jac', 'lu', 'bksub', 'other', 'total', 'zones',
-                         'lu_panel', 'lu_swap_trsm', 'lu_gemm', 'spare'), c))
+        names = ('rates', 'yderiv', 'jac', 'lu', 'bksub', 'other', 'total', 'zones',
+                 'lu_panel', 'lu_swap_trsm', 'lu_gemm', 'spare') + tuple('dbg%d' % k for k in range(12))
+        return dict(zip(names, c))
 
     def copy_bytes(self):
         a = C.c_int64(); b = C.c_int64()

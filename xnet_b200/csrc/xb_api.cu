@@ -92,20 +92,23 @@ static SmemOff smem_layout(int ny, int N, int ld, int npart, bool jac_in_smem) {
   SmemOff L{};
   size_t o = 0;
   L.scal = (int)o; o += (sizeof(ZoneScalars) + 15) / 16 * 16;
-  L.jac = (int)o; if (jac_in_smem) o += ((size_t)N * ld * 8 + 15) / 16 * 16;
+  L.jac = (int)o;
+  if (jac_in_smem) {   // N columns + the right-hand side as column N
+    L.rhs = (int)(o + (size_t)N * ld * 8);
+    o += ((size_t)N * ld * 8 + (size_t)N * 8 + 15) / 16 * 16;
+  } else { L.rhs = (int)o; o += ((size_t)N * 8 + 15) / 16 * 16; }
   L.y = (int)o; o += (size_t)ny * 8;
-  L.yo = (int)o; o += (size_t)ny * 8;
   L.yt = (int)o; o += (size_t)(ny + 1) * 8;
   L.ydot = (int)o; o += (size_t)ny * 8;
-  L.rhs = (int)o; o += (size_t)N * 8;
-  L.gg = (int)o; o += (size_t)(ny + 1) * 8;
   L.rdiag = (int)o; o += (size_t)N * 8;
   o = (o + 15) / 16 * 16;
   L.part = (int)o; o += (size_t)npart * 8;
   o = (o + 15) / 16 * 16;
   L.prow = (int)o; o += (size_t)2 * kPanelWarps * kPanelRec * 8;
   L.indx = (int)o; o += (size_t)N * 4;
-  L.total = (int)((o + 15) / 16 * 16);
+  o = (o + 15) / 16 * 16;
+  L.cs = (int)o;
+  L.total = (int)o;
   return L;
 }
 
@@ -120,6 +123,7 @@ static __device__ void zone_prologue(const DevScratch &scr, double *csect, doubl
     s->g_qkffn = qkffn ? qkffn : g + scr.off_qkffn;
     s->g_prod = g + scr.off_prod;
     s->g_jac = jacg ? jacg : g + scr.off_jac;
+    s->g_yo = g + scr.off_yo;
     reinterpret_cast<double *>(xb_smem + c_net.lay.yt)[c_net.ny] = 1.0;
   }
   __syncthreads();
@@ -175,6 +179,8 @@ module_kernel(const __grid_constant__ ModArgs ma, const __grid_constant__ DevScr
   ZoneScalars *s = zm.s;
   if (OP == OP_CSECT || OP == OP_YDERIV || OP == OP_JBUILD)
     for (int k = tid; k < ny; k += nt) zm.yt[k] = ma.yt[(size_t)iz * ny + k];
+  if (OP == OP_YDERIV || OP == OP_JBUILD)
+    for (int k = net.cs_lo + tid; k < net.nrtot; k += nt) zm.cs_sm[k - net.cs_lo] = zm.csect[k];
   if (tid == 0) {
     for (int k = 0; k < 5; ++k) s->ktot[k] = 0;
     for (int k = 0; k < PH_COUNT; ++k) s->ph[k] = 0;
@@ -198,7 +204,7 @@ module_kernel(const __grid_constant__ ModArgs ma, const __grid_constant__ DevScr
       for (int e = tid; e < N * N; e += nt) { const int j = e / N, i = e - j * N; zm.jac[j * ld + i] = gj[e]; }
       __syncthreads();
     }
-    lu_cta<STRICT>(zm, N);
+    lu_cta<STRICT>(zm, N, false);
     if (net.tile)
       for (int e = tid; e < N * N; e += nt) { const int j = e / N, i = e - j * N; gj[e] = zm.jac[j * ld + i]; }
     for (int k = tid; k < N; k += nt) ma.indx[(size_t)iz * N + k] = zm.indx[k] + 1;  // LAPACK 1-based ipiv
@@ -207,7 +213,7 @@ module_kernel(const __grid_constant__ ModArgs ma, const __grid_constant__ DevScr
     // factors are read straight from HBM/L2 (each element is used once); rdiag is not kept between calls
     for (int k = tid; k < N; k += nt) { zm.indx[k] = ma.indx[(size_t)iz * N + k] - 1; zm.rhs[k] = ma.rhs[(size_t)iz * N + k]; }
     __syncthreads();
-    if (net.tile) bksub_block<STRICT, false>(gj, N, N, zm.indx, zm.rhs, nullptr, zm.prow);
+    if (net.tile) bksub_block<STRICT, false>(gj, N, N, zm.indx, zm.rhs, nullptr, zm.prow, false);
     else bksub_simple<STRICT>(gj, N, N, zm.indx, zm.rhs);
     for (int k = tid; k < N; k += nt) ma.rhs[(size_t)iz * N + k] = zm.rhs[k];
   }
@@ -609,7 +615,7 @@ static int build_plans(xb_ctx *c, int NT, int ld) {
   int rc = upload_plan(c->pby, c->dn.py, py); if (rc) return rc;
   rc = upload_plan(c->pbj, c->dn.pj, pj); if (rc) return rc;
   c->ld = ld; c->dn.ld = ld;
-  c->npart = std::max(std::max(py.npart, pj.npart), std::max(2 * std::max(ny, c->dn.nffr), 128));
+  c->npart = std::max(std::max(py.npart, pj.npart), std::max(2 * std::max(ny, c->dn.nffr) + 2, 128));
   return XB_OK;
 }
 
@@ -629,6 +635,13 @@ static int configure_launch(xb_ctx *c) {
     rc = build_plans(c, c->threads, N); if (rc) return rc;
     L = smem_layout(ny, N, c->ld, c->npart, false);
   }
+  {  // whatever shared memory is left caches csect (the tail of the reaction list: 2-, 3-, 4-body rates first)
+    const size_t budget = max_smem - 64;
+    const size_t room = budget > (size_t)L.total ? (budget - (size_t)L.total) / 8 : 0;
+    const int ncache = (int)std::min<size_t>(room, (size_t)c->dn.nrtot);
+    c->dn.cs_lo = c->dn.nrtot - ncache;
+    L.total = (int)(((size_t)L.total + (size_t)ncache * 8 + 15) / 16 * 16);
+  }
   c->smem_bytes = (size_t)L.total;
   c->dn.lay = L; c->dn.tile = c->jac_in_smem;
   const void *fn = c->ctl.arith ? evolve_fn<true>() : evolve_fn<false>();
@@ -647,6 +660,8 @@ static int configure_launch(xb_ctx *c) {
   s.off_qkffn = o; o += c->dn.nffn + 1;
   o = (o + 15) / 16 * 16;
   s.off_prod = o; if (c->ctl.arith) o += (size_t)std::max(c->dn.py.L, c->dn.pj.L) * c->threads;
+  o = (o + 15) / 16 * 16;
+  s.off_yo = o; o += (size_t)c->dn.ny;
   o = (o + 15) / 16 * 16;
   s.off_jac = o; if (!c->jac_in_smem) o += (size_t)N * c->ld;
   s.stride = (o + 15) / 16 * 16;

@@ -30,10 +30,11 @@ struct DevPlan {
 };
 
 // byte offsets of the zone working set inside the CTA's dynamic shared memory
-struct SmemOff { int scal, jac, y, yo, yt, ydot, rhs, gg, rdiag, part, prow, indx, total; };
+struct SmemOff { int scal, jac, y, yt, ydot, rhs, rdiag, part, prow, indx, cs, total; };
 
 struct DevNet {
   int ny, nrtot, nffn, msize, ld, nffr, tile;
+  int cs_lo;                 // reactions [cs_lo, nrtot) have their rate cached in shared memory
   SmemOff lay;
   DevPlan py, pj;            // ydot and Jacobian plans
   const int *ffr_n1, *ffr_iffn;  // [nffr] FFN reactions in reaction order: first reactant (0-based), table row (1-based)
@@ -81,7 +82,7 @@ struct DevOut {
 struct DevScratch {
   double *base;            // [ncta][stride]
   size_t stride;           // doubles per CTA
-  size_t off_csect, off_rffn, off_qkffn, off_jac, off_prod;  // offsets (doubles)
+  size_t off_csect, off_rffn, off_qkffn, off_jac, off_prod, off_yo;  // offsets (doubles)
   unsigned long long *phase;  // [PH_COUNT] cycle counters, see enum Phase
 };
 
@@ -92,7 +93,8 @@ __constant__ DevCtl c_ctl;
 extern __shared__ __align__(16) unsigned char xb_smem[];
 
 enum Phase { PH_RATES = 0, PH_YDERIV, PH_JAC, PH_LU, PH_BKSUB, PH_OTHER, PH_TOTAL, PH_ZONES,
-             PH_LU_PANEL, PH_LU_SWAP, PH_LU_GEMM, PH_SPARE, PH_COUNT };
+             PH_LU_PANEL, PH_LU_SWAP, PH_LU_GEMM, PH_SPARE,
+             PH_DBG0, PH_DBG_END = PH_DBG0 + 12, PH_COUNT = PH_DBG_END };
 
 // ---------------------------------------------------------------------------------------------
 // Arithmetic policy.  STRICT: every product and sum individually rounded (no FMA contraction), so

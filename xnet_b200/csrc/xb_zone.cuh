@@ -18,12 +18,12 @@ struct ZoneScalars {
   double red[4];             // results of block-wide reductions
   double t09[4];             // T9^(-1/3), T9^(1/3), T9^(5/3), ln T9 of the current rate evaluation
   const double *th, *t9h, *rhoh;
-  double *g_csect, *g_rffn, *g_qkffn, *g_prod, *g_jac;  // per-CTA global scratch (set in the kernel prologue)
+  double *g_csect, *g_rffn, *g_qkffn, *g_prod, *g_jac, *g_yo;  // per-CTA global scratch (set in the kernel prologue)
   int nh, has_scale, nt, ntt, nto, ints, iweak;
   int kmon[5], ktot[5];
   int inr, its, flag, piv, info, tile_ctr;
-  long long ph[12];          // see enum Phase
-  long long tmark;
+  long long ph[PH_COUNT];    // see enum Phase
+  long long tmark, dmark;
 };
 
 // Views of the zone working set
@@ -36,7 +36,8 @@ struct ZoneMem {
   double *prow;     // [2][6][12] published pivot candidates of the LU panel; [2][32] block values of the solve
   double *rdiag;    // [N] reciprocal diagonal of U (fast arithmetic only)
   double *prod;     // per-CTA global scratch for the strict term products
-  double *gg;       // [ny+1]
+  double *gg;       // [ny+1] partition functions (aliases part)
+  double *cs_sm;    // shared-memory cache of csect[cs_lo..nrtot)
   double *csect;    // [nrtot] (global scratch)
   double *rffn;     // [nffn]
   double *qkffn;    // [nffn+1]
@@ -52,11 +53,12 @@ __device__ __forceinline__ ZoneMem zone_mem() {
   zm.ld = c_net.ld; zm.tile = c_net.tile;
   zm.jac = c_net.tile ? reinterpret_cast<double *>(xb_smem + L.jac) : zm.s->g_jac;
   zm.y = reinterpret_cast<double *>(xb_smem + L.y);
-  zm.yo = reinterpret_cast<double *>(xb_smem + L.yo);
+  zm.yo = zm.s->g_yo;
   zm.yt = reinterpret_cast<double *>(xb_smem + L.yt);
   zm.ydot = reinterpret_cast<double *>(xb_smem + L.ydot);
-  zm.rhs = reinterpret_cast<double *>(xb_smem + L.rhs);
-  zm.gg = reinterpret_cast<double *>(xb_smem + L.gg);
+  zm.rhs = reinterpret_cast<double *>(xb_smem + L.rhs);     // tile mode: column N of the tile
+  zm.gg = reinterpret_cast<double *>(xb_smem + L.part);     // lives only inside cross_sect
+  zm.cs_sm = reinterpret_cast<double *>(xb_smem + L.cs);
   zm.rdiag = reinterpret_cast<double *>(xb_smem + L.rdiag);
   zm.part = reinterpret_cast<double *>(xb_smem + L.part);
   zm.prow = reinterpret_cast<double *>(xb_smem + L.prow);
@@ -69,6 +71,16 @@ __device__ __forceinline__ ZoneMem zone_mem() {
   const DevCtl &ctl = c_ctl;            \
   ZoneMem zm = zone_mem();              \
   (void)net; (void)ctl;
+
+// fine-grained debug timers (thread 0): XB_DBG(zm, i) adds the cycles since the previous mark to slot i
+#define XB_DBG(zm, i)                                             \
+  if (threadIdx.x == 0) {                                         \
+    long long now_ = clock64();                                   \
+    (zm).s->ph[PH_DBG0 + (i)] += now_ - (zm).s->dmark;            \
+    (zm).s->dmark = now_;                                         \
+  }
+#define XB_DBG_MARK(zm) \
+  if (threadIdx.x == 0) (zm).s->dmark = clock64();
 
 #define XB_PHASE_BEGIN(zm) \
   if (threadIdx.x == 0) (zm).s->tmark = clock64();
@@ -187,7 +199,7 @@ __device__ __noinline__ void cross_sect_cta() {
   ZoneScalars *s = zm.s;
   const int tid = threadIdx.x, nt = blockDim.x, ny = net.ny;
   const double t9t = s->t9t, rhot = s->rhot;
-
+  XB_DBG_MARK(zm);
   {
     // Ye from the composition moments (xnet_abundances.F90:137-166); sums in the reference order
     const double *aa = net.aa, *zz = net.zz, *yt = zm.yt;
@@ -226,6 +238,7 @@ __device__ __noinline__ void cross_sect_cta() {
     }
   }
   __syncthreads();
+  XB_DBG(zm, 4);
   const double ene = A::mul(s->yet, rhot);
   const int iweak = s->iweak;
 
@@ -257,6 +270,7 @@ __device__ __noinline__ void cross_sect_cta() {
   }
   __syncthreads();
 
+  XB_DBG(zm, 5);
   // REACLIB rates: one thread per reaction, coalesced coefficient loads
   double t09[7];
   t09[0] = 1.0;
@@ -264,26 +278,37 @@ __device__ __noinline__ void cross_sect_cta() {
   t09[2] = s->t09[0]; t09[3] = s->t09[1]; t09[5] = s->t09[2]; t09[6] = s->t09[3];
   t09[4] = t9t;
   const double rho2 = A::mul(rhot, rhot), rho3 = A::mul(rho2, rhot);
-  for (int k = tid; k < net.nrtot; k += nt) {
+  const int nrtot = net.nrtot;
+  const double *__restrict__ rcT = net.rcT;
+  const int2 *__restrict__ ni2 = reinterpret_cast<const int2 *>(net.ni);
+  const int *__restrict__ iwkp = net.iwk, *__restrict__ irevp = net.irev;
+  const double *gg = zm.gg;
+#pragma unroll 2
+  for (int k = tid; k < nrtot; k += nt) {
+    // every load of the reaction is issued up front (one L2 round trip per reaction, not three)
+    const int iwk = __ldg(iwkp + k), irev = __ldg(irevp + k);
+    const int2 n01 = __ldg(ni2 + 3 * k), n23 = __ldg(ni2 + 3 * k + 1), n45 = __ldg(ni2 + 3 * k + 2);
+    double rc[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) rc[j] = __ldg(rcT + (size_t)j * nrtot + k);
     const int c = (k >= net.roff[3]) ? 3 : (k >= net.roff[2]) ? 2 : (k >= net.roff[1]) ? 1 : 0;
-    const int iwk = net.iwk[k];
     double cs;
     if ((iweak < 0 && iwk == 0) || (iweak == 0 && iwk != 0)) {
       cs = 0.0;
     } else {
       double lam = 0.0;
 #pragma unroll
-      for (int j = 0; j < 7; ++j) lam = A::mad(net.rcT[(size_t)j * net.nrtot + k], t09[j], lam);
+      for (int j = 0; j < 7; ++j) lam = A::mad(rc[j], t09[j], lam);
       // h = ascrn*h + lambda with ascrn = 0 (no screening in this build of the path)
       const double h = A::add(A::mul(0.0, 0.0), lam);
       double rpf = 1.0;
-      if (net.irev[k] == 1) {
-        const int *ni = net.ni + (size_t)k * 6;
+      if (irev == 1) {
+        const int ni[6] = {n01.x, n01.y, n23.x, n23.y, n45.x, n45.y};
         const int nreact = c + 1, nslot = (c == 0) ? 5 : 6;
         double p;
-        if (c == 0) p = zm.gg[ni[0]];
-        else { p = 1.0; for (int j = 0; j < nreact; ++j) p = A::mul(p, zm.gg[ni[j]]); }
-        for (int j = nreact; j < nslot; ++j) rpf = A::mul(rpf, zm.gg[ni[j]]);
+        if (c == 0) p = gg[ni[0]];
+        else { p = 1.0; for (int j = 0; j < nreact; ++j) p = A::mul(p, gg[ni[j]]); }
+        for (int j = nreact; j < nslot; ++j) rpf = A::mul(rpf, gg[ni[j]]);
         rpf = A::div(rpf, p);
       }
       if (c == 0) {
@@ -299,8 +324,11 @@ __device__ __noinline__ void cross_sect_cta() {
       }
     }
     zm.csect[k] = cs;
+    if (k >= net.cs_lo) zm.cs_sm[k - net.cs_lo] = cs;
   }
+  XB_DBG(zm, 6);
   __syncthreads();
+  XB_DBG(zm, 7);
 }
 
 // --- term plans -------------------------------------------------------------------------------------
@@ -320,8 +348,14 @@ __device__ __forceinline__ double plan_mul(const double a, const double c, const
 
 // FAST: every thread reduces its chunk; `flush(ctl, acc)` is called at the end of each piece.  Loads of
 // kPlanU records are issued together (two L2 round trips per batch instead of per record).
+// rate of reaction mu: from the shared-memory cache when it is there, else from the L2-resident copy
+__device__ __forceinline__ double cs_fetch(const double *cs, const double *cs_sm, const int cs_lo, const unsigned mu) {
+  return ((int)mu >= cs_lo) ? cs_sm[(int)mu - cs_lo] : __ldcg(cs + mu);
+}
+
 template <class Flush>
-__device__ __forceinline__ void plan_run_fast(const DevPlan &P, const double *cs, const double *y, Flush flush) {
+__device__ __forceinline__ void plan_run_fast(const DevPlan &P, const double *cs, const double *cs_sm, const int cs_lo,
+                                              const double *y, Flush flush) {
   const double *__restrict__ pa = P.a;
   const uint2 *__restrict__ pn = P.nn;
   const uint2 *__restrict__ pm = P.mc;
@@ -329,15 +363,22 @@ __device__ __forceinline__ void plan_run_fast(const DevPlan &P, const double *cs
   int idx = threadIdx.x;
   double acc = 0.0;
   for (int k0 = 0; k0 < L; k0 += kPlanU) {
-    double a[kPlanU], c[kPlanU];
+    // stage 1: the records (coalesced); stage 2: rate and abundance gathers, all in flight together;
+    // stage 3: independent products; stage 4: the only sequential part, accumulate and flush
+    double v[kPlanU], c[kPlanU], f0[kPlanU], f1[kPlanU], f2[kPlanU], f3[kPlanU];
     uint2 nn[kPlanU], mc[kPlanU];
 #pragma unroll
-    for (int u = 0; u < kPlanU; ++u) { a[u] = __ldg(pa + idx + u * nt); nn[u] = __ldg(pn + idx + u * nt); mc[u] = __ldg(pm + idx + u * nt); }
-#pragma unroll
-    for (int u = 0; u < kPlanU; ++u) c[u] = __ldcg(cs + mc[u].x);
+    for (int u = 0; u < kPlanU; ++u) { v[u] = __ldg(pa + idx + u * nt); nn[u] = __ldg(pn + idx + u * nt); mc[u] = __ldg(pm + idx + u * nt); }
 #pragma unroll
     for (int u = 0; u < kPlanU; ++u) {
-      acc += plan_mul<false>(a[u], c[u], nn[u], y);
+      c[u] = cs_fetch(cs, cs_sm, cs_lo, mc[u].x);
+      f0[u] = y[nn[u].x & 0xffffu]; f1[u] = y[nn[u].x >> 16]; f2[u] = y[nn[u].y & 0xffffu]; f3[u] = y[nn[u].y >> 16];
+    }
+#pragma unroll
+    for (int u = 0; u < kPlanU; ++u) v[u] = (((v[u] * c[u]) * f0[u]) * f1[u]) * f2[u] * f3[u];
+#pragma unroll
+    for (int u = 0; u < kPlanU; ++u) {
+      acc += v[u];
       if (mc[u].y & 3u) { flush(mc[u].y, acc); acc = 0.0; }
     }
     idx += kPlanU * nt;
@@ -388,7 +429,7 @@ __device__ __noinline__ void yderiv_cta() {
       ydot[i] = __dadd_rn(__dadd_rn(__dadd_rn(s[0], s[1]), s[2]), s[3]);
     }
   } else {
-    plan_run_fast(P, zm.csect, zm.yt, [&](unsigned ctl, double acc) {
+    plan_run_fast(P, zm.csect, zm.cs_sm, net.cs_lo, zm.yt, [&](unsigned ctl, double acc) {
       if ((ctl & 3u) == 1u) ydot[ctl >> 3] = acc; else part[ctl >> 3] = acc;
     });
     __syncthreads();
@@ -412,6 +453,7 @@ __device__ __forceinline__ void jacobian_build_impl(const DevNet &net, const Zon
   const int tid = threadIdx.x, nt = blockDim.x, N = net.msize, ld = zm.ld;
   const double diag = zm.s->rdt, mult = zm.s->mult;
   double *part = zm.part;
+  XB_DBG_MARK(zm);
   {
     const int n2 = (N * ld) >> 1;
     double2 *J2 = reinterpret_cast<double2 *>(J);
@@ -432,11 +474,14 @@ __device__ __forceinline__ void jacobian_build_impl(const DevNet &net, const Zon
     }
   } else {
     __syncthreads();  // zero fill complete before the scattered stores
-    plan_run_fast(P, zm.csect, zm.yt, [&](unsigned ctl, double acc) {
+    XB_DBG(zm, 0);
+    plan_run_fast(P, zm.csect, zm.cs_sm, net.cs_lo, zm.yt, [&](unsigned ctl, double acc) {
       if ((ctl & 3u) == 1u) J[ctl >> 3] = fma(mult, acc, (ctl & 4u) ? diag : 0.0);
       else part[ctl >> 3] = acc;
     });
+    XB_DBG(zm, 1);
     __syncthreads();
+    XB_DBG(zm, 2);
     for (int m = tid; m < P.nmulti; m += nt) {
       double sm = 0.0;
       for (int q = P.multi_start[m]; q < P.multi_start[m + 1]; ++q) sm += part[q];
@@ -446,6 +491,7 @@ __device__ __forceinline__ void jacobian_build_impl(const DevNet &net, const Zon
   }
   if (tid == 0) zm.s->ktot[2] += 1;
   __syncthreads();
+  XB_DBG(zm, 3);
 }
 template <bool STRICT>
 __device__ __noinline__ void jacobian_build_cta() {
@@ -454,14 +500,18 @@ __device__ __noinline__ void jacobian_build_cta() {
   else jacobian_build_impl<STRICT, false>(net, zm, zm.jac);
 }
 
+// with_rhs: zm.rhs rides through the factorisation as column N of the tile (forward solve for free)
 template <bool STRICT>
-__device__ __forceinline__ void lu_cta(const ZoneMem &zm, const int N) {
-  if (zm.tile) lu_tile<STRICT>(zm.jac, zm.ld, N, zm.indx, &zm.s->info, zm.prow, zm.rdiag, &zm.s->tile_ctr, zm.s->ph + PH_LU_PANEL);
-  else { lu_simple<STRICT>(zm.jac, zm.ld, N, zm.indx, &zm.s->info, &zm.s->piv); }
+__device__ __forceinline__ void lu_cta(const ZoneMem &zm, const int N, const bool with_rhs) {
+  if (zm.tile) {
+    // zm.rhs IS column N of the tile
+    lu_tile<STRICT>(zm.jac, zm.ld, N, with_rhs ? 1 : 0, zm.indx, &zm.s->info, zm.prow, zm.rdiag, &zm.s->tile_ctr,
+                    zm.s->ph + PH_LU_PANEL);
+  } else { lu_simple<STRICT>(zm.jac, zm.ld, N, zm.indx, &zm.s->info, &zm.s->piv); }
 }
 template <bool STRICT>
-__device__ __forceinline__ void bksub_cta(const ZoneMem &zm, const int N) {
-  if (zm.tile) bksub_block<STRICT, true>(zm.jac, zm.ld, N, zm.indx, zm.rhs, zm.rdiag, zm.prow);
+__device__ __forceinline__ void bksub_cta(const ZoneMem &zm, const int N, const bool fwd_done) {
+  if (zm.tile) bksub_block<STRICT, true>(zm.jac, zm.ld, N, zm.indx, zm.rhs, zm.rdiag, zm.prow, fwd_done);
   else bksub_simple<STRICT>(zm.jac, zm.ld, N, zm.indx, zm.rhs);
 }
 
@@ -491,12 +541,7 @@ __device__ __noinline__ void step_be_cta() {
     XB_PHASE_END(zm, PH_RATES);
     yderiv_cta<STRICT>();
     XB_PHASE_END(zm, PH_YDERIV);
-    if (rebuild) {
-      jacobian_build_cta<STRICT>();
-      XB_PHASE_END(zm, PH_JAC);
-      lu_cta<STRICT>(zm, N);
-      XB_PHASE_END(zm, PH_LU);
-    }
+    // right-hand side (xnet_integrate_be.F90:327-349); it does not depend on the Jacobian
     const double rdt = s->rdt;
     if (kit > 1) {
       for (int k = tid; k < ny; k += nt) zm.rhs[k] = A::mad(A::sub(zm.y[k], zm.yt[k]), rdt, zm.ydot[k]);
@@ -504,7 +549,13 @@ __device__ __noinline__ void step_be_cta() {
       for (int k = tid; k < ny; k += nt) zm.rhs[k] = zm.ydot[k];
     }
     __syncthreads();
-    bksub_cta<STRICT>(zm, N);
+    if (rebuild) {
+      jacobian_build_cta<STRICT>();
+      XB_PHASE_END(zm, PH_JAC);
+      lu_cta<STRICT>(zm, N, true);
+      XB_PHASE_END(zm, PH_LU);
+    }
+    bksub_cta<STRICT>(zm, N, rebuild && zm.tile);
     XB_PHASE_END(zm, PH_BKSUB);
     {
       const double *aa = net.aa;
@@ -743,7 +794,7 @@ __device__ __forceinline__ void full_net_cta(const DevZones &zn, const DevOut &o
     s->ye = zn.yestart[fx];
     s->cv = s->etae = s->detaedt9 = s->t9dot = 0.0;
     for (int k = 0; k < 5; ++k) { s->kmon[k] = 0; s->ktot[k] = 0; }
-    for (int k = 0; k < 12; ++k) s->ph[k] = 0;
+    for (int k = 0; k < PH_COUNT; ++k) s->ph[k] = 0;
     s->ints = 0; s->its = 0; s->edot = 0.0; s->sqnu = 0.0;
     if (out.hist_cap > 0) out.hist_n[iz] = 0;
     if (restart) {
