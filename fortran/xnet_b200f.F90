@@ -1,0 +1,71 @@
+!***************************************************************************************************
+! xnet_b200f.F90 -- iso_c_binding interface blocks for libxnet_b200.so (include/xnet_b200.h), in the
+! idiom of the reference's own vendor bindings (source/cublasf.F90:252-263: `type(c_ptr), value`,
+! `integer(c_int), value`, bind(c,name=...)).  NOT compiled in this repository (no Fortran compiler
+! in the build image); it is the reference-side half of the drop-in boundary.
+!***************************************************************************************************
+Module xnet_b200f
+  Use, Intrinsic :: iso_c_binding
+  Implicit None
+
+  ! struct xb_net_arrays (include/xnet_b200.h:52-68)
+  Type, Bind(C) :: xb_net_arrays
+    Integer(C_INT32_T) :: ny, nffn, nnnu
+    Integer(C_INT32_T) :: nreac(4), nan(4)
+    Type(C_PTR) :: rc(4), ni(4)
+    Integer(C_INT32_T) :: ni_ld(4)
+    Type(C_PTR) :: iwk(4), irev(4)
+    Type(C_PTR) :: la, le
+    Type(C_PTR) :: mu(4), a(4)
+    Type(C_PTR) :: aa, zz, mex, be
+    Real(C_DOUBLE) :: mex_n, mex_p
+    Type(C_PTR) :: g, t9i, ffnsum, ffnenu
+    Type(C_PTR) :: ffn_ec = C_NULL_PTR, ffn_beta = C_NULL_PTR, ffn_qval = C_NULL_PTR, has_logft = C_NULL_PTR
+  End Type xb_net_arrays
+
+  ! struct xb_ctl (include/xnet_b200.h:71-77)
+  Type, Bind(C) :: xb_ctl_t
+    Integer(C_INT32_T) :: iweak0, iscrn, iheat, isolv, kstmx, kitmx, ijac, iconvc
+    Real(C_DOUBLE) :: changemx, changemxt, yacc, tolm, tolc, tolt9, ymin, tdel_maxmult
+    Integer(C_INT32_T) :: arith, reserved
+  End Type xb_ctl_t
+
+  Interface
+    Integer(C_INT) Function xb_net_from_arrays(arr,net) Bind(C,name="xb_net_from_arrays")
+      Import ; Type(C_PTR), Value :: arr ; Type(C_PTR) :: net
+    End Function
+    Subroutine xb_net_free(net) Bind(C,name="xb_net_free")
+      Import ; Type(C_PTR), Value :: net
+    End Subroutine
+    Integer(C_INT) Function xb_ctx_create(net,ctl,nzevolve,device,ctx) Bind(C,name="xb_ctx_create")
+      Import ; Type(C_PTR), Value :: net, ctl ; Integer(C_INT32_T), Value :: nzevolve, device ; Type(C_PTR) :: ctx
+    End Function
+    Subroutine xb_ctx_destroy(ctx) Bind(C,name="xb_ctx_destroy")
+      Import ; Type(C_PTR), Value :: ctx
+    End Subroutine
+    Integer(C_INT) Function xb_cross_sect(ctx,zlo,zhi,mask,yt,t9t,rhot,xext,aext,zext,yet) Bind(C,name="xb_cross_sect")
+      Import ; Type(C_PTR), Value :: ctx, mask, yt, t9t, rhot, xext, aext, zext, yet ; Integer(C_INT32_T), Value :: zlo, zhi
+    End Function
+    Integer(C_INT) Function xb_yderiv(ctx,zlo,zhi,mask,yt,ydot) Bind(C,name="xb_yderiv")
+      Import ; Type(C_PTR), Value :: ctx, mask, yt, ydot ; Integer(C_INT32_T), Value :: zlo, zhi
+    End Function
+    Integer(C_INT) Function xb_jacobian_build(ctx,zlo,zhi,mask,diag,mult) Bind(C,name="xb_jacobian_build")
+      Import ; Type(C_PTR), Value :: ctx, mask, diag, mult ; Integer(C_INT32_T), Value :: zlo, zhi
+    End Function
+    Integer(C_INT) Function xb_get_jac(ctx,zlo,zhi,jac) Bind(C,name="xb_get_jac")
+      Import ; Type(C_PTR), Value :: ctx, jac ; Integer(C_INT32_T), Value :: zlo, zhi
+    End Function
+    Integer(C_INT) Function xb_jacobian_decomp(ctx,zlo,zhi,mask,info) Bind(C,name="xb_jacobian_decomp")
+      Import ; Type(C_PTR), Value :: ctx, mask, info ; Integer(C_INT32_T), Value :: zlo, zhi
+    End Function
+    Integer(C_INT) Function xb_jacobian_bksub(ctx,zlo,zhi,mask,yrhs,t9rhs,dy,dt9) Bind(C,name="xb_jacobian_bksub")
+      Import ; Type(C_PTR), Value :: ctx, mask, yrhs, t9rhs, dy, dt9 ; Integer(C_INT32_T), Value :: zlo, zhi
+    End Function
+    Integer(C_INT) Function xb_jacobian_solve(ctx,zlo,zhi,mask,yrhs,t9rhs,dy,dt9,info) Bind(C,name="xb_jacobian_solve")
+      Import ; Type(C_PTR), Value :: ctx, mask, yrhs, t9rhs, dy, dt9, info ; Integer(C_INT32_T), Value :: zlo, zhi
+    End Function
+    Integer(C_INT) Function xb_evolve(ctx,zones,out) Bind(C,name="xb_evolve")
+      Import ; Type(C_PTR), Value :: ctx, zones, out
+    End Function
+  End Interface
+End Module xnet_b200f
