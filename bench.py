@@ -24,8 +24,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 DATA = os.path.join(ROOT, 'data')
 
-WORKLOADS = {
+WORKLOADS = {   # settings fragment, problem setup, description[, screening switch]
+    'sn160_scrn': ('test_settings', 'setup_tnsn_sn160', 'SN160 (160 species, 2048 reactions), BE, screening on, th_sn1aflame', 1),
     'sn160': ('test_settings', 'setup_tnsn_sn160', 'SN160 (160 species, 2048 reactions), BE, th_sn1aflame'),
+    'sn160_heat': ('test_settings_heat', 'setup_heat_sn160', 'SN160, BE, self-heating + screening, C/O burn (test_settings_heat)'),
     'torch47': ('test_settings', 'setup_tnsn_torch47', 'torch47 (47 species), BE, th_sn1aflame'),
     'alpha': ('test_settings_small', 'setup_tnsn_alpha', 'alpha (14 species), BE, th_sn1aflame'),
     'xrb304': ('test_settings', 'setup_xrb_fisker', 'XRB304 (304 species), BE, th_fisker_aboveign_b1'),
@@ -33,8 +35,13 @@ WORKLOADS = {
 
 
 def control_text(w):
-    st, su, _ = WORKLOADS[w]
-    return open(os.path.join(DATA, st)).read() + open(os.path.join(DATA, 'Test_Problems', su)).read()
+    st, su = WORKLOADS[w][:2]
+    txt = open(os.path.join(DATA, st)).read() + open(os.path.join(DATA, 'Test_Problems', su)).read()
+    if len(WORKLOADS[w]) > 3 and WORKLOADS[w][3]:
+        off = '0         Include Screening (yes=1)'
+        assert off in txt
+        txt = txt.replace(off, '1         Include Screening (yes=1)')
+    return txt
 
 
 class ClockSampler(threading.Thread):
@@ -240,8 +247,9 @@ def main():
                      'peak_source': 'FP64 FMA microbenchmark measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry)',
                      'phase_share': {k: round(ph[k] / phase_tot, 4) for k in ('rates', 'yderiv', 'jac', 'lu', 'bksub', 'other', 'lu_panel', 'lu_swap_trsm', 'lu_gemm')},
                      'cycles_per_newton_iter': phase_tot / max(newton, 1.0),
-                     'pivoting_panel_fallbacks_per_lu': ph['spare'] / max(nlu, 1.0),
-                     'dbg_cycles_per_newton_iter': [round(ph['dbg%d' % k] / max(newton, 1.0)) for k in range(12)],
+                     'pivot_steps_per_lu': ph['spare'] / max(nlu, 1.0),
+                     'partially_accepted_panels_per_lu': ph['dbg8'] / max(nlu, 1.0),
+                     'dbg_cycles_per_newton_iter': [round(ph['dbg%d' % k] / max(newton, 1.0)) for k in range(12) if k != 8],
                      'hbm_note': 'Jacobian/csect/state never touch HBM (shared memory / L2 scratch); HBM traffic per launch is '
                                  'inputs+outputs only: %.3g GB/s of measured %.0f GB/s' % (
                                      (h2d + d2h) / (ms_launch * 1e-3) / 1e9, peaks.get('hbm_gbs', 6650.0))},

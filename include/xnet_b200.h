@@ -14,6 +14,8 @@
  *   xb_net_from_arrays    <- read_reaction_data / read_nuclear_data module state
  *                            (source/xnet_data.F90:391-513, 654-956)
  *   xb_net_load           <- net_preprocess + read_* from files (source/xnet_preprocess.F90:505-1011)
+ *   xb_net_load_helm      <- actual_eos_init (tools/starkiller-helmholtz/actual_eos.F90:1520-1700): reads
+ *                            helm_table.dat (ASCII, reference format) or the packed helm_table.bin
  *   xb_ctx_create         <- read_jacobian_data (source/xnet_jacobian_dense.F90:54-119), be_init
  *                            (source/xnet_integrate_be.F90:484-551)
  *   xb_ctx_destroy        <- jacobian_finalize (source/xnet_jacobian_dense.F90:121-134)
@@ -84,6 +86,9 @@ long long xb_launch_count(int reset);
 /* ---- network ---------------------------------------------------------------------------- */
 int xb_net_load(const char *data_dir, int iweak0, xb_net **net);
 int xb_net_from_arrays(const xb_net_arrays *arr, xb_net **net);
+/* Helmholtz table for screening / self-heating (required before xb_ctx_create with iscrn>0 or iheat>0).
+ * path: XNet's ASCII helm_table.dat, or the packed 13-plane float64 file written by tools/make_helm_table.py */
+int xb_net_load_helm(xb_net *net, const char *path);
 void xb_net_free(xb_net *net);
 /* introspection (tests check these bit-exactly): what = "ny","nffn","nnnu","nreac1".."nreac4",
  * "nan1".."nan4","izmax" */

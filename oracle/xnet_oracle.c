@@ -31,18 +31,7 @@
 #include <omp.h>
 #endif
 
-#ifdef OX_PMATH
-#include "ox_pmath.h"
-#define M_EXP(x) oxp_exp(x)
-#define M_LOG(x) oxp_log(x)
-#define M_LOG10(x) oxp_log10(x)
-#define M_POW10(x) oxp_pow10(x)
-#else
-#define M_EXP(x) exp(x)
-#define M_LOG(x) log(x)
-#define M_LOG10(x) log10(x)
-#define M_POW10(x) pow(10.0, (x))
-#endif
+#include "ox_math.h"
 
 #define NG 24
 #define NT9GRID 13
@@ -239,8 +228,8 @@ static int cross_sect(zone_t *z) {
 #else
   t09[2] = pow(t9t, -1.0 / 3.0); t09[3] = pow(t9t, 1.0 / 3.0); t09[5] = pow(t9t, 5.0 / 3.0); t09[6] = log(t9t);
 #endif
-  dt09[0] = 0.0; dt09[1] = -(1.0 / (t9t * t9t)); dt09[2] = -pow(t9t, -4.0 / 3.0) / 3.0;
-  dt09[3] = pow(t9t, -2.0 / 3.0) / 3.0; dt09[4] = 1.0; dt09[5] = pow(t9t, 2.0 / 3.0) * 5.0 / 3.0;
+  dt09[0] = 0.0; dt09[1] = -(1.0 / (t9t * t9t)); dt09[2] = -M_POW(t9t, -4.0 / 3.0) / 3.0;
+  dt09[3] = M_POW(t9t, -2.0 / 3.0) / 3.0; dt09[4] = 1.0; dt09[5] = M_POW(t9t, 2.0 / 3.0) * 5.0 / 3.0;
   dt09[6] = 1.0 / t9t;
   if (net->nffn > 0) ffn_rate(z, t9t, ene);
   /* nnu_rate: ineutrino=0 -> rnnu = 0 (xnet_nnu.F90:222-233) */

@@ -93,6 +93,13 @@ def _pi(a):
     return a.ctypes.data_as(c_ip)
 
 
+def load_helm(root):
+    """13 planes [13][201][541] of the Helmholtz table (data/helm_table.bin, see tools/make_helm_table.py)"""
+    a = np.fromfile(os.path.join(root, 'helm_table.bin'), dtype='<f8')
+    assert a.size == 13 * 201 * 541, a.size
+    return a
+
+
 class Problem:
     def __init__(self, ctl, nuc, net, ffn, fixtures, helm=None):
         self.ctl, self.nuc, self.net, self.ffn, self.fixtures = ctl, nuc, net, ffn, fixtures
@@ -105,6 +112,8 @@ class Problem:
     @classmethod
     def from_control(cls, control_text, root, helm=None):
         ctl, nuc, net, ffn, zones = L.load_problem(control_text, root)
+        if helm is None and (ctl['iscrn'] > 0 or ctl['iheat'] > 0):
+            helm = load_helm(root)
         return cls(ctl, nuc, net, ffn, zones, helm)
 
     def _k(self, a):

@@ -12,8 +12,19 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
 
 
-def control_text(settings, setup):
-    return open(os.path.join(DATA, settings)).read() + open(os.path.join(DATA, 'Test_Problems', setup)).read()
+SCRN_OFF = '0         Include Screening (yes=1)'
+SCRN_ON = '1         Include Screening (yes=1)'
+
+
+def control_text(settings, setup, screening=None):
+    """control file = settings fragment + problem setup (test/test_xnet.sh:86-128); screening=1 flips the
+    'Include Screening' switch of the settings fragment (the reference ships it switched on only in
+    test_settings_heat)."""
+    txt = open(os.path.join(DATA, settings)).read() + open(os.path.join(DATA, 'Test_Problems', setup)).read()
+    if screening:
+        assert SCRN_OFF in txt
+        txt = txt.replace(SCRN_OFF, SCRN_ON)
+    return txt
 
 
 PROBLEMS = {
@@ -21,6 +32,13 @@ PROBLEMS = {
     'torch47': ('test_settings', 'setup_tnsn_torch47'),
     'sn160': ('test_settings', 'setup_tnsn_sn160'),
     'xrb304': ('test_settings', 'setup_xrb_fisker'),
+    'alpha_scrn': ('test_settings_small', 'setup_tnsn_alpha', 1),
+    'torch47_scrn': ('test_settings', 'setup_tnsn_torch47', 1),
+    'sn160_scrn': ('test_settings', 'setup_tnsn_sn160', 1),
+    # self-heating + screening (test_settings_heat; test/test_xnet.sh tests 50-52)
+    'alpha_heat': ('test_settings_heat', 'setup_heat_alpha'),
+    'torch47_heat': ('test_settings_heat', 'setup_heat_torch47'),
+    'sn160_heat': ('test_settings_heat', 'setup_heat_sn160'),
 }
 
 

@@ -32,7 +32,9 @@ def _rel(y, ref, floor=1e-20):
 
 
 # ---------------------------------------------------------------- complete trajectories, strict
-@pytest.mark.parametrize('name,cap', [('alpha', 3000), ('torch47', 3100), ('sn160', 3200)])
+@pytest.mark.parametrize('name,cap', [('alpha', 3000), ('torch47', 3100), ('sn160', 3200),
+                                      ('alpha_scrn', 3000), ('torch47_scrn', 3100), ('sn160_scrn', 3200),
+                                      ('alpha_heat', 800), ('torch47_heat', 800), ('sn160_heat', 800)])
 def test_strict_full_trajectory_bit_exact(gpu_problem, oracle_problem, name, cap):
     X, ctl, net, fx, ctx = _ctx(gpu_problem, name, 3, arith=1)
     r = ctx.full_net(X.build_zone_set(fx, nzone=3), hist_cap=cap)
@@ -42,6 +44,7 @@ def test_strict_full_trajectory_bit_exact(gpu_problem, oracle_problem, name, cap
     assert np.array_equal(r['hist_kstep'][0, :n], o['hist_kstep'][0, :n])
     assert np.array_equal(r['hist_t'][0, :n], o['hist_t'][0, :n])          # accepted-step sequence
     assert np.array_equal(r['hist_tdel'][0, :n], o['hist_tdel'][0, :n])
+    assert np.array_equal(r['hist_t9'][0, :n], o['hist_t9'][0, :n])        # evolves with self-heating
     assert np.array_equal(r['hist_kmon'][0, :n], o['hist_kmon'][0, :n])    # retries / Newton iterations
     assert np.array_equal(r['hist_y'][0, :n], o['hist_y'][0, :n])          # abundances, every step
     assert np.array_equal(r['hist_edot'][0, :n], o['hist_edot'][0, :n])
@@ -51,7 +54,7 @@ def test_strict_full_trajectory_bit_exact(gpu_problem, oracle_problem, name, cap
     ctx.close()
 
 
-@pytest.mark.parametrize('name', ['alpha', 'torch47', 'sn160', 'xrb304'])
+@pytest.mark.parametrize('name', ['alpha', 'torch47', 'sn160', 'xrb304', 'torch47_scrn', 'sn160_scrn'])
 def test_strict_against_committed_golden(gpu_problem, name):
     """Same check against the committed fixtures (tests/golden/ts_*_pm.npz), no oracle involved."""
     g = np.load(os.path.join(GOLD, 'ts_%s_pm.npz' % name))
@@ -64,7 +67,9 @@ def test_strict_against_committed_golden(gpu_problem, name):
 
 
 # ---------------------------------------------------------------- fast arithmetic
-@pytest.mark.parametrize('name,nsteps', [('alpha', 2000), ('torch47', 1200), ('sn160', 1000)])
+@pytest.mark.parametrize('name,nsteps', [('alpha', 2000), ('torch47', 1200), ('sn160', 1000),
+                                         ('alpha_scrn', 2000), ('torch47_scrn', 1200), ('sn160_scrn', 1000),
+                                         ('alpha_heat', 200), ('torch47_heat', 200), ('sn160_heat', 200)])
 def test_fast_prefix_1e10(gpu_problem, oracle_problem, name, nsteps):
     """Fast arithmetic vs the libm oracle: identical accepted-step count/retry pattern and Y (>1e-20)
     within 1e-10 relative per step over the part of the trajectory where rounding is not yet amplified
@@ -247,3 +252,39 @@ def test_resident_path_equals_e2e(gpu_problem):
     h2d, d2h = ctx.copy_bytes()
     assert d2h >= 64 * net.ny * 8
     ctx.close()
+
+
+# ---------------------------------------------------------------- screening / EOS (iscrn = 1)
+@pytest.mark.parametrize('name', ['torch47_scrn', 'sn160_scrn'])
+@pytest.mark.parametrize('arith', [1, 0])
+def test_screened_rates_module_level(gpu_problem, oracle_problem, name, arith):
+    """xb_cross_sect with screening switched on against the oracle's rate evaluation at states sampled
+    along the screened trajectory: strict arithmetic bit for bit (Helmholtz eta, Fermi-Dirac integrals,
+    plasma parameters, per-reaction blend and REACLIB exponent all included), fast arithmetic to 1e-10
+    (the rate is exp(h) with |h| up to a few hundred, so 1e-14 relative in h is 1e-12..1e-11 in the rate)."""
+    import ctypes as C
+    from oracle import xnet_oracle as O
+    X, ctl, net, fx, ctx = _ctx(gpu_problem, name, 6, arith=arith)
+    op = oracle_problem(name)
+    y, t9, rho, rdt = _states(op, name)
+    ye = ctx.cross_sect(y, t9, rho)
+    cs = ctx.csect(len(t9))
+    lib = O.lib('pm' if arith else False)
+    ny = net.ny
+    for z in range(len(t9)):
+        nrt = sum(op.net['nreac']); ocs = np.zeros(nrt); oyd = np.zeros(ny); oj = np.zeros(ny * ny); oye = np.zeros(1)
+        yy = np.ascontiguousarray(y[z])
+        assert lib.ox_eval_point(C.byref(op.cnet), C.byref(op.cctl), t9[z], rho[z], O._pd(yy), 0.0, 1.0, 0.0, rdt[z], -1.0,
+                                 O._pd(ocs), O._pd(oyd), O._pd(oj), O._pd(oye)) == 0
+        if arith:
+            assert ye[z] == oye[0] and np.array_equal(cs[z], ocs)
+        else:
+            assert abs(ye[z] / oye[0] - 1) < 1e-14
+            m = ocs > 0
+            assert np.array_equal(cs[z] > 0, m) and np.abs(cs[z][m] / ocs[m] - 1).max() < 1e-10
+    # screening must actually change the charged-particle rates
+    X0, ctl0, net0, fx0, ctx0 = _ctx(gpu_problem, name.replace('_scrn', ''), 6, arith=arith)
+    ctx0.cross_sect(y, t9, rho)
+    cs0 = ctx0.csect(len(t9))
+    assert (cs >= cs0).all() and (cs > cs0 * (1 + 1e-6)).any()
+    ctx.close(); ctx0.close()

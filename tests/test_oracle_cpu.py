@@ -138,3 +138,102 @@ def test_zone_replication_and_threads(oracle_problem):
     b = p.run(nzone=5, nthreads=4)
     assert np.array_equal(a['y'], b['y']) and np.array_equal(a['ktot'], b['ktot'])
     assert all(np.array_equal(a['y'][0], a['y'][k]) for k in range(5))
+
+
+# ---------------------------------------------------------------- EOS / Fermi-Dirac / screening pins
+def _olib():
+    import ctypes as C
+    from oracle import xnet_oracle as O
+    l = O.lib('strict')
+    for f in ('ox_fdm3h', 'ox_fdm1h', 'ox_fd1h'):
+        getattr(l, f).restype = C.c_double
+        getattr(l, f).argtypes = [C.c_double]
+    return l
+
+
+@pytest.mark.parametrize('x', [-30, -5, -2.0001, -2, -1, -1e-3, 0, 0.5, 1.999, 2, 3.3, 5, 7, 10, 13, 20, 31, 40, 55, 200])
+def test_fermi_dirac_against_quadrature(x):
+    """Pins the restated Fukushima approximations (every interval of every order) to the DEFINITION of the
+    integrals, F_k(x) = int_0^inf t^k/(exp(t-x)+1) dt, by adaptive quadrature: 1e-13 relative for k=+-1/2;
+    F_{-3/2} through d/dx F_{-1/2} = -1/2 F_{-3/2} (central difference of the quadrature, 1e-6)."""
+    from scipy import integrate
+    l = _olib()
+
+    def fd(k, xx):   # t = u^2 removes the square-root singularity
+        h = lambda u: 2 * u ** (2 * k + 1) / (np.exp(min(u * u - xx, 700.0)) + 1.0)
+        return integrate.quad(h, 0, np.sqrt(max(xx, 0) + 60), limit=400, epsabs=0, epsrel=1e-13)[0]
+    assert abs(l.ox_fd1h(x) / fd(0.5, x) - 1) < 1e-13
+    assert abs(l.ox_fdm1h(x) / fd(-0.5, x) - 1) < 1e-13
+    h = 1e-4 * max(1.0, abs(x))
+    d = (fd(-0.5, x + h) - fd(-0.5, x - h)) / (2 * h)
+    assert abs(l.ox_fdm3h(x) / (-2 * d) - 1) < 1e-5
+
+
+def test_helmholtz_eta_and_cv_consistency():
+    """Helmholtz pieces: d(eta)/dT9 returned by the bicubic interpolation equals the finite difference of
+    eta itself (pins the derivative weights), and cv reproduces the ideal-gas + radiation limit at low
+    density (ions 3/2 k/(A m_u), fully ionised electrons 3/2 k Ye/m_u, radiation 4aT^3/rho) to 1 %."""
+    import ctypes as C
+    from oracle import xnet_oracle as O
+    p = O.Problem.from_control(control_text('test_settings_small', 'setup_tnsn_alpha', 1), DATA)
+    l = O.lib('strict')
+    l.ox_eos_interface.restype = C.c_int
+    c_dp = C.POINTER(C.c_double)
+    ny = p.nuc['ny']
+    y = np.zeros(ny); y[0] = 1.0 / p.nuc['aa'][0]   # pure 4He
+
+    def eos(t9, rho):
+        out = [C.c_double() for _ in range(4)]
+        rc = l.ox_eos_interface(C.byref(p.cnet), C.byref(p.cctl), C.c_double(t9), C.c_double(rho), y.ctypes.data_as(c_dp),
+                                C.c_double(0.0), C.c_double(1.0), C.c_double(0.0), *[C.byref(o) for o in out])
+        assert rc == 0
+        return [o.value for o in out]   # ye, cv [MeV/GK/nucleon], eta, detadt9
+    for t9, rho in [(0.01, 1.0), (0.5, 1e5), (1.0, 1e7), (3.0, 1e9), (4.7, 2e9)]:
+        ye, cv, eta, deta = eos(t9, rho)
+        h = 1e-6 * t9
+        fd = (eos(t9 + h, rho)[2] - eos(t9 - h, rho)[2]) / (2 * h)
+        assert ye == 0.5 and abs(deta / fd - 1) < 1e-6
+    amu = 1.0 / (6.022140857e+23 * 1.6021766208e-06)
+    cv_cgs = eos(0.01, 1.0)[1] / (amu * 1e9)
+    ideal = 1.5 * 1.380650424e-16 * 6.0221417930e23 * (0.25 + 0.5) + 4 * 7.5657e-15 * 1e21
+    assert abs(cv_cgs / ideal - 1) < 1e-2
+
+
+def test_screening_enhances_charged_particle_rates_only():
+    """ox_screening: factors are zero for reactions with a neutral reactant pair (zeta_w = 0), positive
+    otherwise, grow with density, and the weak-screening limit h = ztilde*lambda0*Z1*Z2 holds at low density."""
+    import ctypes as C
+    from oracle import xnet_oracle as O
+    p = O.Problem.from_control(control_text('test_settings', 'setup_tnsn_torch47', 1), DATA)
+    l = O.lib('strict')
+    ny = p.nuc['ny']; nr = p.net['nreac']
+    y = np.zeros(ny); y[:] = 1.0 / (ny * np.asarray(p.nuc['aa']))
+    zz = np.asarray(p.nuc['zz'])
+    n2 = np.asarray(p.net['n2']).reshape(-1, 6)
+    zw = zz[n2[:, 0] - 1] * zz[n2[:, 1] - 1]
+
+    def h2(t9, rho):
+        nrt = sum(nr); ocs = np.zeros(nrt); oyd = np.zeros(ny); oj = np.zeros(ny * ny); oye = np.zeros(1)
+        assert l.ox_eval_point(C.byref(p.cnet), C.byref(p.cctl), t9, rho, O._pd(y), 0.0, 1.0, 0.0, 1.0, -1.0,
+                               O._pd(ocs), O._pd(oyd), O._pd(oj), O._pd(oye)) == 0
+        return ocs[nr[0]:nr[0] + nr[1]]
+    p0 = O.Problem.from_control(control_text('test_settings', 'setup_tnsn_torch47'), DATA)
+
+    def h2_off(t9, rho):
+        nrt = sum(nr); ocs = np.zeros(nrt); oyd = np.zeros(ny); oj = np.zeros(ny * ny); oye = np.zeros(1)
+        assert l.ox_eval_point(C.byref(p0.cnet), C.byref(p0.cctl), t9, rho, O._pd(y), 0.0, 1.0, 0.0, 1.0, -1.0,
+                               O._pd(ocs), O._pd(oyd), O._pd(oj), O._pd(oye)) == 0
+        return ocs[nr[0]:nr[0] + nr[1]]
+    for t9, rho in [(1.0, 1e6), (2.0, 1e8), (0.5, 1e9)]:
+        on, off = h2(t9, rho), h2_off(t9, rho)
+        live = off > 0
+        assert np.array_equal(on[live & (zw == 0)], off[live & (zw == 0)])
+        assert (on[live & (zw > 0)] > off[live & (zw > 0)]).all()
+    f_lo = (h2(1.0, 1e4) / np.where(h2_off(1.0, 1e4) > 0, h2_off(1.0, 1e4), 1))[(zw > 0) & (h2_off(1.0, 1e4) > 0)]
+    f_hi = (h2(1.0, 1e8) / np.where(h2_off(1.0, 1e8) > 0, h2_off(1.0, 1e8), 1))[(zw > 0) & (h2_off(1.0, 1e8) > 0)]
+    assert (f_hi > f_lo).all() and f_lo.max() < 1.25
+    # weak-screening limit (lambda <= 0.1): ln(enhancement) = ztilde*lambda0 * Z1*Z2, one constant for all reactions
+    sel = (zw > 0) & (h2_off(1.0, 1e4) > 0)
+    k = np.log(f_lo) / zw[sel]
+    k = k[np.log(f_lo) < 0.09]
+    assert k.size > 10 and np.ptp(k) / k.mean() < 1e-9

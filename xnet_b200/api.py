@@ -19,7 +19,8 @@ class XnetB200Error(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, 'libxnet_b200.so')
+    # XNET_B200_LIB: development aid for A/B-testing kernel variants built next to the library
+    return os.environ.get('XNET_B200_LIB') or os.path.join(_HERE, 'libxnet_b200.so')
 
 
 class XbCtl(C.Structure):
@@ -49,7 +50,7 @@ class XbOut(C.Structure):
 _lib = None
 
 # every symbol include/xnet_b200.h declares (tests check the library exports all of them)
-EXPORTS = ['xb_last_error', 'xb_version', 'xb_launch_count', 'xb_net_load', 'xb_net_from_arrays', 'xb_net_free',
+EXPORTS = ['xb_last_error', 'xb_version', 'xb_launch_count', 'xb_net_load', 'xb_net_load_helm', 'xb_net_from_arrays', 'xb_net_free',
            'xb_net_int', 'xb_net_itable', 'xb_net_dtable', 'xb_read_thermo', 'xb_read_inab', 'xb_zone_start',
            'xb_ctx_create', 'xb_ctx_destroy', 'xb_cross_sect', 'xb_get_csect', 'xb_yderiv', 'xb_jacobian_build',
            'xb_get_jac', 'xb_set_jac', 'xb_jacobian_decomp', 'xb_get_indx', 'xb_jacobian_bksub',
@@ -70,6 +71,7 @@ def lib():
         l.xb_launch_count.argtypes = [C.c_int]
         l.xb_net_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
         l.xb_net_free.argtypes = [C.c_void_p]
+        l.xb_net_load_helm.argtypes = [C.c_void_p, C.c_char_p]
         l.xb_net_int.argtypes = [C.c_void_p, C.c_char_p, c_ip]
         l.xb_net_itable.argtypes = [C.c_void_p, C.c_char_p, c_ip, C.c_int64, C.POINTER(C.c_int64)]
         l.xb_net_dtable.argtypes = [C.c_void_p, C.c_char_p, c_dp, C.c_int64, C.POINTER(C.c_int64)]
@@ -203,6 +205,19 @@ class Network:
         self.nreac = [self.int('nreac%d' % k) for k in (1, 2, 3, 4)]
         self.nan = [self.int('nan%d' % k) for k in (1, 2, 3, 4)]
         self.nffn = self.int('nffn'); self.nnnu = self.int('nnnu')
+        self.helm_loaded = False
+
+    def load_helm(self, path=None):
+        """Helmholtz table for screening / self-heating (XNet reads helm_table.dat from the run directory);
+        default: helm_table.bin or helm_table.dat next to the network directory."""
+        if self.helm_loaded:
+            return
+        if path is None:
+            root = os.path.dirname(os.path.abspath(self.data_dir.rstrip('/')))
+            cands = [os.path.join(root, n) for n in ('helm_table.bin', 'helm_table.dat')]
+            path = next((p for p in cands if os.path.exists(p)), cands[0])
+        _chk(lib().xb_net_load_helm(self.h, path.encode()))
+        self.helm_loaded = True
 
     def int(self, what):
         v = C.c_int32()
@@ -312,6 +327,8 @@ class Context:
     def __init__(self, net, controls, nzevolve=1, device=0, arith=0, **override):
         self.net = net
         self.ctl = controls.to_struct(arith=arith, **override)
+        if self.ctl.iscrn > 0 or self.ctl.iheat > 0:
+            net.load_helm()
         self.h = C.c_void_p()
         self.nzevolve = nzevolve
         _chk(lib().xb_ctx_create(net.h, C.byref(self.ctl), nzevolve, device, C.byref(self.h)))

@@ -60,6 +60,8 @@ struct xb_ctx {
   // network tables
   DevBuf<double> rcT, a[4], aa, zz, mex, be, g, lng, dlng, t9i, ffnsum, ffnenu;
   DevBuf<int> ni, iwk, irev, iffn, la, le, mu[4], nn[4][4], ffr_n1, ffr_iffn;
+  DevBuf<double> helm, helm_t, helm_d, zzi, zseq53, sc_zw, sc_zi, z_zexti;
+  DevBuf<int2> sc_iz;
   // term plans (ydot, Jacobian)
   struct PlanBufs { DevBuf<double> a; DevBuf<uint2> nn, mc; DevBuf<int> seg_start, seg_dest, multi_start, multi_dest; } pby, pbj;
   int ld = 0, npart = 0;
@@ -88,7 +90,7 @@ struct xb_ctx {
 
 // ------------------------------------------------------------------------------------------------
 // shared-memory carve-up of one zone
-static SmemOff smem_layout(int ny, int N, int ld, int npart, bool jac_in_smem) {
+static SmemOff smem_layout(int ny, int N, int ld, int npart, bool jac_in_smem, int nzs) {
   SmemOff L{};
   size_t o = 0;
   L.scal = (int)o; o += (sizeof(ZoneScalars) + 15) / 16 * 16;
@@ -104,9 +106,12 @@ static SmemOff smem_layout(int ny, int N, int ld, int npart, bool jac_in_smem) {
   o = (o + 15) / 16 * 16;
   L.part = (int)o; o += (size_t)npart * 8;
   o = (o + 15) / 16 * 16;
-  L.prow = (int)o; o += (size_t)2 * kPanelWarps * kPanelRec * 8;
+  L.prow = (int)o; o += (size_t)kPbufDoubles * 8;
   L.indx = (int)o; o += (size_t)N * 4;
+  L.orig = (int)o; o += (size_t)N * 4;
+  L.pos = (int)o; o += (size_t)N * 4;
   o = (o + 15) / 16 * 16;
+  L.fhs = (int)o; o += (size_t)2 * nzs * 8;
   L.cs = (int)o;
   L.total = (int)o;
   return L;
@@ -124,6 +129,8 @@ static __device__ void zone_prologue(const DevScratch &scr, double *csect, doubl
     s->g_prod = g + scr.off_prod;
     s->g_jac = jacg ? jacg : g + scr.off_jac;
     s->g_yo = g + scr.off_yo;
+    s->g_dcsect = g + scr.off_dcsect;
+    s->g_dlnrffn = g + scr.off_dlnrffn;
     reinterpret_cast<double *>(xb_smem + c_net.lay.yt)[c_net.ny] = 1.0;
   }
   __syncthreads();
@@ -181,11 +188,13 @@ module_kernel(const __grid_constant__ ModArgs ma, const __grid_constant__ DevScr
     for (int k = tid; k < ny; k += nt) zm.yt[k] = ma.yt[(size_t)iz * ny + k];
   if (OP == OP_YDERIV || OP == OP_JBUILD)
     for (int k = net.cs_lo + tid; k < net.nrtot; k += nt) zm.cs_sm[k - net.cs_lo] = zm.csect[k];
+  for (int k = tid; k < N; k += nt) { zm.orig[k] = k; zm.pos[k] = k; }   // module level: LAPACK order, no prediction
   if (tid == 0) {
     for (int k = 0; k < 5; ++k) s->ktot[k] = 0;
     for (int k = 0; k < PH_COUNT; ++k) s->ph[k] = 0;
     s->t9t = ma.t9t[iz]; s->rhot = ma.rhot[iz];
     s->xext = ma.ext[3 * iz]; s->aext = ma.ext[3 * iz + 1]; s->zext = ma.ext[3 * iz + 2];
+    s->zexti = (s->zext == 0.0) ? 0.0 : pow(s->zext, 1.58);
     s->rdt = ma.diag[iz]; s->mult = ma.mult[iz];
   }
   __syncthreads();
@@ -213,8 +222,8 @@ module_kernel(const __grid_constant__ ModArgs ma, const __grid_constant__ DevScr
     // factors are read straight from HBM/L2 (each element is used once); rdiag is not kept between calls
     for (int k = tid; k < N; k += nt) { zm.indx[k] = ma.indx[(size_t)iz * N + k] - 1; zm.rhs[k] = ma.rhs[(size_t)iz * N + k]; }
     __syncthreads();
-    if (net.tile) bksub_block<STRICT, false>(gj, N, N, zm.indx, zm.rhs, nullptr, zm.prow, false);
-    else bksub_simple<STRICT>(gj, N, N, zm.indx, zm.rhs);
+    if (net.tile) bksub_block<STRICT, false>(gj, N, N, zm.indx, zm.rhs, nullptr, zm.prow, false, true);
+    else bksub_simple<STRICT>(gj, N, N, zm.indx, zm.rhs, true);
     for (int k = tid; k < N; k += nt) ma.rhs[(size_t)iz * N + k] = zm.rhs[k];
   }
 }
@@ -286,6 +295,12 @@ int xb_net_from_arrays(const xb_net_arrays *A, xb_net **net) {
     }
   h.chap_la.assign(kNChap, 0); h.chap_le.assign(kNChap, 0);
   *net = n;
+  return XB_OK;
+}
+
+int xb_net_load_helm(xb_net *net, const char *path) {
+  if (!net || !path) return fail(XB_ERR_ARG, "xb_net_load_helm: null argument");
+  try { load_helm_table(path, net->h); } catch (const std::exception &e) { return fail(XB_ERR_IO, e.what()); }
   return XB_OK;
 }
 
@@ -484,6 +499,60 @@ static int upload_network(xb_ctx *c) {
   CUDA_TRY(c->ffnsum.put(h.ffnsum)); CUDA_TRY(c->ffnenu.put(h.ffnenu));
   d.aa = c->aa.p; d.zz = c->zz.p; d.mex = c->mex.p; d.be = c->be.p; d.g = c->g.p; d.lng = c->lng.p; d.dlng = c->dlng.p;
   d.t9i = c->t9i.p; d.ffnsum = c->ffnsum.p; d.ffnenu = c->ffnenu.p;
+  // composition moment table (always: cheap) and, for screening / self-heating, the EOS and screening tables
+  {
+    std::vector<double> zzi(std::max(ny, 1), 0.0);
+    for (int k = 0; k < ny; ++k) zzi[k] = std::pow(h.zz[k], 1.58);            // zzi = zz**thbim1 (xnet_data.F90:471)
+    CUDA_TRY(c->zzi.put(zzi)); d.zzi = c->zzi.p;
+  }
+  d.nzs = 0;
+  if (c->ctl.iscrn > 0 || c->ctl.iheat > 0) {
+    if (h.helm.size() != (size_t)13 * kHelmI * kHelmJ) return fail(XB_ERR_ARG, "Helmholtz table not loaded (xb_net_load_helm)");
+    CUDA_TRY(c->helm.put(h.helm)); d.helm = c->helm.p;
+    // grid of the table (actual_eos.F90:1590-1607): t(j) = 10**(tlo + (j-1)*tstp), d(i) = 10**(dlo + (i-1)*dstp)
+    const double tlo = 3.0, dlo = -12.0, tstp = (13.0 - 3.0) / 200.0, dstp = (15.0 - (-12.0)) / 540.0;
+    std::vector<double> ht(kHelmJ), hd(kHelmI);
+    for (int j = 1; j <= kHelmJ; ++j) ht[j - 1] = std::pow(10.0, tlo + (double)(j - 1) * tstp);
+    for (int i = 1; i <= kHelmI; ++i) hd[i - 1] = std::pow(10.0, dlo + (double)(i - 1) * dstp);
+    CUDA_TRY(c->helm_t.put(ht)); CUDA_TRY(c->helm_d.put(hd)); d.helm_t = c->helm_t.p; d.helm_d = c->helm_d.p;
+  }
+  if (c->ctl.iscrn > 0) {
+    // screening_init (xnet_screening.F90:45-148): reaction charge parameters; zseq53 (xnet_data.F90:473-476).
+    // The per-charge table covers every composite charge that can occur (the reference sizes it izmax+2).
+    const double bip1 = 1.86;
+    const int izmax = h.izmax;
+    d.nzs = izmax + 3;   // the reference's table: 0 .. izmax+2; grown below to the largest composite charge
+    for (int cI = 1; cI < 4; ++cI)
+      for (int k = 0; k < h.nreac[cI]; ++k) {
+        int izc = 0;
+        for (int j = 0; j <= cI; ++j) izc += (int)std::lrint(h.zz[h.ni[cI][(size_t)k * 6 + j] - 1]);
+        d.nzs = std::max(d.nzs, izc + 1);
+      }
+    std::vector<double> z53(d.nzs);
+    for (int j = 0; j < d.nzs; ++j) z53[j] = std::pow((double)j, 5.0 / 3.0);
+    CUDA_TRY(c->zseq53.put(z53)); d.zseq53 = c->zseq53.p;
+    std::vector<double> zw(nrt, 0.0), zi(nrt, 0.0);
+    std::vector<int2> izp(nrt, make_int2(0, 0));
+    for (int cI = 1; cI < 4; ++cI)
+      for (int k = 0; k < h.nreac[cI]; ++k) {
+        const int gk = d.roff[cI] + k, nreact = cI + 1;
+        double z[4] = {0, 0, 0, 0}; int iz[4] = {0, 0, 0, 0}, izc = 0;
+        for (int j = 0; j < nreact; ++j) { z[j] = h.zz[h.ni[cI][(size_t)k * 6 + j] - 1]; iz[j] = (int)std::lrint(z[j]); izc += iz[j]; }
+        const double zc = (double)izc;
+        if (cI == 1) { zw[gk] = z[0] * z[1]; zi[gk] = std::pow(zc, bip1) - std::pow(z[0], bip1) - std::pow(z[1], bip1); }
+        else if (cI == 2) {
+          zw[gk] = z[0] * z[1] + z[0] * z[2] + z[1] * z[2];
+          zi[gk] = std::pow(zc, bip1) - std::pow(z[0], bip1) - std::pow(z[1], bip1) - std::pow(z[2], bip1);
+        } else {
+          zw[gk] = z[0] * (z[1] + z[2] + z[3]) + z[1] * (z[2] + z[3]) + z[2] * z[3];
+          zi[gk] = std::pow(zc, bip1) - std::pow(z[0], bip1) - std::pow(z[1], bip1) - std::pow(z[2], bip1) - std::pow(z[3], bip1);
+        }
+        if (izc >= d.nzs) return fail(XB_ERR_ARG, "composite charge outside the screening table");
+        izp[gk] = make_int2(iz[0] | (iz[1] << 8) | (iz[2] << 16) | (iz[3] << 24), izc);
+      }
+    CUDA_TRY(c->sc_zw.put(zw)); CUDA_TRY(c->sc_zi.put(zi)); CUDA_TRY(c->sc_iz.put(izp));
+    d.sc_zw = c->sc_zw.p; d.sc_zi = c->sc_zi.p; d.sc_iz = c->sc_iz.p;
+  }
   return XB_OK;
 }
 
@@ -606,7 +675,7 @@ static int build_plans(xb_ctx *c, int NT, int ld) {
     if (key != prev) {
       ++id; prev = key;
       const int i0 = key / N, col = key % N;
-      js_start.push_back((int)r); js_dest.push_back(((i0 + col * ld) << 1) | (i0 == col ? 1 : 0));
+      js_start.push_back((int)r); js_dest.push_back(((col << 10 | i0) << 1) | (i0 == col ? 1 : 0));   // device: column*ld + slot(row)
     }
     rj[r].fseg = id; rj[r].sseg = id; rj[r].fdest = js_dest.back();
   }
@@ -628,12 +697,15 @@ static int configure_launch(xb_ctx *c) {
   const size_t max_smem = prop.sharedMemPerBlockOptin;
   c->threads = N <= 32 ? 64 : (N <= 64 ? 128 : XB_MAX_THREADS);
   // Jacobian tile in shared memory (odd leading dimension) when it fits and the register-panel LU applies
-  int rc = build_plans(c, c->threads, N | 1); if (rc) return rc;
-  SmemOff L = smem_layout(ny, N, c->ld, c->npart, true);
+  // leading dimension of the shared tile: 4 (mod 8) makes the DMMA fragment accesses of the trailing update
+  // (and the column accesses everywhere else) bank-conflict free
+  int ld_tile = N; while ((ld_tile & 7) != 4) ++ld_tile;
+  int rc = build_plans(c, c->threads, ld_tile); if (rc) return rc;
+  SmemOff L = smem_layout(ny, N, c->ld, c->npart, true, c->dn.nzs);
   c->jac_in_smem = (N <= 192 && c->threads >= ((N + 31) / 32) * 32 && (size_t)L.total + 64 <= max_smem) ? 1 : 0;
   if (!c->jac_in_smem) {
     rc = build_plans(c, c->threads, N); if (rc) return rc;
-    L = smem_layout(ny, N, c->ld, c->npart, false);
+    L = smem_layout(ny, N, c->ld, c->npart, false, c->dn.nzs);
   }
   {  // whatever shared memory is left caches csect (the tail of the reaction list: 2-, 3-, 4-body rates first)
     const size_t budget = max_smem - 64;
@@ -658,6 +730,8 @@ static int configure_launch(xb_ctx *c) {
   s.off_csect = o; o += c->dn.nrtot;
   s.off_rffn = o; o += std::max(c->dn.nffn, 1);
   s.off_qkffn = o; o += c->dn.nffn + 1;
+  s.off_dcsect = o; if (c->ctl.iheat > 0) o += c->dn.nrtot;
+  s.off_dlnrffn = o; if (c->ctl.iheat > 0) o += std::max(c->dn.nffn, 1);
   o = (o + 15) / 16 * 16;
   s.off_prod = o; if (c->ctl.arith) o += (size_t)std::max(c->dn.py.L, c->dn.pj.L) * c->threads;
   o = (o + 15) / 16 * 16;
@@ -677,8 +751,6 @@ static int configure_launch(xb_ctx *c) {
 
 int xb_ctx_create(const xb_net *net, const xb_ctl *ctl, int32_t nzevolve, int32_t device, xb_ctx **ctx) {
   if (!net || !ctl || !ctx || nzevolve < 1) return fail(XB_ERR_ARG, "xb_ctx_create: bad argument");
-  if (ctl->iscrn > 0 || ctl->iheat > 0)
-    return fail(XB_ERR_UNSUPPORTED, "screening / self-heating are not built yet (iscrn, iheat must be 0)");
   if (ctl->isolv != 1) return fail(XB_ERR_UNSUPPORTED, "only isolv=1 (backward Euler) is built");
   int ndev = 0;
   CUDA_TRY(cudaGetDeviceCount(&ndev));
@@ -705,7 +777,8 @@ void xb_ctx_destroy(xb_ctx *c) {
   cudaDeviceSynchronize();
   // DevBuf members are plain pointers: release explicitly
   c->rcT.release(); c->aa.release(); c->zz.release(); c->mex.release(); c->be.release(); c->g.release(); c->lng.release();
-  c->dlng.release(); c->t9i.release(); c->ffnsum.release(); c->ffnenu.release(); c->ni.release(); c->iwk.release();
+  c->dlng.release(); c->t9i.release(); c->helm.release(); c->helm_t.release(); c->helm_d.release(); c->zzi.release();
+  c->zseq53.release(); c->sc_zw.release(); c->sc_zi.release(); c->z_zexti.release(); c->sc_iz.release(); c->ffnsum.release(); c->ffnenu.release(); c->ni.release(); c->iwk.release();
   c->irev.release(); c->iffn.release(); c->la.release(); c->le.release();
   for (int k = 0; k < 4; ++k) { c->a[k].release(); c->mu[k].release(); for (int r = 0; r < 4; ++r) c->nn[k][r].release(); }
   c->scratch.release(); c->phase.release(); c->counter.release();
@@ -756,6 +829,8 @@ static int module_state(xb_ctx *c) {
 static int check_slice(xb_ctx *c, int zlo, int zhi) {
   if (!c) return fail(XB_ERR_ARG, "null context");
   if (zlo < 1 || zhi < zlo || zhi > c->nzevolve) return fail(XB_ERR_ARG, "zone slice outside 1..nzevolve");
+  if (c->ctl.iheat > 0)
+    return fail(XB_ERR_UNSUPPORTED, "module-level drop-ins are built for iheat = 0; self-heating runs through xb_evolve");
   CUDA_TRY(cudaSetDevice(c->device));
   return module_state(c);
 }
@@ -909,8 +984,14 @@ int xb_zones_upload(xb_ctx *c, const xb_zones *z, int32_t hist_cap) {
   PUT(c->z_tstart, z->tstart, K); PUT(c->z_tstop, z->tstop, K); PUT(c->z_tdelstart, z->tdelstart, K);
   PUT(c->z_t9start, z->t9start, K); PUT(c->z_rhostart, z->rhostart, K); PUT(c->z_yestart, z->yestart, K);
   PUT(c->z_ystart, z->ystart, (size_t)K * ny); PUT(c->z_xext, z->xext, K); PUT(c->z_aext, z->aext, K); PUT(c->z_zext, z->zext, K);
+  {   // zext**thbim1 of y_moment (xnet_abundances.F90:160), evaluated on the host like the other charge powers
+    std::vector<double> zi(K);
+    for (int k = 0; k < K; ++k) zi[k] = std::pow(z->zext[k], 1.58);
+    PUT(c->z_zexti, zi.data(), K);
+  }
   DevZones &d = c->dz;
   d = DevZones{};
+  d.zexti = c->z_zexti.p;
   d.nfix = K; d.nzone = nz; d.nh = c->z_nh.p; d.off = c->z_off.p; d.nstart = c->z_nstart.p; d.zfix = c->z_zfix.p;
   d.th = c->z_th.p; d.t9h = c->z_t9h.p; d.rhoh = c->z_rhoh.p; d.tstart = c->z_tstart.p; d.tstop = c->z_tstop.p;
   d.tdelstart = c->z_tdelstart.p; d.t9start = c->z_t9start.p; d.rhostart = c->z_rhostart.p; d.yestart = c->z_yestart.p;

@@ -30,7 +30,7 @@ struct DevPlan {
 };
 
 // byte offsets of the zone working set inside the CTA's dynamic shared memory
-struct SmemOff { int scal, jac, y, yt, ydot, rhs, rdiag, part, prow, indx, cs, total; };
+struct SmemOff { int scal, jac, y, yt, ydot, rhs, rdiag, part, prow, indx, orig, pos, fhs, cs, total; };
 
 struct DevNet {
   int ny, nrtot, nffn, msize, ld, nffr, tile;
@@ -53,6 +53,14 @@ struct DevNet {
   const double *t9i;         // [24]
   const double *ffnsum, *ffnenu;  // [nffn][143]
   double mex_n, mex_p;
+  // equation of state and screening (iscrn > 0 or iheat > 0), see xb_eos.cuh
+  const double *helm;        // [13][201][541] Helmholtz table planes
+  const double *helm_t, *helm_d;  // [201], [541] grid temperatures and densities
+  const double *zzi;         // [ny] zz**1.58
+  const double *zseq53;      // [nzs] j**(5/3)
+  const double *sc_zw, *sc_zi;    // [nrtot] reaction charge parameters zeta_w, zeta_i (0 for one-reactant reactions)
+  const int2 *sc_iz;         // [nrtot] x = iz1 | iz2<<8 | iz3<<16 | iz4<<24, y = composite charge
+  int nzs;                   // entries of the per-charge strong-screening table
 };
 
 struct DevCtl {
@@ -65,6 +73,7 @@ struct DevZones {
   const int *nh, *off, *nstart, *zfix;
   const double *th, *t9h, *rhoh;
   const double *tstart, *tstop, *tdelstart, *t9start, *rhostart, *yestart, *ystart, *xext, *aext, *zext;
+  const double *zexti;       // [nfix] zext**1.58 (host)
   const double *rho_scale;
   const double *rs_t, *rs_tdel, *rs_t9, *rs_rho, *rs_t9o, *rs_y, *rs_yo;
   const int *rs_kstep0;
@@ -82,7 +91,7 @@ struct DevOut {
 struct DevScratch {
   double *base;            // [ncta][stride]
   size_t stride;           // doubles per CTA
-  size_t off_csect, off_rffn, off_qkffn, off_jac, off_prod, off_yo;  // offsets (doubles)
+  size_t off_csect, off_rffn, off_qkffn, off_jac, off_prod, off_yo, off_dcsect, off_dlnrffn;  // offsets (doubles)
   unsigned long long *phase;  // [PH_COUNT] cycle counters, see enum Phase
 };
 

@@ -34,11 +34,14 @@ struct Network {
   // FFN tables [nffn][143]
   std::vector<double> ffnsum, ffnenu, ffn_ec, ffn_beta, ffn_qval;
   std::vector<int32_t> has_logft;
+  // Helmholtz table planes [13][201][541]: f fd ft fdd ftt fdt fddt fdtt fddtt ef efd eft efdt (empty = not loaded)
+  std::vector<double> helm;
 };
 
 // throws std::runtime_error on malformed input
 void load_network(const std::string &data_dir, int iweak0, Network &net);
 int index_from_name(const Network &net, const std::string &name);
+void load_helm_table(const std::string &path, Network &net);
 
 struct Thermo {
   std::string desc;

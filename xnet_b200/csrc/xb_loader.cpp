@@ -438,3 +438,41 @@ void read_inab_file(const Network &net, const std::string &path, InAb &ab) {
 }
 
 }  // namespace xb
+
+// ---- Helmholtz free-energy table (actual_eos.F90:1609-1652 in the XNet tree) -----------------------------
+// ASCII form: 541*201 records of 9 numbers (f fd ft fdd ftt fdt fddt fdtt fddtt), then three blocks of
+// 541*201 records of 4 numbers (dpdf*, ef*, xf*); temperature index outermost, density index fastest.
+// Only f* and ef* are used by XNet's pruned EOS.  Packed form: those 13 planes as raw little-endian doubles.
+namespace xb {
+void load_helm_table(const std::string &path, Network &net) {
+  const size_t n = (size_t)541 * 201;
+  FILE *f = std::fopen(path.c_str(), "rb");
+  if (!f) throw std::runtime_error("cannot open Helmholtz table " + path);
+  std::fseek(f, 0, SEEK_END);
+  const long size = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  std::vector<double> planes(13 * n);
+  if ((size_t)size == 13 * n * sizeof(double)) {
+    const size_t got = std::fread(planes.data(), sizeof(double), 13 * n, f);
+    std::fclose(f);
+    if (got != 13 * n) throw std::runtime_error("short read on " + path);
+  } else {
+    std::vector<char> buf((size_t)size + 1);
+    const size_t got = std::fread(buf.data(), 1, (size_t)size, f);
+    std::fclose(f);
+    buf[got] = 0;
+    char *p = buf.data();
+    auto next = [&](double &v) {
+      char *e = nullptr;
+      v = std::strtod(p, &e);
+      if (e == p) throw std::runtime_error("malformed Helmholtz table " + path);
+      p = e;
+    };
+    double v;
+    for (size_t r = 0; r < n; ++r) for (int q = 0; q < 9; ++q) { next(v); planes[(size_t)q * n + r] = v; }
+    for (size_t r = 0; r < n; ++r) for (int q = 0; q < 4; ++q) next(v);                 // dpdf block: unused
+    for (size_t r = 0; r < n; ++r) for (int q = 0; q < 4; ++q) { next(v); planes[(size_t)(9 + q) * n + r] = v; }
+  }
+  net.helm.swap(planes);
+}
+}  // namespace xb

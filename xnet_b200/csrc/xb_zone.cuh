@@ -5,6 +5,7 @@
 #include "xb_device.cuh"
 #include "xb_math.cuh"
 #include "xb_lu.cuh"
+#include "xb_eos.cuh"
 
 namespace xb {
 
@@ -12,13 +13,17 @@ namespace xb {
 struct ZoneScalars {
   double t, tt, to, tdel, tdel_next, tdel_old, tdelstart, tstart, tstop;
   double t9, t9t, t9o, t9dot, rho, rhot, rhoo, ye, yet, yeo, cv, etae, detaedt9;
-  double xext, aext, zext, rho_scale;
+  double xext, aext, zext, zexti, rho_scale;
+  // composition moments and plasma parameters of the current rate evaluation (iscrn > 0 or iheat > 0)
+  double mom[2], ytot, abar, zbar, z2bar, zibar, ztilde, zinter, lambda0, gammae, dztildedt9;
+  double hw0, hi0, dlnhw0dt9, dlnhi0dt9;
   double rdt, mult, xtot_init, enm, enold, edot, sqnu;
   double t9rhs, dt9, relt9;
   double red[4];             // results of block-wide reductions
   double t09[4];             // T9^(-1/3), T9^(1/3), T9^(5/3), ln T9 of the current rate evaluation
   const double *th, *t9h, *rhoh;
   double *g_csect, *g_rffn, *g_qkffn, *g_prod, *g_jac, *g_yo;  // per-CTA global scratch (set in the kernel prologue)
+  double *g_dcsect, *g_dlnrffn;   // self-heating: d csect / d T9 [nrtot], d ln rffn / d T9 [nffn]
   int nh, has_scale, nt, ntt, nto, ints, iweak;
   int kmon[5], ktot[5];
   int inr, its, flag, piv, info, tile_ctr;
@@ -33,15 +38,18 @@ struct ZoneMem {
   int ld, tile;     // leading dimension (odd); tile = 1 when the Jacobian is the shared-memory tile
   double *y, *yo, *yt, *ydot, *rhs;  // [ny]; yt has ny+1 entries (yt[ny] = 1); rhs [N]
   double *part;     // partial sums of the term plans / scratch of block reductions
-  double *prow;     // [2][6][12] published pivot candidates of the LU panel; [2][32] block values of the solve
+  double *prow;     // [kPbufDoubles] panel buffer of the LU (xb_lu.cuh); [2][32] block values of the solve
   double *rdiag;    // [N] reciprocal diagonal of U (fast arithmetic only)
   double *prod;     // per-CTA global scratch for the strict term products
   double *gg;       // [ny+1] partition functions (aliases part)
   double *cs_sm;    // shared-memory cache of csect[cs_lo..nrtot)
+  double *fhs;      // [2][nzs] strong-screening energy per charge and its T9 derivative (iscrn > 0)
   double *csect;    // [nrtot] (global scratch)
   double *rffn;     // [nffn]
+  double *dcsect, *dlnrffn;   // self-heating only (global scratch)
   double *qkffn;    // [nffn+1]
   int *indx;        // [N] 0-based pivot rows
+  int *orig, *pos;  // [N] slot permutation of the Jacobian rows: slot s holds row orig[s]; row i sits in slot pos[i]
 };
 
 // The zone working set is addressed from the dynamic shared-memory symbol with offsets that the host
@@ -59,11 +67,15 @@ __device__ __forceinline__ ZoneMem zone_mem() {
   zm.rhs = reinterpret_cast<double *>(xb_smem + L.rhs);     // tile mode: column N of the tile
   zm.gg = reinterpret_cast<double *>(xb_smem + L.part);     // lives only inside cross_sect
   zm.cs_sm = reinterpret_cast<double *>(xb_smem + L.cs);
+  zm.fhs = reinterpret_cast<double *>(xb_smem + L.fhs);
   zm.rdiag = reinterpret_cast<double *>(xb_smem + L.rdiag);
   zm.part = reinterpret_cast<double *>(xb_smem + L.part);
   zm.prow = reinterpret_cast<double *>(xb_smem + L.prow);
   zm.indx = reinterpret_cast<int *>(xb_smem + L.indx);
+  zm.orig = reinterpret_cast<int *>(xb_smem + L.orig);
+  zm.pos = reinterpret_cast<int *>(xb_smem + L.pos);
   zm.csect = zm.s->g_csect; zm.rffn = zm.s->g_rffn; zm.qkffn = zm.s->g_qkffn; zm.prod = zm.s->g_prod;
+  zm.dcsect = zm.s->g_dcsect; zm.dlnrffn = zm.s->g_dlnrffn;
   return zm;
 }
 #define XB_ZONE_PROLOGUE                \
@@ -206,6 +218,14 @@ __device__ __noinline__ void cross_sect_cta() {
     block_sum2<STRICT>(ny, [&](int k, double &ta, double &tb) { ta = A::mul(yt[k], aa[k]); tb = A::mul(yt[k], zz[k]); },
                        zm.part, s->red);
   }
+  const bool eos_on = ctl.iscrn > 0 || ctl.iheat > 0;
+  if (eos_on) {
+    // remaining composition moments: sum Y, sum Y Z^2, sum Y Z^1.58 (xnet_abundances.F90:137-166)
+    const double *zz = net.zz, *zzi = net.zzi, *yt = zm.yt;
+    block_sum2<STRICT>(ny, [&](int k, double &ta, double &tb) { ta = yt[k]; tb = A::mul(yt[k], A::mul(zz[k], zz[k])); },
+                       zm.part, s->red + 2);
+    block_sum2<STRICT>(ny, [&](int k, double &ta, double &tb) { ta = A::mul(yt[k], zzi[k]); tb = 0.0; }, zm.part, s->mom);
+  }
   if (tid == 0) {
     const double yext = A::div(s->xext, s->aext);
     const double atot = A::add(s->red[0], s->xext);
@@ -214,6 +234,39 @@ __device__ __noinline__ void cross_sect_cta() {
     s->cv = 0.0; s->etae = 0.0; s->detaedt9 = 0.0;
     s->iweak = (t9t < 0.01 && ctl.iweak0 != 0) ? -abs(ctl.iweak0) : ctl.iweak0;
     s->ktot[4] += 1;
+    if (eos_on) {
+      // update_eos -> eos_interface -> eosx (xnet_eos_starkiller.F90:64-135) and eos_screen (:244-323)
+      const double ntot = A::add(s->red[2], yext);
+      const double z2tot = A::add(s->red[3], A::mul(A::mul(yext, s->zext), s->zext));
+      const double zitot = A::add(s->mom[0], A::mul(yext, s->zexti));
+      s->ytot = ntot; s->abar = A::div(atot, ntot); s->zbar = A::div(ztot, ntot);
+      s->z2bar = A::div(z2tot, ntot); s->zibar = A::div(zitot, ntot);
+      const double temp = A::mul(t9t, 1e9);
+      double e, de;
+      helm_eta<STRICT>(net, temp, rhot, s->yet, &e, &de);
+      s->etae = e; s->detaedt9 = A::mul(de, 1e9);
+      if (ctl.iheat > 0) {   // cv only enters t9dot; without self-heating the reference computes and ignores it
+        const double amu = 1.0 / (6.022140857e+23 * 1.6021766208e-06);
+        double c;
+        helm_cv<STRICT>(net, temp, rhot, s->abar, s->zbar, s->yet, &c);
+        s->cv = A::mul(A::mul(c, amu), 1e9);
+      }
+      if (ctl.iscrn > 0) {
+        using R = Num<STRICT>;
+        const double bi = 0.86, kbi = 0.38, thbim2 = 0.58;
+        double sratio, dz;
+        salpeter_ratio<STRICT>(s->etae, ctl.iheat > 0, &sratio, &dz);
+        const R zbar(s->zbar);
+        const R ztilde = EMath<STRICT>::sqrt(R(s->z2bar) + R(sratio) * zbar);
+        const R dzt = 0.5 * zbar / ztilde * dz * s->detaedt9;
+        s->ztilde = ztilde.v; s->dztildedt9 = dzt.v;
+        plasma<STRICT>(t9t, rhot, s->ytot, s->yet, s->zbar, s->zibar, ztilde.v, &s->zinter, &s->lambda0, &s->gammae);
+        s->hw0 = (ztilde * s->lambda0).v;
+        s->hi0 = (kbi * R(s->zinter) * EMath<STRICT>::pow(R(s->lambda0), bi)).v;
+        s->dlnhw0dt9 = (dzt / ztilde - 1.5 / R(t9t)).v;
+        s->dlnhi0dt9 = (-thbim2 * dzt / ztilde - 1.5 * bi / R(t9t)).v;
+      }
+    }
   }
   // temperature powers: four threads of different warps evaluate one transcendental each
   // t09(3,4,6,7) = T9^(-1/3), T9^(1/3), T9^(5/3), ln T9   (xnet_integrate.F90:650-656)
@@ -236,11 +289,34 @@ __device__ __noinline__ void cross_sect_cta() {
         zm.gg[k + 1] = Mx::safe_exp(v);
       }
     }
+    if (ctl.iheat > 0) {
+      // d ln g / d T9 (xnet_data.F90:247-266): slope of ln g on the bracketing interval (end intervals clamped)
+      const int idx = (ii == 1) ? 1 : (ii == kNG + 1) ? kNG - 1 : ii - 1;
+      const double dt = A::sub(net.t9i[idx], net.t9i[idx - 1]);
+      double *dl = zm.gg + (ny + 1);
+      if (tid == 0) dl[0] = 0.0;
+      for (int k = tid; k < ny; k += nt) dl[k + 1] = A::div(net.dlng[k * kNG + idx], dt);
+    }
   }
   __syncthreads();
   XB_DBG(zm, 4);
   const double ene = A::mul(s->yet, rhot);
   const int iweak = s->iweak;
+  if (ctl.iscrn > 0) {
+    // strong-screening energy per charge, DeWitt & Slattery (2003) fit (xnet_screening.F90:225-235)
+    using R = Num<STRICT>;
+    const double cds1 = -0.899172, cds2 = 0.602249, cds3 = -0.274823, cds4 = -1.401915, cds5 = 0.3230064;
+    double *fhs = zm.fhs, *dfhs = zm.fhs + net.nzs;
+    const double gammae = s->gammae;
+    for (int j = tid; j < net.nzs; j += nt) {
+      if (j == 0) { fhs[0] = 0.0; dfhs[0] = 0.0; continue; }
+      const R gammaz = R(gammae) * net.zseq53[j];
+      const R gammaz5 = EMath<STRICT>::pow(gammaz, cds5);
+      const R lgammaz = EMath<STRICT>::log(gammaz);
+      fhs[j] = (cds1 * gammaz + cds2 / cds5 * gammaz5 + cds3 * lgammaz + cds4).v;
+      dfhs[j] = (-(cds1 * gammaz + cds2 * gammaz5 + cds3) / R(t9t)).v;
+    }
+  }
 
   // FFN tabulated weak rates
   if (net.nffn > 0) {
@@ -265,6 +341,11 @@ __device__ __noinline__ void cross_sect_cta() {
       double r1 = A::mad(rdt9, dr1, sum[i1]), r2 = A::mad(rdt9, dr2, sum[i3]);
       double rf = A::mad(rdene, A::sub(r2, r1), r1);
       zm.rffn[k] = (rf < -30.0) ? 0.0 : Mx::pow10(rf);
+      if (ctl.iheat > 0) {   // d ln rffn / d T9 (xnet_ffn.F90:290-297)
+        const double ln_10 = 2.302585092994046;
+        zm.dlnrffn[k] = (rf < -30.0) ? 0.0
+            : A::div(A::mul(ln_10, A::add(A::mul(rdene, dr2), A::mul(A::sub(1.0, rdene), dr1))), dt9);
+      }
     }
     if (tid == 0) zm.qkffn[0] = 0.0;
   }
@@ -278,6 +359,20 @@ __device__ __noinline__ void cross_sect_cta() {
   t09[2] = s->t09[0]; t09[3] = s->t09[1]; t09[5] = s->t09[2]; t09[6] = s->t09[3];
   t09[4] = t9t;
   const double rho2 = A::mul(rhot, rhot), rho3 = A::mul(rho2, rhot);
+  // d t09 / d T9 (xnet_integrate.F90:658-665); the fractional powers follow from the published ones:
+  // T9^(-4/3) etc. are evaluated as the reference does, by pow
+  double dt09[7] = {0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0};
+  const bool heat = ctl.iheat > 0;
+  if (heat) {
+    using R = Num<STRICT>;
+    const R t(t9t);
+    dt09[1] = (-(1.0 / (t * t))).v;
+    dt09[2] = (-EMath<STRICT>::pow(t, -4.0 / 3.0) / 3.0).v;
+    dt09[3] = (EMath<STRICT>::pow(t, -2.0 / 3.0) / 3.0).v;
+    dt09[5] = (EMath<STRICT>::pow(t, 2.0 / 3.0) * 5.0 / 3.0).v;
+    dt09[6] = (1.0 / t).v;
+  }
+  const double *dlg = zm.gg + (ny + 1);
   const int nrtot = net.nrtot;
   const double *__restrict__ rcT = net.rcT;
   const int2 *__restrict__ ni2 = reinterpret_cast<const int2 *>(net.ni);
@@ -292,16 +387,45 @@ __device__ __noinline__ void cross_sect_cta() {
 #pragma unroll
     for (int j = 0; j < 7; ++j) rc[j] = __ldg(rcT + (size_t)j * nrtot + k);
     const int c = (k >= net.roff[3]) ? 3 : (k >= net.roff[2]) ? 2 : (k >= net.roff[1]) ? 1 : 0;
-    double cs;
+    double cs, dcs = 0.0;
     if ((iweak < 0 && iwk == 0) || (iweak == 0 && iwk != 0)) {
       cs = 0.0;
     } else {
-      double lam = 0.0;
+      double lam = 0.0, dlam = 0.0, dhscr = 0.0;
 #pragma unroll
       for (int j = 0; j < 7; ++j) lam = A::mad(rc[j], t09[j], lam);
-      // h = ascrn*h + lambda with ascrn = 0 (no screening in this build of the path)
-      const double h = A::add(A::mul(0.0, 0.0), lam);
-      double rpf = 1.0;
+      if (heat) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j) dlam = A::mad(rc[j], dt09[j], dlam);
+      }
+      // h = ascrn*h + lambda (xnet_integrate.F90:711-762); h = screening factor when iscrn > 0
+      double hscr = 0.0;
+      if (ctl.iscrn > 0 && c > 0) {
+        const double zw = __ldg(net.sc_zw + k);
+        if (zw > 0.0) {
+          const double zi = __ldg(net.sc_zi + k);
+          const int2 izp = __ldg(net.sc_iz + k);
+          const double *fhs = zm.fhs, *dfhs = zm.fhs + net.nzs;
+          const int i1 = izp.x & 255, i2 = (izp.x >> 8) & 255, i3 = (izp.x >> 16) & 255, i4 = (izp.x >> 24) & 255, ic = izp.y;
+          const double lambda = A::mul(s->hw0, zw);
+          const double hi = A::mul(s->hi0, zi);
+          double hs, dhs;
+          if (c == 1) {
+            hs = A::sub(A::add(fhs[i1], fhs[i2]), fhs[ic]);
+            dhs = A::sub(A::add(dfhs[i1], dfhs[i2]), dfhs[ic]);
+          } else if (c == 2) {   // the reference omits fhs(iz32) here (xnet_screening.F90:262); reproduced
+            hs = A::sub(A::add(fhs[i1], fhs[i3]), fhs[ic]);
+            dhs = A::sub(A::add(A::add(dfhs[i1], dfhs[i2]), dfhs[i3]), dfhs[ic]);
+          } else {
+            hs = A::sub(A::add(A::add(A::add(fhs[i1], fhs[i2]), fhs[i3]), fhs[i4]), fhs[ic]);
+            dhs = A::sub(A::add(A::add(A::add(dfhs[i1], dfhs[i2]), dfhs[i3]), dfhs[i4]), dfhs[ic]);
+          }
+          screen_blend<STRICT>(lambda, lambda, hi, hs, A::mul(lambda, s->dlnhw0dt9), A::mul(hi, s->dlnhi0dt9), dhs, &hscr, &dhscr);
+        }
+      }
+      const double ascrn = (ctl.iscrn > 0) ? 1.0 : 0.0;
+      const double h = A::add(A::mul(ascrn, hscr), lam);
+      double rpf = 1.0, dlnrpf = 0.0;
       if (irev == 1) {
         const int ni[6] = {n01.x, n01.y, n23.x, n23.y, n45.x, n45.y};
         const int nreact = c + 1, nslot = (c == 0) ? 5 : 6;
@@ -310,6 +434,13 @@ __device__ __noinline__ void cross_sect_cta() {
         else { p = 1.0; for (int j = 0; j < nreact; ++j) p = A::mul(p, gg[ni[j]]); }
         for (int j = nreact; j < nslot; ++j) rpf = A::mul(rpf, gg[ni[j]]);
         rpf = A::div(rpf, p);
+        if (heat) {   // d ln rpf / d T9 = sum over products - sum over reactants of d ln g / d T9
+          double sr;
+          if (c == 0) sr = dlg[ni[0]];
+          else { sr = 0.0; for (int j = 0; j < nreact; ++j) sr = A::add(sr, dlg[ni[j]]); }
+          for (int j = nreact; j < nslot; ++j) dlnrpf = A::add(dlnrpf, dlg[ni[j]]);
+          dlnrpf = A::sub(dlnrpf, sr);
+        }
       }
       if (c == 0) {
         if (iwk == 1) cs = A::mul(A::mul(ene, rpf), Mx::safe_exp(h));
@@ -322,7 +453,14 @@ __device__ __noinline__ void cross_sect_cta() {
         else cs = A::mul(A::mul(rf, rpf), Mx::safe_exp(h));
         if (c == 2 && cs < 1.0e-20) cs = 0.0;
       }
+      if (heat) {   // xnet_integrate.F90:807-815 and the corresponding blocks of the other classes
+        const double dh = A::add(A::mul(ascrn, dhscr), dlam);
+        if (c == 0 && (iwk == 2 || iwk == 3)) dcs = A::mul(cs, zm.dlnrffn[net.iffn[k] - 1]);
+        else if (c == 0 && (iwk == 7 || iwk == 8)) dcs = A::mul(cs, dlnrpf);
+        else dcs = A::mul(cs, A::add(dh, dlnrpf));
+      }
     }
+    if (heat) zm.dcsect[k] = dcs;
     zm.csect[k] = cs;
     if (k >= net.cs_lo) zm.cs_sm[k - net.cs_lo] = cs;
   }
@@ -441,6 +579,16 @@ __device__ __noinline__ void yderiv_cta() {
   }
   if (tid == 0) zm.s->ktot[3] += 1;
   __syncthreads();
+  if (ctl.iheat > 0) {
+    // t9dot = - sum_i mex_i ydot_i / cv (xnet_integrate.F90:471-487); (0 - t1) - t2 ... == -(t1 + t2 + ...) bit for bit
+    using A = Ar<STRICT>;
+    const double *mex = net.mex;
+    const double cv = zm.s->cv;
+    block_sum2<STRICT>(ny, [&](int k, double &ta, double &tb) { ta = A::div(A::mul(mex[k], ydot[k]), cv); tb = 0.0; },
+                       part, zm.s->red);
+    if (tid == 0) zm.s->t9dot = -zm.s->red[0];
+    __syncthreads();
+  }
 }
 
 // --- jacobian_build + jacobian_scale (xnet_jacobian_dense.F90:183-200, 303-341) ----------------------
@@ -451,8 +599,17 @@ __device__ __forceinline__ void jacobian_build_impl(const DevNet &net, const Zon
   if (TILE) XB_ASSUME_SHARED(J);
   const DevPlan &P = net.pj;
   const int tid = threadIdx.x, nt = blockDim.x, N = net.msize, ld = zm.ld;
-  const double diag = zm.s->rdt, mult = zm.s->mult;
+  // self-heating: the unscaled dydotdy is assembled first (the T9 row is a linear functional of it), scaled last
+  const bool heat = c_ctl.iheat > 0;
+  const double diag = heat ? 0.0 : zm.s->rdt, mult = heat ? 1.0 : zm.s->mult;
   double *part = zm.part;
+  int *pos = zm.pos;
+  XB_ASSUME_SHARED(pos);
+  // plan destinations are (column << 10 | row); row i of the matrix lives in slot pos[i]
+  auto slot = [&](const unsigned d) { return (int)(d >> 10) * ld + pos[d & 1023u]; };
+  if (STRICT) {   // strict arithmetic reproduces DGETRF's interchanges: no pivot prediction
+    for (int k = tid; k < N; k += nt) { pos[k] = k; zm.orig[k] = k; }
+  }
   XB_DBG_MARK(zm);
   {
     const int n2 = (N * ld) >> 1;
@@ -470,13 +627,13 @@ __device__ __forceinline__ void jacobian_build_impl(const DevNet &net, const Zon
       const int d = P.seg_dest[e];
       double v = __dmul_rn(mult, sc);
       if (d & 1) v = __dadd_rn(v, diag);
-      J[d >> 1] = v;
+      J[slot((unsigned)d >> 1)] = v;
     }
   } else {
     __syncthreads();  // zero fill complete before the scattered stores
     XB_DBG(zm, 0);
     plan_run_fast(P, zm.csect, zm.cs_sm, net.cs_lo, zm.yt, [&](unsigned ctl, double acc) {
-      if ((ctl & 3u) == 1u) J[ctl >> 3] = fma(mult, acc, (ctl & 4u) ? diag : 0.0);
+      if ((ctl & 3u) == 1u) J[slot(ctl >> 3)] = fma(mult, acc, (ctl & 4u) ? diag : 0.0);
       else part[ctl >> 3] = acc;
     });
     XB_DBG(zm, 1);
@@ -486,12 +643,69 @@ __device__ __forceinline__ void jacobian_build_impl(const DevNet &net, const Zon
       double sm = 0.0;
       for (int q = P.multi_start[m]; q < P.multi_start[m + 1]; ++q) sm += part[q];
       const int d = P.multi_dest[m];
-      J[d >> 1] = fma(mult, sm, (d & 1) ? diag : 0.0);
+      J[slot((unsigned)d >> 1)] = fma(mult, sm, (d & 1) ? diag : 0.0);
     }
   }
   if (tid == 0) zm.s->ktot[2] += 1;
   __syncthreads();
   XB_DBG(zm, 3);
+  if (heat) {
+    using A = Ar<STRICT>;
+    const int ny = net.ny;
+    const DevPlan &Py = net.py;
+    double *colT = J + (size_t)ny * ld;   // column ny: d ydot_i / d T9 = the ydot sums with dcsect/dT9 (xnet_jacobian_dense.F90:343-399)
+    if (STRICT) {
+      plan_products_strict(Py, zm.dcsect, zm.yt, zm.prod);
+      __syncthreads();
+      const double *prod = zm.prod;
+      for (int i = tid; i < ny; i += nt) {
+        double s4[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          double sc = 0.0;
+          for (int q = Py.seg_start[4 * i + c]; q < Py.seg_start[4 * i + c + 1]; ++q) sc = __dadd_rn(sc, __ldcg(prod + q));
+          s4[c] = sc;
+        }
+        colT[pos[i]] = __dadd_rn(__dadd_rn(__dadd_rn(s4[0], s4[1]), s4[2]), s4[3]);
+      }
+    } else {
+      plan_run_fast(Py, zm.dcsect, zm.cs_sm, net.nrtot, zm.yt, [&](unsigned ctl, double acc) {
+        if ((ctl & 3u) == 1u) colT[pos[ctl >> 3]] = acc; else part[ctl >> 3] = acc;
+      });
+      __syncthreads();
+      for (int m = tid; m < Py.nmulti; m += nt) {
+        double sm = 0.0;
+        for (int q = Py.multi_start[m]; q < Py.multi_start[m + 1]; ++q) sm += part[q];
+        colT[pos[Py.multi_dest[m] >> 1]] = sm;
+      }
+    }
+    __syncthreads();
+    // row ny: d t9dot / d(y_j, T9) = - sum_i mex_i dydotdy(j,i) / cv, summed over i in order
+    {
+      const double *mex = net.mex;
+      const double cv = zm.s->cv;
+      const int rT = pos[ny];
+      for (int j = tid; j < N; j += nt) {
+        const double *col = J + (size_t)j * ld;
+        double sdot = 0.0;
+        for (int i = 0; i < ny; ++i) sdot = A::sub(sdot, A::div(A::mul(mex[i], col[pos[i]]), cv));
+        J[(size_t)j * ld + rT] = sdot;
+      }
+    }
+    __syncthreads();
+    // jacobian_scale: jac = mult * dydotdy^T + diag on the diagonal
+    {
+      const double rdt = zm.s->rdt, m = zm.s->mult;
+      for (int e = tid; e < N * N; e += nt) {
+        const int j = e / N, i = e - j * N;
+        const int idx = j * ld + pos[i];
+        double v = A::mul(m, J[idx]);
+        if (i == j) v = A::add(v, rdt);
+        J[idx] = v;
+      }
+    }
+    __syncthreads();
+  }
 }
 template <bool STRICT>
 __device__ __noinline__ void jacobian_build_cta() {
@@ -505,14 +719,18 @@ template <bool STRICT>
 __device__ __forceinline__ void lu_cta(const ZoneMem &zm, const int N, const bool with_rhs) {
   if (zm.tile) {
     // zm.rhs IS column N of the tile
-    lu_tile<STRICT>(zm.jac, zm.ld, N, with_rhs ? 1 : 0, zm.indx, &zm.s->info, zm.prow, zm.rdiag, &zm.s->tile_ctr,
-                    zm.s->ph + PH_LU_PANEL);
-  } else { lu_simple<STRICT>(zm.jac, zm.ld, N, zm.indx, &zm.s->info, &zm.s->piv); }
+    lu_blocked<STRICT, true, 1>(zm.jac, zm.ld, N, with_rhs ? 1 : 0, zm.indx, &zm.s->info, zm.prow, zm.rdiag,
+                                zm.s->ph + PH_LU_PANEL, zm.orig, zm.pos);
+  } else {
+    lu_blocked<STRICT, false, 2>(zm.jac, zm.ld, N, 0, zm.indx, &zm.s->info, zm.prow, nullptr, zm.s->ph + PH_LU_PANEL,
+                                 zm.orig, zm.pos);
+  }
 }
 template <bool STRICT>
+// the right-hand side is already in slot order (rhs[pos[i]] = b_i), so no interchanges are applied here
 __device__ __forceinline__ void bksub_cta(const ZoneMem &zm, const int N, const bool fwd_done) {
-  if (zm.tile) bksub_block<STRICT, true>(zm.jac, zm.ld, N, zm.indx, zm.rhs, zm.rdiag, zm.prow, fwd_done);
-  else bksub_simple<STRICT>(zm.jac, zm.ld, N, zm.indx, zm.rhs);
+  if (zm.tile) bksub_block<STRICT, true>(zm.jac, zm.ld, N, zm.indx, zm.rhs, zm.rdiag, zm.prow, fwd_done, false);
+  else bksub_simple<STRICT>(zm.jac, zm.ld, N, zm.indx, zm.rhs, false);
 }
 
 // --- step_be: Newton-Raphson loop (xnet_integrate_be.F90:233-482) -------------------------------
@@ -543,15 +761,21 @@ __device__ __noinline__ void step_be_cta() {
     XB_PHASE_END(zm, PH_YDERIV);
     // right-hand side (xnet_integrate_be.F90:327-349); it does not depend on the Jacobian
     const double rdt = s->rdt;
-    if (kit > 1) {
-      for (int k = tid; k < ny; k += nt) zm.rhs[k] = A::mad(A::sub(zm.y[k], zm.yt[k]), rdt, zm.ydot[k]);
-    } else {
-      for (int k = tid; k < ny; k += nt) zm.rhs[k] = zm.ydot[k];
-    }
-    __syncthreads();
+    // in slot order: row k of the system sits in slot pos[k] of the Jacobian.  The slots are fixed by the
+    // previous factorisation (or reset by the strict build), so the Jacobian is assembled first.
     if (rebuild) {
       jacobian_build_cta<STRICT>();
       XB_PHASE_END(zm, PH_JAC);
+    }
+    if (kit > 1) {
+      for (int k = tid; k < ny; k += nt) zm.rhs[zm.pos[k]] = A::mad(A::sub(zm.y[k], zm.yt[k]), rdt, zm.ydot[k]);
+      if (ctl.iheat > 0 && tid == 0) zm.rhs[zm.pos[ny]] = A::mad(A::sub(s->t9, s->t9t), rdt, s->t9dot);
+    } else {
+      for (int k = tid; k < ny; k += nt) zm.rhs[zm.pos[k]] = zm.ydot[k];
+      if (ctl.iheat > 0 && tid == 0) zm.rhs[zm.pos[ny]] = s->t9dot;
+    }
+    __syncthreads();
+    if (rebuild) {
       lu_cta<STRICT>(zm, N, true);
       XB_PHASE_END(zm, PH_LU);
     }
@@ -579,6 +803,11 @@ __device__ __noinline__ void step_be_cta() {
       const double testn = (ctl.iconvc != 0) ? s->red[0] : testm;
       const double toln = (ctl.iconvc != 0) ? ctl.tolc : ctl.tolm;
       s->relt9 = 0.0;
+      if (ctl.iheat > 0) {   // temperature update and its convergence measure (xnet_integrate_be.F90:402-416)
+        s->dt9 = zm.rhs[ny];
+        s->t9t = A::add(s->t9t, s->dt9);
+        s->relt9 = (fabs(s->t9t) > 2.2250738585072014e-308) ? fabs(A::div(s->dt9, s->t9t)) : 0.0;
+      }
       s->flag = (fabs(testn) <= toln && s->relt9 < ctl.tolt9) ? 1 : 0;
       if (s->flag) s->inr = kit;
     }
@@ -627,19 +856,23 @@ __device__ __noinline__ void timestep_cta() {
   }
   if (threadIdx.x == 0) {
     const double changeth = 0.1;
-    double changey, tdel_init, tdel_dy, tdel_dt9;
+    double changey, changet9, tdel_init, tdel_dy, tdel_dt9;
     const double tdel_stop = A::sub(s->tstop, s->t);
     if (mask_init) {
       const double changest = (s->tdelstart < 0.0) ? 0.5 : 0.01;
       changey = A::mul(changest, fmin(0.1, ctl.changemx));
+      changet9 = A::mul(changest, fmin(0.01, ctl.changemxt));
       tdel_init = fmin(A::mul(changest, fabs(s->tdelstart)), tdel_stop);
       s->tdel_next = (s->nh > 2) ? A::mul(1.0e-4, tdel_stop) : tdel_stop;
-    } else { changey = ctl.changemx; tdel_init = 0.0; }
+    } else { changey = ctl.changemx; changet9 = ctl.changemxt; tdel_init = 0.0; }
     if (fwd) {
       const double vmax = s->red[0];
       s->ints += 1;
       tdel_dy = (fabs(vmax) > 0.0) ? A::div(changey, vmax) : s->tdel_next;
-      tdel_dt9 = s->tdel_next;  // rtau_t9 = 0 without self-heating
+      double rtau_t9 = 0.0;   // temperature time scale (xnet_integrate.F90:141-160); zero without self-heating
+      if (ctl.iheat > 0)
+        rtau_t9 = mask_init ? fabs(A::div(s->t9dot, s->t9)) : A::div(fabs(A::div(A::sub(s->t9, s->t9o), s->t9)), s->tdel_old);
+      tdel_dt9 = (rtau_t9 > 0.0) ? A::div(changet9, rtau_t9) : s->tdel_next;
       s->tdel = fmax(tdel_init, fmin(fmin(tdel_stop, s->tdel_next), fmin(tdel_dy, tdel_dt9)));
     } else s->tdel = -s->tdel_old;
     s->tt = fmin(A::add(s->t, s->tdel), s->tstop);
@@ -699,6 +932,7 @@ __device__ __noinline__ void solve_be_cta() {
         s->yet = s->ye;
         s->kmon[1] = ctl.kitmx + 1; s->ktot[1] += ctl.kitmx + 1;
         t9rhofind<STRICT>(s, s->tt, &s->ntt, &s->t9t, &s->rhot);
+        if (ctl.iheat > 0) s->t9t = s->t9;
         if (kts == ktsmx - 1) { s->tdel = 0.0; s->tdelstart = 0.0; }
       }
       __syncthreads();
@@ -790,7 +1024,7 @@ __device__ __forceinline__ void full_net_cta(const DevZones &zn, const DevOut &o
     s->nh = zn.nh[fx]; s->th = zn.th + zn.off[fx]; s->t9h = zn.t9h + zn.off[fx]; s->rhoh = zn.rhoh + zn.off[fx];
     s->has_scale = zn.rho_scale != nullptr; s->rho_scale = s->has_scale ? zn.rho_scale[iz] : 1.0;
     s->tstart = zn.tstart[fx]; s->tstop = zn.tstop[fx]; s->tdelstart = zn.tdelstart[fx];
-    s->xext = zn.xext[fx]; s->aext = zn.aext[fx]; s->zext = zn.zext[fx];
+    s->xext = zn.xext[fx]; s->aext = zn.aext[fx]; s->zext = zn.zext[fx]; s->zexti = zn.zexti[fx];
     s->ye = zn.yestart[fx];
     s->cv = s->etae = s->detaedt9 = s->t9dot = 0.0;
     for (int k = 0; k < 5; ++k) { s->kmon[k] = 0; s->ktot[k] = 0; }
@@ -819,6 +1053,7 @@ __device__ __forceinline__ void full_net_cta(const DevZones &zn, const DevOut &o
     }
   }
   for (int k = tid; k <= net.nffn; k += nt) zm.qkffn[k] = 0.0;
+  for (int k = tid; k < net.msize; k += nt) { zm.orig[k] = k; zm.pos[k] = k; }   // no pivot history yet
   __syncthreads();
   if (tid == 0) {
     if (restart) { double t9x, rhox; t9rhofind<STRICT>(s, s->t, &s->nt, &t9x, &rhox); }
