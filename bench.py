@@ -144,10 +144,11 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=2)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours')
-    ap.add_argument('--workload', default='sn160', choices=list(WORKLOADS))
+    ap.add_argument('--workload', default='sn160_scrn', choices=list(WORKLOADS),
+                    help="default: BASELINE.json configs[2] (SN160 with screening, 16384 zones; BE, the integrator the reference builds)")
     ap.add_argument('--zones', type=int, default=16384, help='zones per GPU')
     ap.add_argument('--arith', default='fast', choices=['fast', 'strict'])
     ap.add_argument('--kstmx', type=int, default=None, help='cap on accepted steps per zone (default: complete trajectory)')
@@ -240,11 +241,12 @@ def main():
                 'd2h_bytes_per_step': d2h},
         'gpu_launches': int(launches),
         'clocks': sampler.summary(),
-        'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak / 1e12, 'unit': 'TFLOP/s',
+        'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': fp64_peak / 1e12, 'unit': 'TFLOP/s',
                      'frac': achieved / (fp64_peak / 1e12), 'traffic': None,
                      'kernel': 'evolve_kernel (fused rates+ydot+Jacobian+LU+bksub+Newton/timestep control)',
                      'algorithmic': '2/3*N^3 flops x ktot(3) LU factorizations per launch (N=%d, %d factorizations)' % (N, int(nlu)),
-                     'peak_source': 'FP64 FMA microbenchmark measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry)',
+                     'peak_source': 'FP64 peak measured live on this GPU (DFMA microbenchmark; tools/dmma_probe.cu: the FP64 tensor pipe '
+                                    'DMMA.8x8x4 peaks at the same 64 FMA/clk/SM); MEASURED_PEAKS.json has only bf16/HBM entries',
                      'phase_share': {k: round(ph[k] / phase_tot, 4) for k in ('rates', 'yderiv', 'jac', 'lu', 'bksub', 'other', 'lu_panel', 'lu_swap_trsm', 'lu_gemm')},
                      'cycles_per_newton_iter': phase_tot / max(newton, 1.0),
                      'pivot_steps_per_lu': ph['spare'] / max(nlu, 1.0),

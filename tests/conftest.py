@@ -39,6 +39,8 @@ PROBLEMS = {
     'alpha_heat': ('test_settings_heat', 'setup_heat_alpha'),
     'torch47_heat': ('test_settings_heat', 'setup_heat_torch47'),
     'sn160_heat': ('test_settings_heat', 'setup_heat_sn160'),
+    # logft weak rates + self-heating + screening on SN231 (test/test_xnet.sh test 53; BASELINE configs[3])
+    'sn231_logft': ('test_settings_logft', 'setup_logft_sn231'),
 }
 
 

@@ -24,7 +24,12 @@ CASES = {'alpha': ('test_settings_small', 'setup_tnsn_alpha', 3000, None),
          'xrb304': ('test_settings', 'setup_xrb_fisker', 40, 39),
          # screening switched on (Helmholtz eta, Fermi-Dirac integrals, Graboske/DeWitt blend)
          'torch47_scrn': ('test_settings', 'setup_tnsn_torch47', 400, 399),
-         'sn160_scrn': ('test_settings', 'setup_tnsn_sn160', 120, 119)}
+         'sn160_scrn': ('test_settings', 'setup_tnsn_sn160', 120, 119),
+         # self-heating + screening (test_settings_heat)
+         'torch47_heat': ('test_settings_heat', 'setup_heat_torch47', 300, 299),
+         'sn160_heat': ('test_settings_heat', 'setup_heat_sn160', 120, 119),
+         # logft weak rates + self-heating + screening, SN231 (N = 232: global-memory Jacobian)
+         'sn231_logft': ('test_settings_logft', 'setup_logft_sn231', 60, 59)}
 
 for net in ('alpha', 'torch47', 'SN160', 'SN231', 'XRB304'):
     shutil.copy(os.path.join(DATA, 'Data_' + net, 'net_desc'), os.path.join(OUT, 'net_desc_%s.txt' % net))

@@ -98,7 +98,7 @@ def test_pmath_accuracy(built):
 def test_oracle_matches_committed_golden(oracle_problem):
     """The oracle reproduces the committed golden trajectories bit for bit (guards the fixtures and
     the generating script)."""
-    for name, cap in (('alpha', 3000), ('torch47', 400)):
+    for name, cap in (('alpha', 3000), ('torch47', 400), ('torch47_scrn', 400), ('torch47_heat', 300), ('sn160_heat', 120)):
         for math, fast in (('libm', False), ('pm', 'pm')):
             g = np.load(os.path.join(GOLD, 'ts_%s_%s.npz' % (name, math)))
             r = oracle_problem(name).run(nzone=1, hist_cap=cap, fast=fast,
@@ -149,6 +149,20 @@ def _olib():
         getattr(l, f).restype = C.c_double
         getattr(l, f).argtypes = [C.c_double]
     return l
+
+
+@pytest.mark.parametrize('k,name', [(0, 'ox_fd0h'), (1, 'ox_fd2h'), (2, 'ox_fd4h'), (3, 'ox_fd6h'), (4, 'ox_fd8h')])
+def test_integer_order_fermi_dirac_against_quadrature(k, name):
+    """Integer orders k = 0..4 used by the logft phase space (both intervals and the reflection branch): 1e-13."""
+    import ctypes as C
+    from scipy import integrate
+    from oracle import xnet_oracle as O
+    fn = getattr(O.lib('strict'), name)
+    fn.restype = C.c_double; fn.argtypes = [C.c_double]
+    for x in [-40, -10, -2.5, -2, -1, -0.1, 0, 0.3, 1, 2, 2.5, 5, 10, 30, 100]:
+        h = lambda t: t ** k / (np.exp(min(t - x, 700.0)) + 1.0)
+        q = integrate.quad(h, 0, max(x, 0) + 80, limit=500, epsabs=0, epsrel=1e-13, points=[x] if x > 0 else None)[0]
+        assert abs(fn(x) / q - 1) < 1e-13
 
 
 @pytest.mark.parametrize('x', [-30, -5, -2.0001, -2, -1, -1e-3, 0, 0.5, 1.999, 2, 3.3, 5, 7, 10, 13, 20, 31, 40, 55, 200])

@@ -23,7 +23,7 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
 
 
 def function_body(src, name):
-    m = re.search(r'Function %s\(x\)(.*?)End Function %s' % (name, name), src, re.S)
+    m = re.search(r'[Ff]unction %s\([xy]\)(.*?)End Function %s' % (name, name), src, re.S)
     return m.group(1)
 
 
@@ -102,6 +102,8 @@ def find_rational(node):
 def tables(name, src):
     rows = []
     for cond, defs, expr in branches(function_body(src, name)):
+        if cond and 'y>' in cond:
+            continue   # reflection formula of the integer orders: hand written in the evaluators
         tree = ast.parse(expr, mode='eval').body
         rat = find_rational(tree)
         lead = re.match(r'\s*-\(', expr) is not None
@@ -130,26 +132,28 @@ def emit(rows_by_fn, qualifier, guard):
            '// integrals of order -3/2, -1/2, 1/2 (XNet: source/xnet_fd.F90).  Interval k of function f:',
            '//   numerator   P[k][0..np-1], denominator Q[k][0..nq-1], ascending powers (Horner from the top);',
            '//   c0/sign     additive constant and sign of the rational part where the closed form has them.',
-           '// Intervals: 0: x<-2, 1: x<0, 2: x<2, 3: x<5, 4: x<10, 5: x<20, 6: x<40, 7: x>=40.',
+           '// Intervals: 0: x<-2, 1: x<0, 2: x<2, 3: x<5, 4: x<10, 5: x<20, 6: x<40, 7: x>=40.  The integer orders',
+           '// (fd0h, fd2h, ... = k = 0, 1, 2, 3, 4) have the first two intervals only, on x = -|y|, plus a reflection formula.',
            '#pragma once', '#define %s 1' % guard, '#define FD_MAXC 10']
     for fn, rows in rows_by_fn.items():
-        assert len(rows) == 8, (fn, len(rows))
+        n_iv = len(rows)
+        assert n_iv in (2, 8), (fn, n_iv)
         for key in ('p', 'q'):
-            out.append('%s double %s_%s[8][FD_MAXC] = {' % (qualifier, fn, key))
+            out.append('%s double %s_%s[%d][FD_MAXC] = {' % (qualifier, fn, key, n_iv))
             for r in rows:
                 cs = r[key] + [0.0] * (10 - len(r[key]))
                 assert len(cs) == 10, (fn, len(r[key]))
                 out.append('  {' + ', '.join(repr(c) for c in cs) + '},')
             out.append('};')
-            out.append('%s int %s_n%s[8] = {%s};' % (qualifier, fn, key, ', '.join(str(len(r[key])) for r in rows)))
+            out.append('%s int %s_n%s[%d] = {%s};' % (qualifier, fn, key, n_iv, ', '.join(str(len(r[key])) for r in rows)))
         out.append('%s double %s_c0 = %r;' % (qualifier, fn, rows[0]['c0']))
-        out.append('%s double %s_sign[8] = {%s};' % (qualifier, fn, ', '.join(repr(r['sign']) for r in rows)))
+        out.append('%s double %s_sign[%d] = {%s};' % (qualifier, fn, n_iv, ', '.join(repr(r['sign']) for r in rows)))
     return '\n'.join(out) + '\n'
 
 
 def main():
     src = open(REF).read()
-    rows = {fn: tables(fn, src) for fn in ('fdm3h', 'fdm1h', 'fd1h')}
+    rows = {fn: tables(fn, src) for fn in ('fdm3h', 'fdm1h', 'fd1h', 'fd0h', 'fd2h', 'fd4h', 'fd6h', 'fd8h')}
     for fn, rs in rows.items():
         for k, r in enumerate(rs):
             print(fn, k, r['cond'], r['defs'], 'np', len(r['p']), 'nq', len(r['q']), 'c0', r['c0'], 'sign', r['sign'])

@@ -60,7 +60,8 @@ struct xb_ctx {
   // network tables
   DevBuf<double> rcT, a[4], aa, zz, mex, be, g, lng, dlng, t9i, ffnsum, ffnenu;
   DevBuf<int> ni, iwk, irev, iffn, la, le, mu[4], nn[4][4], ffr_n1, ffr_iffn;
-  DevBuf<double> helm, helm_t, helm_d, zzi, zseq53, sc_zw, sc_zi, z_zexti;
+  DevBuf<double> helm, helm_t, helm_d, zzi, zseq53, sc_zw, sc_zi, z_zexti, ffn_ec, ffn_beta, ffn_qval;
+  DevBuf<int> has_logft;
   DevBuf<int2> sc_iz;
   // term plans (ydot, Jacobian)
   struct PlanBufs { DevBuf<double> a; DevBuf<uint2> nn, mc; DevBuf<int> seg_start, seg_dest, multi_start, multi_dest; } pby, pbj;
@@ -128,6 +129,7 @@ static __device__ void zone_prologue(const DevScratch &scr, double *csect, doubl
     s->g_qkffn = qkffn ? qkffn : g + scr.off_qkffn;
     s->g_prod = g + scr.off_prod;
     s->g_jac = jacg ? jacg : g + scr.off_jac;
+    s->rhs_in_jac = jacg ? 0 : 1;   // module kernels work on the caller's msize x msize array: no room for column N
     s->g_yo = g + scr.off_yo;
     s->g_dcsect = g + scr.off_dcsect;
     s->g_dlnrffn = g + scr.off_dlnrffn;
@@ -213,7 +215,7 @@ module_kernel(const __grid_constant__ ModArgs ma, const __grid_constant__ DevScr
       for (int e = tid; e < N * N; e += nt) { const int j = e / N, i = e - j * N; zm.jac[j * ld + i] = gj[e]; }
       __syncthreads();
     }
-    lu_cta<STRICT>(zm, N, false);
+    lu_cta<STRICT>(zm, N, false, false);
     if (net.tile)
       for (int e = tid; e < N * N; e += nt) { const int j = e / N, i = e - j * N; gj[e] = zm.jac[j * ld + i]; }
     for (int k = tid; k < N; k += nt) ma.indx[(size_t)iz * N + k] = zm.indx[k] + 1;  // LAPACK 1-based ipiv
@@ -222,8 +224,8 @@ module_kernel(const __grid_constant__ ModArgs ma, const __grid_constant__ DevScr
     // factors are read straight from HBM/L2 (each element is used once); rdiag is not kept between calls
     for (int k = tid; k < N; k += nt) { zm.indx[k] = ma.indx[(size_t)iz * N + k] - 1; zm.rhs[k] = ma.rhs[(size_t)iz * N + k]; }
     __syncthreads();
-    if (net.tile) bksub_block<STRICT, false>(gj, N, N, zm.indx, zm.rhs, nullptr, zm.prow, false, true);
-    else bksub_simple<STRICT>(gj, N, N, zm.indx, zm.rhs, true);
+    if (net.tile) bksub_block<STRICT, false, 1>(gj, N, N, zm.indx, zm.rhs, nullptr, zm.prow, false, true);
+    else bksub_block<STRICT, false, 2>(gj, N, N, zm.indx, zm.rhs, nullptr, zm.prow, false, true);
     for (int k = tid; k < N; k += nt) ma.rhs[(size_t)iz * N + k] = zm.rhs[k];
   }
 }
@@ -497,6 +499,9 @@ static int upload_network(xb_ctx *c) {
     for (int i = 1; i < kNG; ++i) dlng[(size_t)k * kNG + i] = std::log(h.g[(size_t)k * kNG + i] / h.g[(size_t)k * kNG + i - 1]);
   CUDA_TRY(c->lng.put(lng)); CUDA_TRY(c->dlng.put(dlng));
   CUDA_TRY(c->ffnsum.put(h.ffnsum)); CUDA_TRY(c->ffnenu.put(h.ffnenu));
+  CUDA_TRY(c->ffn_ec.put(h.ffn_ec)); CUDA_TRY(c->ffn_beta.put(h.ffn_beta)); CUDA_TRY(c->ffn_qval.put(h.ffn_qval));
+  CUDA_TRY(c->has_logft.put(h.has_logft));
+  d.ffn_ec = c->ffn_ec.p; d.ffn_beta = c->ffn_beta.p; d.ffn_qval = c->ffn_qval.p; d.has_logft = c->has_logft.p;
   d.aa = c->aa.p; d.zz = c->zz.p; d.mex = c->mex.p; d.be = c->be.p; d.g = c->g.p; d.lng = c->lng.p; d.dlng = c->dlng.p;
   d.t9i = c->t9i.p; d.ffnsum = c->ffnsum.p; d.ffnenu = c->ffnenu.p;
   // composition moment table (always: cheap) and, for screening / self-heating, the EOS and screening tables
@@ -737,7 +742,7 @@ static int configure_launch(xb_ctx *c) {
   o = (o + 15) / 16 * 16;
   s.off_yo = o; o += (size_t)c->dn.ny;
   o = (o + 15) / 16 * 16;
-  s.off_jac = o; if (!c->jac_in_smem) o += (size_t)N * c->ld;
+  s.off_jac = o; if (!c->jac_in_smem) o += (size_t)(N + 1) * c->ld;   // + the right-hand side as column N
   s.stride = (o + 15) / 16 * 16;
   const size_t nblocks = std::max<size_t>(c->grid, c->nzevolve);
   CUDA_TRY(c->scratch.resize(nblocks * s.stride));
@@ -778,6 +783,7 @@ void xb_ctx_destroy(xb_ctx *c) {
   // DevBuf members are plain pointers: release explicitly
   c->rcT.release(); c->aa.release(); c->zz.release(); c->mex.release(); c->be.release(); c->g.release(); c->lng.release();
   c->dlng.release(); c->t9i.release(); c->helm.release(); c->helm_t.release(); c->helm_d.release(); c->zzi.release();
+  c->ffn_ec.release(); c->ffn_beta.release(); c->ffn_qval.release(); c->has_logft.release();
   c->zseq53.release(); c->sc_zw.release(); c->sc_zi.release(); c->z_zexti.release(); c->sc_iz.release(); c->ffnsum.release(); c->ffnenu.release(); c->ni.release(); c->iwk.release();
   c->irev.release(); c->iffn.release(); c->la.release(); c->le.release();
   for (int k = 0; k < 4; ++k) { c->a[k].release(); c->mu[k].release(); for (int r = 0; r < 4; ++r) c->nn[k][r].release(); }

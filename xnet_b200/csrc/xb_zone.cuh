@@ -27,6 +27,7 @@ struct ZoneScalars {
   int nh, has_scale, nt, ntt, nto, ints, iweak;
   int kmon[5], ktot[5];
   int inr, its, flag, piv, info, tile_ctr;
+  int rhs_in_jac;            // global-memory Jacobian: the right-hand side rides as column N of the per-CTA scratch (fused path)
   long long ph[PH_COUNT];    // see enum Phase
   long long tmark, dmark;
 };
@@ -65,6 +66,7 @@ __device__ __forceinline__ ZoneMem zone_mem() {
   zm.yt = reinterpret_cast<double *>(xb_smem + L.yt);
   zm.ydot = reinterpret_cast<double *>(xb_smem + L.ydot);
   zm.rhs = reinterpret_cast<double *>(xb_smem + L.rhs);     // tile mode: column N of the tile
+  if (!c_net.tile && zm.s->rhs_in_jac) zm.rhs = zm.s->g_jac + (size_t)c_net.msize * c_net.ld;
   zm.gg = reinterpret_cast<double *>(xb_smem + L.part);     // lives only inside cross_sect
   zm.cs_sm = reinterpret_cast<double *>(xb_smem + L.cs);
   zm.fhs = reinterpret_cast<double *>(xb_smem + L.fhs);
@@ -337,6 +339,42 @@ __device__ __noinline__ void cross_sect_cta() {
       double qr1 = A::mad(rdt9, qdr1, enu[i1]), qr2 = A::mad(rdt9, qdr2, enu[i3]);
       double qk = A::mad(rdene, A::sub(qr2, qr1), qr1);
       zm.qkffn[k + 1] = (qk > -90.0) ? Mx::pow10(qk) : 0.0;
+      if (net.has_logft[k] > 0) {
+        // logft rates (xnet_ffn.F90:222-289): rate = 10^beta + ln2 * phase-space integral / 10^logft
+        using R = Num<STRICT>;
+        const double ln_2 = 0.6931471805599453, ln_10 = 2.302585092994046, rfmin = 1.0e-30, lrfmin = -30.0;
+        const double bok = 8.6173303e-02, m_e = 0.5109989461;
+        const double cheme = -fabs((R(s->etae) * bok * t9t + m_e).v);   // sign(cheme, -has_logft-1.5)
+        double phasei, dphaseidt9;
+        effphase<STRICT>(t9t, cheme, net.ffn_qval[k], &phasei, &dphaseidt9);
+        const double *ec = net.ffn_ec + (size_t)k * kNGrid, *be = net.ffn_beta + (size_t)k * kNGrid;
+        const R rd(rdt9), re(rdene);
+        const R dr1e = R(ec[i2]) - ec[i1], dr2e = R(ec[i4]) - ec[i3];
+        R r1 = R(ec[i1]) + rd * dr1e, r2 = R(ec[i3]) + rd * dr2e;
+        R rf_ec = r1 + re * (r2 - r1);
+        if (phasei > rfmin && rf_ec.v > lrfmin) rf_ec = ln_2 * R(phasei) / R(Mx::pow10(rf_ec.v));
+        else rf_ec = R(0.0);
+        const R dr1b = R(be[i2]) - be[i1], dr2b = R(be[i4]) - be[i3];
+        r1 = R(be[i1]) + rd * dr1b; r2 = R(be[i3]) + rd * dr2b;
+        R rf_beta = r1 + re * (r2 - r1);
+        rf_beta = (rf_beta.v > lrfmin) ? R(Mx::pow10(rf_beta.v)) : R(0.0);
+        const R rft = rf_beta + rf_ec;
+        double dln = 0.0;
+        if (rf_beta.v < rfmin && rf_ec.v < rfmin) zm.rffn[k] = 0.0;
+        else {
+          zm.rffn[k] = rft.v;
+          if (ctl.iheat > 0) {
+            if (rf_ec.v < rfmin) dln = (ln_10 * (re * dr2b + (1.0 - re) * dr1b) / dt9).v;
+            else {
+              const R drbeta_dt = rf_beta * ln_10 * (re * dr2b + (1.0 - re) * dr1b) / dt9;
+              const R drec_dt = rf_ec * (-ln_10 * (re * dr2e + (1.0 - re) * dr1e) / dt9 + R(dphaseidt9) / phasei);
+              dln = ((drbeta_dt + drec_dt) / rft).v;
+            }
+          }
+        }
+        if (ctl.iheat > 0) zm.dlnrffn[k] = dln;
+        continue;
+      }
       double dr1 = A::sub(sum[i2], sum[i1]), dr2 = A::sub(sum[i4], sum[i3]);
       double r1 = A::mad(rdt9, dr1, sum[i1]), r2 = A::mad(rdt9, dr2, sum[i3]);
       double rf = A::mad(rdene, A::sub(r2, r1), r1);
@@ -682,26 +720,44 @@ __device__ __forceinline__ void jacobian_build_impl(const DevNet &net, const Zon
     __syncthreads();
     // row ny: d t9dot / d(y_j, T9) = - sum_i mex_i dydotdy(j,i) / cv, summed over i in order
     {
-      const double *mex = net.mex;
       const double cv = zm.s->cv;
       const int rT = pos[ny];
+      double *mexs = part;   // mass excesses staged in shared memory, in slot order: mexs[pos[i]] = mex[i]
+      if (!STRICT) {
+        for (int i = tid; i < N; i += nt) mexs[i] = 0.0;
+        __syncthreads();
+        for (int i = tid; i < ny; i += nt) mexs[pos[i]] = net.mex[i];
+        __syncthreads();
+      }
       for (int j = tid; j < N; j += nt) {
         const double *col = J + (size_t)j * ld;
         double sdot = 0.0;
-        for (int i = 0; i < ny; ++i) sdot = A::sub(sdot, A::div(A::mul(mex[i], col[pos[i]]), cv));
+        if (STRICT) {
+          const double *mex = net.mex;
+          for (int i = 0; i < ny; ++i) sdot = A::sub(sdot, A::div(A::mul(mex[i], col[pos[i]]), cv));
+        } else {   // one pass over the slots (the T9 slot still holds 0), one division
+          double s0 = 0.0, s1 = 0.0;
+          int r = 0;
+          for (; r + 1 < N; r += 2) { s0 = fma(mexs[r], col[r], s0); s1 = fma(mexs[r + 1], col[r + 1], s1); }
+          if (r < N) s0 = fma(mexs[r], col[r], s0);
+          sdot = -(s0 + s1) / cv;
+        }
         J[(size_t)j * ld + rT] = sdot;
       }
     }
     __syncthreads();
-    // jacobian_scale: jac = mult * dydotdy^T + diag on the diagonal
+    // jacobian_scale: jac = mult * dydotdy^T + diag on the diagonal (a warp per column, no index division)
     {
       const double rdt = zm.s->rdt, m = zm.s->mult;
-      for (int e = tid; e < N * N; e += nt) {
-        const int j = e / N, i = e - j * N;
-        const int idx = j * ld + pos[i];
-        double v = A::mul(m, J[idx]);
-        if (i == j) v = A::add(v, rdt);
-        J[idx] = v;
+      const int lane = tid & 31, wq = tid >> 5, nw = nt >> 5;
+      for (int j = wq; j < N; j += nw) {
+        double *col = J + (size_t)j * ld;
+        const int dslot = pos[j];
+        for (int r = lane; r < N; r += 32) {
+          double v = A::mul(m, col[r]);
+          if (r == dslot) v = A::add(v, rdt);
+          col[r] = v;
+        }
       }
     }
     __syncthreads();
@@ -716,21 +772,21 @@ __device__ __noinline__ void jacobian_build_cta() {
 
 // with_rhs: zm.rhs rides through the factorisation as column N of the tile (forward solve for free)
 template <bool STRICT>
-__device__ __forceinline__ void lu_cta(const ZoneMem &zm, const int N, const bool with_rhs) {
+__device__ __forceinline__ void lu_cta(const ZoneMem &zm, const int N, const bool with_rhs, const bool invert) {
   if (zm.tile) {
     // zm.rhs IS column N of the tile
     lu_blocked<STRICT, true, 1>(zm.jac, zm.ld, N, with_rhs ? 1 : 0, zm.indx, &zm.s->info, zm.prow, zm.rdiag,
-                                zm.s->ph + PH_LU_PANEL, zm.orig, zm.pos);
+                                zm.s->ph + PH_LU_PANEL, zm.orig, zm.pos, invert);
   } else {
-    lu_blocked<STRICT, false, 2>(zm.jac, zm.ld, N, 0, zm.indx, &zm.s->info, zm.prow, nullptr, zm.s->ph + PH_LU_PANEL,
-                                 zm.orig, zm.pos);
+    lu_blocked<STRICT, false, 2>(zm.jac, zm.ld, N, (with_rhs && zm.s->rhs_in_jac) ? 1 : 0, zm.indx, &zm.s->info, zm.prow,
+                                 zm.rdiag, zm.s->ph + PH_LU_PANEL, zm.orig, zm.pos, invert);
   }
 }
 template <bool STRICT>
 // the right-hand side is already in slot order (rhs[pos[i]] = b_i), so no interchanges are applied here
 __device__ __forceinline__ void bksub_cta(const ZoneMem &zm, const int N, const bool fwd_done) {
-  if (zm.tile) bksub_block<STRICT, true>(zm.jac, zm.ld, N, zm.indx, zm.rhs, zm.rdiag, zm.prow, fwd_done, false);
-  else bksub_simple<STRICT>(zm.jac, zm.ld, N, zm.indx, zm.rhs, false);
+  if (zm.tile) bksub_block<STRICT, true, 1>(zm.jac, zm.ld, N, zm.indx, zm.rhs, zm.rdiag, zm.prow, fwd_done, false, !STRICT);
+  else bksub_block<STRICT, false, 2>(zm.jac, zm.ld, N, zm.indx, zm.rhs, zm.rdiag, zm.prow, fwd_done, false, !STRICT);
 }
 
 // --- step_be: Newton-Raphson loop (xnet_integrate_be.F90:233-482) -------------------------------
@@ -776,10 +832,10 @@ __device__ __noinline__ void step_be_cta() {
     }
     __syncthreads();
     if (rebuild) {
-      lu_cta<STRICT>(zm, N, true);
+      lu_cta<STRICT>(zm, N, true, true);
       XB_PHASE_END(zm, PH_LU);
     }
-    bksub_cta<STRICT>(zm, N, rebuild && zm.tile);
+    bksub_cta<STRICT>(zm, N, rebuild && (zm.tile || s->rhs_in_jac));
     XB_PHASE_END(zm, PH_BKSUB);
     {
       const double *aa = net.aa;
