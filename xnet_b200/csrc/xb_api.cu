@@ -113,6 +113,14 @@ static SmemOff smem_layout(int ny, int N, int ld, int npart, bool jac_in_smem, i
   L.pos = (int)o; o += (size_t)N * 4;
   o = (o + 15) / 16 * 16;
   L.fhs = (int)o; o += (size_t)2 * nzs * 8;
+  o = (o + 15) / 16 * 16;
+  L.lds2 = 0; L.lu_s = L.lu_u = (int)o;
+  if (!jac_in_smem && N <= 320) {   // two-level LU: 32-column panel (ld = 4 mod 8) and the 32 x (N+1-32) block of U
+    int l2 = N; while ((l2 & 7) != 4) ++l2;
+    L.lds2 = l2;
+    L.lu_s = (int)o; o += (size_t)32 * l2 * 8;
+    L.lu_u = (int)o; o += (size_t)32 * (N + 1) * 8;
+  }
   L.cs = (int)o;
   L.total = (int)o;
   return L;

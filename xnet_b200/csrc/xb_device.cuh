@@ -30,7 +30,7 @@ struct DevPlan {
 };
 
 // byte offsets of the zone working set inside the CTA's dynamic shared memory
-struct SmemOff { int scal, jac, y, yt, ydot, rhs, rdiag, part, prow, indx, orig, pos, fhs, cs, total; };
+struct SmemOff { int scal, jac, y, yt, ydot, rhs, rdiag, part, prow, indx, orig, pos, fhs, lu_s, lu_u, lds2, cs, total; };
 
 struct DevNet {
   int ny, nrtot, nffn, msize, ld, nffr, tile;

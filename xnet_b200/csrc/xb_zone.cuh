@@ -45,6 +45,8 @@ struct ZoneMem {
   double *gg;       // [ny+1] partition functions (aliases part)
   double *cs_sm;    // shared-memory cache of csect[cs_lo..nrtot)
   double *fhs;      // [2][nzs] strong-screening energy per charge and its T9 derivative (iscrn > 0)
+  double *lu_s, *lu_u;   // two-level LU of global-memory Jacobians: panel [32][lds2] and U block [ncol][32] (else null)
+  int lds2;
   double *csect;    // [nrtot] (global scratch)
   double *rffn;     // [nffn]
   double *dcsect, *dlnrffn;   // self-heating only (global scratch)
@@ -70,6 +72,9 @@ __device__ __forceinline__ ZoneMem zone_mem() {
   zm.gg = reinterpret_cast<double *>(xb_smem + L.part);     // lives only inside cross_sect
   zm.cs_sm = reinterpret_cast<double *>(xb_smem + L.cs);
   zm.fhs = reinterpret_cast<double *>(xb_smem + L.fhs);
+  zm.lds2 = L.lds2;
+  zm.lu_s = L.lds2 ? reinterpret_cast<double *>(xb_smem + L.lu_s) : nullptr;
+  zm.lu_u = L.lds2 ? reinterpret_cast<double *>(xb_smem + L.lu_u) : nullptr;
   zm.rdiag = reinterpret_cast<double *>(xb_smem + L.rdiag);
   zm.part = reinterpret_cast<double *>(xb_smem + L.part);
   zm.prow = reinterpret_cast<double *>(xb_smem + L.prow);
@@ -777,6 +782,9 @@ __device__ __forceinline__ void lu_cta(const ZoneMem &zm, const int N, const boo
     // zm.rhs IS column N of the tile
     lu_blocked<STRICT, true, 1>(zm.jac, zm.ld, N, with_rhs ? 1 : 0, zm.indx, &zm.s->info, zm.prow, zm.rdiag,
                                 zm.s->ph + PH_LU_PANEL, zm.orig, zm.pos, invert);
+  } else if (zm.lu_s) {
+    lu_two_level<STRICT>(zm.jac, zm.ld, N, (with_rhs && zm.s->rhs_in_jac) ? 1 : 0, zm.indx, &zm.s->info, zm.prow, zm.rdiag,
+                         zm.s->ph + PH_LU_PANEL, zm.orig, zm.pos, invert, zm.lu_s, zm.lds2, zm.lu_u);
   } else {
     lu_blocked<STRICT, false, 2>(zm.jac, zm.ld, N, (with_rhs && zm.s->rhs_in_jac) ? 1 : 0, zm.indx, &zm.s->info, zm.prow,
                                  zm.rdiag, zm.s->ph + PH_LU_PANEL, zm.orig, zm.pos, invert);
