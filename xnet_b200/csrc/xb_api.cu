@@ -115,7 +115,14 @@ static SmemOff smem_layout(int ny, int N, int ld, int npart, bool jac_in_smem, i
   L.fhs = (int)o; o += (size_t)2 * nzs * 8;
   o = (o + 15) / 16 * 16;
   L.lds2 = 0; L.lu_s = L.lu_u = (int)o;
-  if (!jac_in_smem && N <= 320) {   // two-level LU: 32-column panel (ld = 4 mod 8) and the 32 x (N+1-32) block of U
+  // Two-level LU (lu_two_level): built, parity-green, but measured slower than the single-level path on XRB304
+  // (1.89M vs 1.63M cycles per Newton iteration), so it is only enabled with -DXB_TWO_LEVEL.
+#ifdef XB_TWO_LEVEL
+  const bool two_level = true;
+#else
+  const bool two_level = false;
+#endif
+  if (two_level && !jac_in_smem && N <= 320) {   // 32-column panel (ld = 4 mod 8) and the 32 x (N+1-32) block of U
     int l2 = N; while ((l2 & 7) != 4) ++l2;
     L.lds2 = l2;
     L.lu_s = (int)o; o += (size_t)32 * l2 * 8;
