@@ -28,6 +28,7 @@ WORKLOADS = {   # settings fragment, problem setup, description[, screening swit
     'sn160_scrn': ('test_settings', 'setup_tnsn_sn160', 'SN160 (160 species, 2048 reactions), BE, screening on, th_sn1aflame', 1),
     'sn160': ('test_settings', 'setup_tnsn_sn160', 'SN160 (160 species, 2048 reactions), BE, th_sn1aflame'),
     'sn160_heat': ('test_settings_heat', 'setup_heat_sn160', 'SN160, BE, self-heating + screening, C/O burn (test_settings_heat)'),
+    'sn231_logft': ('test_settings_logft', 'setup_logft_sn231', 'SN231 logft weak rates, BE, self-heating + screening, C/O burn (test_settings_logft)'),
     'torch47': ('test_settings', 'setup_tnsn_torch47', 'torch47 (47 species), BE, th_sn1aflame'),
     'alpha': ('test_settings_small', 'setup_tnsn_alpha', 'alpha (14 species), BE, th_sn1aflame'),
     'xrb304': ('test_settings', 'setup_xrb_fisker', 'XRB304 (304 species), BE, th_fisker_aboveign_b1'),

@@ -421,7 +421,11 @@ __device__ __noinline__ void cross_sect_cta() {
   const int2 *__restrict__ ni2 = reinterpret_cast<const int2 *>(net.ni);
   const int *__restrict__ iwkp = net.iwk, *__restrict__ irevp = net.irev;
   const double *gg = zm.gg;
-#pragma unroll 2
+#ifndef XB_RATE_UNROLL
+#define XB_RATE_UNROLL 1
+#endif
+  constexpr int kRateUnroll = XB_RATE_UNROLL;
+#pragma unroll kRateUnroll
   for (int k = tid; k < nrtot; k += nt) {
     // every load of the reaction is issued up front (one L2 round trip per reaction, not three)
     const int iwk = __ldg(iwkp + k), irev = __ldg(irevp + k);
