@@ -101,6 +101,15 @@ def reduce_max_sum(world, tmax, vsum):
     return float(a.item()), float(b.item())
 
 
+def zone_block(rank, world, zones_per_gpu, nfix):
+    """Block partition of the job's zones: rank r owns the global zones [r*Z, (r+1)*Z); global zone z
+    evolves fixture z mod K.  Returns (global zone numbers, fixture index per zone)."""
+    import numpy as np
+    assert 0 <= rank < world and zones_per_gpu > 0 and nfix > 0
+    gz = np.arange(rank * zones_per_gpu, (rank + 1) * zones_per_gpu)
+    return gz, gz % nfix
+
+
 def barrier(world):
     if world > 1:
         import torch.distributed as dist
@@ -176,8 +185,8 @@ def main():
     ctx = X.Context(net, ctl, nzevolve=1, device=local, arith=1 if args.arith == 'strict' else 0, **ov)
     nz = args.zones
     # zone z of the whole job uses fixture (global z) mod K; rank r owns the block [r*nz, (r+1)*nz)
-    gz = np.arange(rank * nz, (rank + 1) * nz)
-    zones = X.build_zone_set(fx, nzone=nz, zfix=gz % len(fx))
+    gz, zfix = zone_block(rank, world, nz, len(fx))
+    zones = X.build_zone_set(fx, nzone=nz, zfix=zfix)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')   # > 126 MB L2
 
     fp64_peak = api.measure_fp64_peak(local)
