@@ -251,12 +251,13 @@ def main():
                 'd2h_bytes_per_step': d2h},
         'gpu_launches': int(launches),
         'clocks': sampler.summary(),
-        'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': fp64_peak / 1e12, 'unit': 'TFLOP/s',
+        'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak / 1e12, 'unit': 'TFLOP/s',
                      'frac': achieved / (fp64_peak / 1e12), 'traffic': None,
                      'kernel': 'evolve_kernel (fused rates+ydot+Jacobian+LU+bksub+Newton/timestep control)',
                      'algorithmic': '2/3*N^3 flops x ktot(3) LU factorizations per launch (N=%d, %d factorizations)' % (N, int(nlu)),
-                     'peak_source': 'FP64 peak measured live on this GPU (DFMA microbenchmark; tools/dmma_probe.cu: the FP64 tensor pipe '
-                                    'DMMA.8x8x4 peaks at the same 64 FMA/clk/SM); MEASURED_PEAKS.json has only bf16/HBM entries',
+                     'bound_note': 'FP64 compute (the LU): neither HBM nor the bf16 tensor peak bounds this path; the FP64 tensor '
+                                   'pipe (DMMA.8x8x4) has the same 64 FMA/clk/SM peak as DFMA on B200 (tools/dmma_probe.cu)',
+                     'peak_source': 'FP64 FMA peak measured live on this GPU (DFMA microbenchmark); MEASURED_PEAKS.json has only bf16/HBM entries',
                      'phase_share': {k: round(ph[k] / phase_tot, 4) for k in ('rates', 'yderiv', 'jac', 'lu', 'bksub', 'other', 'lu_panel', 'lu_swap_trsm', 'lu_gemm')},
                      'cycles_per_newton_iter': phase_tot / max(newton, 1.0),
                      'pivot_steps_per_lu': ph['spare'] / max(nlu, 1.0),
