@@ -110,6 +110,13 @@ def zone_block(rank, world, zones_per_gpu, nfix):
     return gz, gz % nfix
 
 
+def dist_teardown(world):
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
 def barrier(world):
     if world > 1:
         import torch.distributed as dist
@@ -128,7 +135,8 @@ def cpu_run(workload, nzone, threads, kstmx=None):
 
 
 def run_reference(args):
-    rank, world, _ = dist_setup(args.gpus)
+    # no process group: the reference arm has nothing to exchange; under torchrun rank 0 alone works and prints
+    rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
@@ -227,6 +235,8 @@ def main():
     ok = bool((res['status'] == -1).all())
 
     if rank != 0:
+        ctx.close()
+        dist_teardown(world)
         return
     N = ctx.msize
     lu_flops = (2.0 / 3.0) * N ** 3 * nlu               # per launch, this rank
@@ -276,6 +286,7 @@ def main():
                                           '(Fortran reference not buildable: no Fortran compiler)' % cz}
     print(json.dumps(line))
     ctx.close()
+    dist_teardown(world)
 
 
 if __name__ == '__main__':

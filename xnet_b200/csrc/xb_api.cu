@@ -517,6 +517,8 @@ static int upload_network(xb_ctx *c) {
   CUDA_TRY(c->ffn_ec.put(h.ffn_ec)); CUDA_TRY(c->ffn_beta.put(h.ffn_beta)); CUDA_TRY(c->ffn_qval.put(h.ffn_qval));
   CUDA_TRY(c->has_logft.put(h.has_logft));
   d.ffn_ec = c->ffn_ec.p; d.ffn_beta = c->ffn_beta.p; d.ffn_qval = c->ffn_qval.p; d.has_logft = c->has_logft.p;
+  d.any_logft = 0;
+  for (int k = 0; k < h.nffn; ++k) if (h.has_logft[k] > 0) d.any_logft = 1;
   d.aa = c->aa.p; d.zz = c->zz.p; d.mex = c->mex.p; d.be = c->be.p; d.g = c->g.p; d.lng = c->lng.p; d.dlng = c->dlng.p;
   d.t9i = c->t9i.p; d.ffnsum = c->ffnsum.p; d.ffnenu = c->ffnenu.p;
   // composition moment table (always: cheap) and, for screening / self-heating, the EOS and screening tables

@@ -55,6 +55,7 @@ struct DevNet {
   const double *ffn_ec, *ffn_beta;   // [nffn][143] logft tables (xnet_ffn.F90:100-137)
   const double *ffn_qval;    // [nffn]
   const int *has_logft;      // [nffn] 0 = tabulated rate, 1/2 = logft (ft-/ft+)
+  int any_logft;             // some FFN reaction uses the logft form (needs the electron chemical potential)
   double mex_n, mex_p;
   // equation of state and screening (iscrn > 0 or iheat > 0), see xb_eos.cuh
   const double *helm;        // [13][201][541] Helmholtz table planes

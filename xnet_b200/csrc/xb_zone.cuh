@@ -233,15 +233,15 @@ __device__ __noinline__ void cross_sect_cta() {
                        zm.part, s->red + 2);
     block_sum2<STRICT>(ny, [&](int k, double &ta, double &tb) { ta = A::mul(yt[k], zzi[k]); tb = 0.0; }, zm.part, s->mom);
   }
-  if (tid == 0) {
+  // With screening / self-heating the scalar EOS chain (cold code, ~25k cycles) is moved to the first lane of the
+  // last warp and overlapped with everything that does not depend on it: the FFN table rates and the
+  // one-reactant rates of the other warps.  logft rates need the electron chemical potential first: no split.
+  const bool split = eos_on && nt >= 64 && !net.any_logft;
+  // EOS / plasma / screening scalars of this rate evaluation: one thread (scalar chain)
+  auto eos_chain = [&]() {
     const double yext = A::div(s->xext, s->aext);
     const double atot = A::add(s->red[0], s->xext);
     const double ztot = A::mad(yext, s->zext, s->red[1]);
-    s->yet = A::div(ztot, atot);
-    s->cv = 0.0; s->etae = 0.0; s->detaedt9 = 0.0;
-    s->iweak = (t9t < 0.01 && ctl.iweak0 != 0) ? -abs(ctl.iweak0) : ctl.iweak0;
-    s->ktot[4] += 1;
-    if (eos_on) {
       // update_eos -> eos_interface -> eosx (xnet_eos_starkiller.F90:64-135) and eos_screen (:244-323)
       const double ntot = A::add(s->red[2], yext);
       const double z2tot = A::add(s->red[3], A::mul(A::mul(yext, s->zext), s->zext));
@@ -273,7 +273,16 @@ __device__ __noinline__ void cross_sect_cta() {
         s->dlnhw0dt9 = (dzt / ztilde - 1.5 / R(t9t)).v;
         s->dlnhi0dt9 = (-thbim2 * dzt / ztilde - 1.5 * bi / R(t9t)).v;
       }
-    }
+  };
+  if (tid == 0) {
+    const double yext = A::div(s->xext, s->aext);
+    const double atot = A::add(s->red[0], s->xext);
+    const double ztot = A::mad(yext, s->zext, s->red[1]);
+    s->yet = A::div(ztot, atot);
+    s->cv = 0.0; s->etae = 0.0; s->detaedt9 = 0.0;
+    s->iweak = (t9t < 0.01 && ctl.iweak0 != 0) ? -abs(ctl.iweak0) : ctl.iweak0;
+    s->ktot[4] += 1;
+    if (eos_on && !split) eos_chain();
   }
   // temperature powers: four threads of different warps evaluate one transcendental each
   // t09(3,4,6,7) = T9^(-1/3), T9^(1/3), T9^(5/3), ln T9   (xnet_integrate.F90:650-656)
@@ -309,7 +318,10 @@ __device__ __noinline__ void cross_sect_cta() {
   XB_DBG(zm, 4);
   const double ene = A::mul(s->yet, rhot);
   const int iweak = s->iweak;
-  if (ctl.iscrn > 0) {
+  const bool worker = !split || tid < nt - 32;       // threads that run the FFN block and the first rate pass
+  const int wnt = split ? nt - 32 : nt;
+  if (split && tid == nt - 32) eos_chain();
+  auto fhs_table = [&]() {
     // strong-screening energy per charge, DeWitt & Slattery (2003) fit (xnet_screening.F90:225-235)
     using R = Num<STRICT>;
     const double cds1 = -0.899172, cds2 = 0.602249, cds3 = -0.274823, cds4 = -1.401915, cds5 = 0.3230064;
@@ -323,10 +335,11 @@ __device__ __noinline__ void cross_sect_cta() {
       fhs[j] = (cds1 * gammaz + cds2 / cds5 * gammaz5 + cds3 * lgammaz + cds4).v;
       dfhs[j] = (-(cds1 * gammaz + cds2 * gammaz5 + cds3) / R(t9t)).v;
     }
-  }
+  };
+  if (ctl.iscrn > 0 && !split) fhs_table();
 
   // FFN tabulated weak rates
-  if (net.nffn > 0) {
+  if (net.nffn > 0 && worker) {
     const double t9grid[13] = {0.01, 0.1, 0.2, 0.4, 0.7, 1.0, 1.5, 2.0, 3.0, 5.0, 10.0, 30.0, 100.0};
     int i = 1;
     for (; i <= 13; ++i) if (t9t <= t9grid[i - 1]) break;
@@ -338,7 +351,7 @@ __device__ __noinline__ void cross_sect_cta() {
     const double dene = A::sub((double)(le1 + 1), (double)le1);
     const double rdene = A::div(A::sub(enel, (double)le1), dene);
     const int i1 = 13 * (le1 - 1) + lt1 - 1, i2 = i1 + 1, i3 = 13 * le1 + lt1 - 1, i4 = i3 + 1;  // 0-based
-    for (int k = tid; k < net.nffn; k += nt) {
+    for (int k = tid; k < net.nffn; k += wnt) {
       const double *enu = net.ffnenu + (size_t)k * kNGrid, *sum = net.ffnsum + (size_t)k * kNGrid;
       double qdr1 = A::sub(enu[i2], enu[i1]), qdr2 = A::sub(enu[i4], enu[i3]);
       double qr1 = A::mad(rdt9, qdr1, enu[i1]), qr2 = A::mad(rdt9, qdr2, enu[i3]);
@@ -392,7 +405,8 @@ __device__ __noinline__ void cross_sect_cta() {
     }
     if (tid == 0) zm.qkffn[0] = 0.0;
   }
-  __syncthreads();
+  if (!split) __syncthreads();
+  else if (worker) bar_named(2, nt - 32);            // the FFN rates are visible to the workers' rate pass
 
   XB_DBG(zm, 5);
   // REACLIB rates: one thread per reaction, coalesced coefficient loads
@@ -425,8 +439,20 @@ __device__ __noinline__ void cross_sect_cta() {
 #define XB_RATE_UNROLL 1
 #endif
   constexpr int kRateUnroll = XB_RATE_UNROLL;
+  // split: pass 0 = one-reactant rates by the worker warps while the EOS chain runs, pass 1 = the screened
+  // classes by everybody once the plasma parameters and the per-charge table exist (one copy of the loop body)
+  for (int pass = 0; pass < (split ? 2 : 1); ++pass) {
+  int kbeg = 0, kend = nrtot, kstride = nt;
+  if (split) {
+    if (pass == 0) { kend = net.roff[1]; kstride = nt - 32; if (!worker) kbeg = kend; }
+    else {
+      kbeg = net.roff[1];
+      __syncthreads();                                 // EOS chain and pass 0 done
+      if (ctl.iscrn > 0) { fhs_table(); __syncthreads(); }
+    }
+  }
 #pragma unroll kRateUnroll
-  for (int k = tid; k < nrtot; k += nt) {
+  for (int k = kbeg + tid; k < kend; k += kstride) {
     // every load of the reaction is issued up front (one L2 round trip per reaction, not three)
     const int iwk = __ldg(iwkp + k), irev = __ldg(irevp + k);
     const int2 n01 = __ldg(ni2 + 3 * k), n23 = __ldg(ni2 + 3 * k + 1), n45 = __ldg(ni2 + 3 * k + 2);
@@ -511,6 +537,7 @@ __device__ __noinline__ void cross_sect_cta() {
     zm.csect[k] = cs;
     if (k >= net.cs_lo) zm.cs_sm[k - net.cs_lo] = cs;
   }
+  }   // pass
   XB_DBG(zm, 6);
   __syncthreads();
   XB_DBG(zm, 7);
