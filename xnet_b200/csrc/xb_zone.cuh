@@ -574,13 +574,23 @@ __device__ __forceinline__ void plan_run_fast(const DevPlan &P, const double *cs
   const int L = P.L, nt = blockDim.x;
   int idx = threadIdx.x;
   double acc = 0.0;
+  // software pipeline over batches of kPlanU records: the records of the next batch (coalesced loads from L2) are
+  // in flight while the current batch gathers its rates and abundances from shared memory and multiplies
+  double va[kPlanU]; uint2 na[kPlanU], ma[kPlanU];
+#pragma unroll
+  for (int u = 0; u < kPlanU; ++u) { va[u] = __ldg(pa + idx + u * nt); na[u] = __ldg(pn + idx + u * nt); ma[u] = __ldg(pm + idx + u * nt); }
   for (int k0 = 0; k0 < L; k0 += kPlanU) {
-    // stage 1: the records (coalesced); stage 2: rate and abundance gathers, all in flight together;
-    // stage 3: independent products; stage 4: the only sequential part, accumulate and flush
     double v[kPlanU], c[kPlanU], f0[kPlanU], f1[kPlanU], f2[kPlanU], f3[kPlanU];
     uint2 nn[kPlanU], mc[kPlanU];
 #pragma unroll
-    for (int u = 0; u < kPlanU; ++u) { v[u] = __ldg(pa + idx + u * nt); nn[u] = __ldg(pn + idx + u * nt); mc[u] = __ldg(pm + idx + u * nt); }
+    for (int u = 0; u < kPlanU; ++u) { v[u] = va[u]; nn[u] = na[u]; mc[u] = ma[u]; }
+    idx += kPlanU * nt;
+    if (k0 + kPlanU < L) {
+#pragma unroll
+      for (int u = 0; u < kPlanU; ++u) { va[u] = __ldg(pa + idx + u * nt); na[u] = __ldg(pn + idx + u * nt); ma[u] = __ldg(pm + idx + u * nt); }
+    }
+    // rate and abundance gathers, all in flight together; independent products; then the only sequential
+    // part: accumulate and flush
 #pragma unroll
     for (int u = 0; u < kPlanU; ++u) {
       c[u] = cs_fetch(cs, cs_sm, cs_lo, mc[u].x);
@@ -593,7 +603,6 @@ __device__ __forceinline__ void plan_run_fast(const DevPlan &P, const double *cs
       acc += v[u];
       if (mc[u].y & 3u) { flush(mc[u].y, acc); acc = 0.0; }
     }
-    idx += kPlanU * nt;
   }
 }
 
