@@ -139,6 +139,28 @@ int xb_jacobian_bksub(xb_ctx *ctx, int32_t zlo, int32_t zhi, const int32_t *mask
                       const double *t9rhs, double *dy, double *dt9);
 int xb_jacobian_solve(xb_ctx *ctx, int32_t zlo, int32_t zhi, const int32_t *mask, const double *yrhs,
                       const double *t9rhs, double *dy, double *dt9, int32_t *info);
+/* Self-heating (iheat > 0, msize = ny+1) at module level: the T9 equation is row/column ny of jac, t9rhs/dt9 are
+ * required by bksub/solve, and the module variables the reference keeps between calls are mirrored on the device:
+ * dcsect*(nr,nz) (xnet_integrate.F90:807-815), cv/etae/detaedt9 (xnet_conditions, set by update_eos inside
+ * cross_sect) and t9dot (set by yderiv, xnet_integrate.F90:471-487).  NULL outputs are skipped. */
+int xb_get_dcsect(xb_ctx *ctx, int32_t zlo, int32_t zhi, double *dcsect);
+int xb_get_eos(xb_ctx *ctx, int32_t zlo, int32_t zhi, double *cv, double *etae, double *detaedt9, double *t9dot);
+
+/* step_be (source/xnet_integrate_be.F90:233-482): the complete Newton-Raphson loop of ONE backward-Euler step in one
+ * launch -- no host synchronisation per iteration (the reference has one, :430).  Module-variable interface of the
+ * reference spelled out as arguments, all host arrays over the slice:
+ *   inr(nz)    in: 0 = active, anything else = inactive (left untouched); out: > 0 = Newton iterations to convergence,
+ *              0 = not converged in kitmx iterations
+ *   y(ny,nz)   abundances at the start of the step;  yt(ny,nz) in: first guess, out: last iterate
+ *   tdel(nz)   step size (non-zero for active zones);  t9(nz) temperature at the start of the step
+ *   t9t(nz)    in: trial temperature, out: updated when iheat > 0;  rhot(nz) trial density
+ *   nh(nz)     trajectory length (rates are re-evaluated at kit = 1 only when nh > 1, :300-307); NULL = 2
+ *   ydot, t9dot (optional out) derivative of the last iterate's evaluation; kcount(5,nz) (optional out) increments
+ *   of ktot(3:5) = Jacobian builds, yderiv calls, cross_sect calls made by this call (ktot(1:2) belong to solve_be).
+ * With iheat = 0 and nh <= 1 the rates of the previous xb_cross_sect call are used, as in the reference. */
+int xb_step_be(xb_ctx *ctx, int32_t zlo, int32_t zhi, int32_t kstep, int32_t *inr, const double *y, double *yt,
+               const double *tdel, const double *t9, double *t9t, const double *rhot, const int32_t *nh,
+               double *ydot, double *t9dot, int32_t *kcount);
 
 /* ---- fused evolve (full_net on device) ------------------------------------------------------ */
 typedef struct {

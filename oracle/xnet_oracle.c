@@ -850,3 +850,53 @@ int ox_eval_point(const ox_net *net, const ox_ctl *ctl, double t9, double rho, c
   zone_free(z);
   return rc_;
 }
+
+/* Same chain with the self-heating outputs (iheat > 0: msize = ny+1): additionally dcsect (concatenated classes),
+ * eos[3] = cv, etae, detaedt9 (update_eos inside cross_sect) and t9dot (yderiv, xnet_integrate.F90:471-487).
+ * jac is msize x msize. */
+int ox_eval_point_heat(const ox_net *net, const ox_ctl *ctl, double t9, double rho, const double *y,
+                       double xext, double aext, double zext, double diag, double mult,
+                       double *csect, double *dcsect, double *ydot, double *jac, double *ye_out, double *eos,
+                       double *t9dot) {
+  zone_t *z = zone_new(net, ctl); int k, c, o = 0, rc_;
+  zone_reset_scratch(z);
+  z->t9t = t9; z->rhot = rho; z->xext = xext; z->aext = aext; z->zext = zext; z->nh = 2;
+  for (k = 0; k < z->ny; k++) { z->yt[k] = y[k]; z->y[k] = y[k]; }
+  rc_ = cross_sect(z);
+  if (!rc_) {
+    yderiv(z);
+    jacobian_build(z, diag, mult);
+    for (c = 0; c < 4; c++) {
+      memcpy(csect + o, z->csect[c], sizeof(double) * net->nr[c]);
+      memcpy(dcsect + o, z->dcsect[c], sizeof(double) * net->nr[c]);
+      o += net->nr[c];
+    }
+    memcpy(ydot, z->ydot, sizeof(double) * z->ny);
+    memcpy(jac, z->jac, sizeof(double) * z->msize * z->msize);
+    *ye_out = z->yet; eos[0] = z->cv; eos[1] = z->etae; eos[2] = z->detaedt9; *t9dot = z->t9dot;
+  }
+  zone_free(z);
+  return rc_;
+}
+
+/* One call of step_be (xnet_integrate_be.F90:233-482) on an explicit state: y, tdel, t9 at the start of the step;
+ * yt/t9t first guess in, last iterate out; nh > 1 makes the rates be evaluated at kit = 1.  Returns inr through
+ * *inr_out (0 = no convergence), ydot/t9dot of the last evaluation, kcount[5] = counter increments. */
+int ox_step_be_point(const ox_net *net, const ox_ctl *ctl, const double *y, double *yt, double tdel, double t9,
+                     double *t9t, double rhot, int nh, double xext, double aext, double zext,
+                     int *inr_out, double *ydot, double *t9dot, int *kcount) {
+  zone_t *z = zone_new(net, ctl); int k, rc_, inr = 0;
+  zone_reset_scratch(z);
+  z->t9 = t9; z->t9t = *t9t; z->rhot = rhot; z->tdel = tdel; z->nh = nh;
+  z->xext = xext; z->aext = aext; z->zext = zext;
+  for (k = 0; k < 5; k++) z->ktot[k] = 0;
+  for (k = 0; k < z->ny; k++) { z->y[k] = y[k]; z->yt[k] = yt[k]; }
+  rc_ = step_be(z, &inr);
+  if (!rc_) {
+    for (k = 0; k < z->ny; k++) { yt[k] = z->yt[k]; ydot[k] = z->ydot[k]; }
+    *t9t = z->t9t; *t9dot = z->t9dot; *inr_out = inr;
+    for (k = 0; k < 5; k++) kcount[k] = z->ktot[k];
+  }
+  zone_free(z);
+  return rc_;
+}

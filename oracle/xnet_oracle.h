@@ -85,6 +85,16 @@ int ox_eval_point(const ox_net *net, const ox_ctl *ctl, double t9, double rho, c
                   double xext, double aext, double zext, double diag, double mult,
                   double *csect, double *ydot, double *jac, double *ye_out);
 
+/* ox_eval_point with the self-heating outputs (jac is msize x msize, msize = ny + (iheat>0)) */
+int ox_eval_point_heat(const ox_net *net, const ox_ctl *ctl, double t9, double rho, const double *y,
+                       double xext, double aext, double zext, double diag, double mult,
+                       double *csect, double *dcsect, double *ydot, double *jac, double *ye_out, double *eos,
+                       double *t9dot);
+/* one step_be call (Newton loop of one backward-Euler step) on an explicit state */
+int ox_step_be_point(const ox_net *net, const ox_ctl *ctl, const double *y, double *yt, double tdel, double t9,
+                     double *t9t, double rhot, int nh, double xext, double aext, double zext,
+                     int *inr_out, double *ydot, double *t9dot, int *kcount);
+
 #ifdef __cplusplus
 }
 #endif

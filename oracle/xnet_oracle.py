@@ -73,6 +73,12 @@ def lib(fast=False):
         l.ox_eval_point.restype = C.c_int
         l.ox_eval_point.argtypes = [C.POINTER(OxNet), C.POINTER(OxCtl)] + [C.c_double] * 2 + [c_dp] + \
             [C.c_double] * 5 + [c_dp, c_dp, c_dp, c_dp]
+        l.ox_eval_point_heat.restype = C.c_int
+        l.ox_eval_point_heat.argtypes = [C.POINTER(OxNet), C.POINTER(OxCtl)] + [C.c_double] * 2 + [c_dp] + \
+            [C.c_double] * 5 + [c_dp] * 7
+        l.ox_step_be_point.restype = C.c_int
+        l.ox_step_be_point.argtypes = [C.POINTER(OxNet), C.POINTER(OxCtl), c_dp, c_dp, C.c_double, C.c_double, c_dp,
+                                       C.c_double, C.c_int] + [C.c_double] * 3 + [c_ip, c_dp, c_dp, c_ip]
         _libs[key] = l
     return _libs[key]
 
@@ -224,6 +230,32 @@ class Problem:
         if rc:
             raise RuntimeError('ox_eval_point rc=%d' % rc)
         return cs, yd, jac.reshape(ny, ny).T.copy(), ye[0]   # jac returned as [row, col]
+
+
+def eval_point_heat(prob, t9, rho, y, diag, mult, which='strict', xext=0.0, aext=1.0, zext=0.0):
+    """cross_sect -> yderiv -> jacobian_build on one state with the self-heating outputs.
+    Returns dict(csect, dcsect, ydot, jac [col,row] (msize x msize), ye, eos (cv, etae, detaedt9), t9dot)."""
+    ny = prob.nuc['ny']; nrt = sum(prob.net['nreac']); m = ny + (1 if prob.ctl['iheat'] > 0 else 0)
+    cs = np.zeros(nrt); dcs = np.zeros(nrt); yd = np.zeros(ny); jac = np.zeros(m * m); ye = np.zeros(1)
+    eos = np.zeros(3); t9d = np.zeros(1)
+    yy = _d(y)
+    rc = lib(which).ox_eval_point_heat(C.byref(prob.cnet), C.byref(prob.cctl), t9, rho, _pd(yy), xext, aext, zext, diag, mult,
+                                       _pd(cs), _pd(dcs), _pd(yd), _pd(jac), _pd(ye), _pd(eos), _pd(t9d))
+    if rc:
+        raise RuntimeError('ox_eval_point_heat rc=%d' % rc)
+    return dict(csect=cs, dcsect=dcs, ydot=yd, jac=jac.reshape(m, m), ye=ye[0], eos=eos, t9dot=t9d[0])
+
+
+def step_be_point(prob, y, yt, tdel, t9, t9t, rhot, nh=2, which='strict', xext=0.0, aext=1.0, zext=0.0):
+    """One step_be call on an explicit state. Returns dict(inr, yt, t9t, ydot, t9dot, kcount)."""
+    ny = prob.nuc['ny']
+    yy = _d(y); ytt = _d(yt).copy(); t9tt = np.array([t9t], dtype=np.float64)
+    inr = np.zeros(1, dtype=np.int32); yd = np.zeros(ny); t9d = np.zeros(1); kc = np.zeros(5, dtype=np.int32)
+    rc = lib(which).ox_step_be_point(C.byref(prob.cnet), C.byref(prob.cctl), _pd(yy), _pd(ytt), tdel, t9, _pd(t9tt), rhot, nh,
+                                     xext, aext, zext, _pi(inr), _pd(yd), _pd(t9d), _pi(kc))
+    if rc:
+        raise RuntimeError('ox_step_be_point rc=%d' % rc)
+    return dict(inr=int(inr[0]), yt=ytt, t9t=t9tt[0], ydot=yd, t9dot=t9d[0], kcount=kc)
 
 
 def dgetrf(a):

@@ -54,7 +54,7 @@ EXPORTS = ['xb_last_error', 'xb_version', 'xb_launch_count', 'xb_net_load', 'xb_
            'xb_net_int', 'xb_net_itable', 'xb_net_dtable', 'xb_read_thermo', 'xb_read_inab', 'xb_zone_start',
            'xb_ctx_create', 'xb_ctx_destroy', 'xb_cross_sect', 'xb_get_csect', 'xb_yderiv', 'xb_jacobian_build',
            'xb_get_jac', 'xb_set_jac', 'xb_jacobian_decomp', 'xb_get_indx', 'xb_jacobian_bksub',
-           'xb_jacobian_solve', 'xb_evolve', 'xb_zones_upload', 'xb_evolve_resident', 'xb_results_download',
+           'xb_jacobian_solve', 'xb_get_dcsect', 'xb_get_eos', 'xb_step_be', 'xb_evolve', 'xb_zones_upload', 'xb_evolve_resident', 'xb_results_download',
            'xb_phase_cycles', 'xb_last_copy_bytes', 'xb_launch_config', 'xb_measure_fp64_peak']
 
 
@@ -90,6 +90,10 @@ def lib():
         l.xb_get_indx.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_ip]
         l.xb_jacobian_bksub.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp]
         l.xb_jacobian_solve.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, c_ip]
+        l.xb_get_dcsect.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_dp]
+        l.xb_get_eos.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_dp, c_dp, c_dp, c_dp]
+        l.xb_step_be.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_ip,
+                                 c_dp, c_dp, c_ip]
         l.xb_evolve.argtypes = [C.c_void_p, C.POINTER(XbZones), C.POINTER(XbOut)]
         l.xb_zones_upload.argtypes = [C.c_void_p, C.POINTER(XbZones), C.c_int32]
         l.xb_evolve_resident.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -394,11 +398,40 @@ class Context:
         _chk(lib().xb_get_indx(self.h, 1, nz, _pi(out)))
         return out
 
-    def jacobian_bksub(self, yrhs, mask=None):
+    def jacobian_bksub(self, yrhs, mask=None, t9rhs=None):
+        """jacobian_bksub(kstep,yrhs,dy,t9rhs,dt9,mask_in) (xnet_jacobian_dense.F90:618).  Returns dy, or (dy, dt9)
+        when t9rhs is given (self-heating, msize = ny+1)."""
         yrhs = _d(yrhs); nz = yrhs.shape[0]; dy = np.zeros_like(yrhs)
         m = None if mask is None else _i(mask)
-        _chk(lib().xb_jacobian_bksub(self.h, 1, nz, _pi(m), _pd(yrhs), None, _pd(dy), None))
-        return dy
+        if t9rhs is None:
+            _chk(lib().xb_jacobian_bksub(self.h, 1, nz, _pi(m), _pd(yrhs), None, _pd(dy), None))
+            return dy
+        t9rhs = _d(t9rhs); dt9 = np.zeros(nz)
+        _chk(lib().xb_jacobian_bksub(self.h, 1, nz, _pi(m), _pd(yrhs), _pd(t9rhs), _pd(dy), _pd(dt9)))
+        return dy, dt9
+
+    def dcsect(self, nz):
+        out = np.zeros((nz, sum(self.net.nreac)))
+        _chk(lib().xb_get_dcsect(self.h, 1, nz, _pd(out)))
+        return out
+
+    def eos(self, nz):
+        """(cv, etae, detaedt9) of the last cross_sect and t9dot of the last yderiv, per zone."""
+        cv = np.zeros(nz); etae = np.zeros(nz); deta = np.zeros(nz); t9dot = np.zeros(nz)
+        _chk(lib().xb_get_eos(self.h, 1, nz, _pd(cv), _pd(etae), _pd(deta), _pd(t9dot)))
+        return cv, etae, deta, t9dot
+
+    def step_be(self, y, yt, tdel, t9, t9t, rhot, inr=None, nh=None, kstep=1):
+        """step_be(kstep,inr) (xnet_integrate_be.F90:233): one launch for the whole Newton loop.
+        Returns dict(inr, yt, t9t, ydot, t9dot, kcount[nz,5]); inputs are not modified."""
+        y = _d(y); nz = y.shape[0]
+        yt = _d(yt).copy(); t9t = _d(t9t).copy(); tdel = _d(tdel); t9 = _d(t9); rhot = _d(rhot)
+        inr = np.zeros(nz, np.int32) if inr is None else _i(inr).copy()
+        nhh = None if nh is None else _i(nh)
+        ydot = np.zeros_like(y); t9dot = np.zeros(nz); kc = np.zeros((nz, 5), np.int32)
+        _chk(lib().xb_step_be(self.h, 1, nz, kstep, _pi(inr), _pd(y), _pd(yt), _pd(tdel), _pd(t9), _pd(t9t), _pd(rhot),
+                              _pi(nhh), _pd(ydot), _pd(t9dot), _pi(kc)))
+        return dict(inr=inr, yt=yt, t9t=t9t, ydot=ydot, t9dot=t9dot, kcount=kc)
 
     # ---- fused evolve ----
     def full_net(self, zones, hist_cap=0, pinned=False):

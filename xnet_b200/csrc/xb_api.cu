@@ -75,7 +75,8 @@ struct xb_ctx {
   DevBuf<int> counter;
   // module-level per-zone state (HBM)
   DevBuf<double> m_yt, m_t9t, m_rhot, m_ext, m_yet, m_csect, m_qk, m_ydot, m_jac, m_rhs, m_diag, m_mult;
-  DevBuf<int> m_indx, m_info, m_mask;
+  DevBuf<double> m_dcsect, m_eos, m_t9dot, m_y, m_t9, m_tdel;
+  DevBuf<int> m_indx, m_info, m_mask, m_nh, m_inr, m_kcnt;
   // evolve: zones + outputs
   DevZones dz{};
   DevOut dout{};
@@ -135,7 +136,8 @@ static SmemOff smem_layout(int ny, int N, int ld, int npart, bool jac_in_smem, i
 
 // Kernel prologue: per-CTA global scratch pointers into the zone scalars, yt[ny] = 1 (the factor that
 // stands in for absent reactants in the term plans).
-static __device__ void zone_prologue(const DevScratch &scr, double *csect, double *qkffn, double *jacg) {
+static __device__ void zone_prologue(const DevScratch &scr, double *csect, double *qkffn, double *jacg,
+                                     double *dcsect = nullptr) {
   ZoneScalars *s = reinterpret_cast<ZoneScalars *>(xb_smem + c_net.lay.scal);
   if (threadIdx.x == 0) {
     double *g = scr.base + (size_t)blockIdx.x * scr.stride;
@@ -146,7 +148,7 @@ static __device__ void zone_prologue(const DevScratch &scr, double *csect, doubl
     s->g_jac = jacg ? jacg : g + scr.off_jac;
     s->rhs_in_jac = jacg ? 0 : 1;   // module kernels work on the caller's msize x msize array: no room for column N
     s->g_yo = g + scr.off_yo;
-    s->g_dcsect = g + scr.off_dcsect;
+    s->g_dcsect = dcsect ? dcsect : g + scr.off_dcsect;
     s->g_dlnrffn = g + scr.off_dlnrffn;
     reinterpret_cast<double *>(xb_smem + c_net.lay.yt)[c_net.ny] = 1.0;
   }
@@ -181,12 +183,15 @@ evolve_kernel(const __grid_constant__ DevZones zn, const __grid_constant__ DevOu
 // ------------------------------------------------------------------------------------------------
 // Module-level kernels (drop-ins for cross_sect / yderiv / jacobian_*): one CTA per zone of the
 // slice, state in HBM between calls as in the reference's OpenACC build.
-enum ModOp { OP_CSECT = 0, OP_YDERIV, OP_JBUILD, OP_DECOMP, OP_BKSUB };
+enum ModOp { OP_CSECT = 0, OP_YDERIV, OP_JBUILD, OP_DECOMP, OP_BKSUB, OP_STEPBE };
 struct ModArgs {
   int z0, nz;            // first zone (0-based) and count
   const int *mask;       // [nzevolve] or null
   double *yt, *t9t, *rhot, *ext, *yet, *csect, *qk, *ydot, *jac, *rhs, *diag, *mult;
+  double *dcsect, *eos, *t9dot;   // self-heating state: d csect/d T9 [nrtot], (cv, etae, detaedt9) [3], t9dot per zone
+  double *y, *t9, *tdel;          // step_be: abundances and temperature at the start of the step, step size
   int *indx, *info;
+  int *nh, *inr, *kcnt;           // step_be: trajectory length (nh > 1: rates are re-evaluated), inr in/out, counter increments [5]
 };
 
 template <bool STRICT, int OP>
@@ -198,12 +203,18 @@ module_kernel(const __grid_constant__ ModArgs ma, const __grid_constant__ DevScr
   const int tid = threadIdx.x, nt = blockDim.x, ny = net.ny, N = net.msize, ld = net.ld;
   double *gj = ma.jac + (size_t)iz * N * N;   // caller-visible layout: msize x msize, column-major
   // without the shared tile the kernels work in place on the caller-visible array (ld == N)
-  zone_prologue(scr, ma.csect + (size_t)iz * net.nrtot, ma.qk + (size_t)iz * (net.nffn + 1), gj);
+  if (OP == OP_STEPBE && ma.inr[iz] != 0) return;   // inr = -1: inactive zone (xnet_integrate_be.F90:254-256)
+  // step_be without the shared tile factors in the per-CTA scratch, where the right-hand side rides as column N
+  // (the interchanges of the factorisation must reach it); the other module ops work on the caller-visible array
+  zone_prologue(scr, ma.csect + (size_t)iz * net.nrtot, ma.qk + (size_t)iz * (net.nffn + 1),
+                (OP == OP_STEPBE && !net.tile) ? nullptr : gj, ma.dcsect + (size_t)iz * net.nrtot);
   ZoneMem zm = zone_mem();
   ZoneScalars *s = zm.s;
-  if (OP == OP_CSECT || OP == OP_YDERIV || OP == OP_JBUILD)
+  if (OP == OP_CSECT || OP == OP_YDERIV || OP == OP_JBUILD || OP == OP_STEPBE)
     for (int k = tid; k < ny; k += nt) zm.yt[k] = ma.yt[(size_t)iz * ny + k];
-  if (OP == OP_YDERIV || OP == OP_JBUILD)
+  if (OP == OP_STEPBE)
+    for (int k = tid; k < ny; k += nt) zm.y[k] = ma.y[(size_t)iz * ny + k];
+  if (OP == OP_YDERIV || OP == OP_JBUILD || OP == OP_STEPBE)   // step_be: constant conditions keep the previous rates
     for (int k = net.cs_lo + tid; k < net.nrtot; k += nt) zm.cs_sm[k - net.cs_lo] = zm.csect[k];
   for (int k = tid; k < N; k += nt) { zm.orig[k] = k; zm.pos[k] = k; }   // module level: LAPACK order, no prediction
   if (tid == 0) {
@@ -213,14 +224,35 @@ module_kernel(const __grid_constant__ ModArgs ma, const __grid_constant__ DevScr
     s->xext = ma.ext[3 * iz]; s->aext = ma.ext[3 * iz + 1]; s->zext = ma.ext[3 * iz + 2];
     s->zexti = (s->zext == 0.0) ? 0.0 : pow(s->zext, 1.58);
     s->rdt = ma.diag[iz]; s->mult = ma.mult[iz];
+    // EOS scalars of the last rate evaluation (cv feeds t9dot and the T9 row of the Jacobian when iheat > 0)
+    s->yet = ma.yet[iz]; s->cv = ma.eos[3 * iz]; s->etae = ma.eos[3 * iz + 1]; s->detaedt9 = ma.eos[3 * iz + 2];
+    s->t9dot = ma.t9dot[iz];
+    if (OP == OP_STEPBE) {
+      s->t9 = ma.t9[iz]; s->tdel = ma.tdel[iz]; s->nh = ma.nh[iz]; s->inr = 0; s->ye = s->yet;
+    }
   }
   __syncthreads();
   if (OP == OP_CSECT) {
     cross_sect_cta<STRICT>();
-    if (tid == 0) ma.yet[iz] = s->yet;
+    if (tid == 0) {
+      ma.yet[iz] = s->yet; ma.eos[3 * iz] = s->cv; ma.eos[3 * iz + 1] = s->etae; ma.eos[3 * iz + 2] = s->detaedt9;
+    }
   } else if (OP == OP_YDERIV) {
     yderiv_cta<STRICT>();
     for (int k = tid; k < ny; k += nt) ma.ydot[(size_t)iz * ny + k] = zm.ydot[k];
+    if (tid == 0) ma.t9dot[iz] = s->t9dot;
+  } else if (OP == OP_STEPBE) {
+    // the whole Newton loop of one BE step (xnet_integrate_be.F90:233-482) in one launch: no host sync per iteration
+    step_be_cta<STRICT>();
+    for (int k = tid; k < ny; k += nt) {
+      ma.yt[(size_t)iz * ny + k] = zm.yt[k];
+      ma.ydot[(size_t)iz * ny + k] = zm.ydot[k];
+    }
+    if (tid == 0) {
+      ma.inr[iz] = s->inr; ma.t9t[iz] = s->t9t; ma.t9dot[iz] = s->t9dot;
+      ma.yet[iz] = s->yet; ma.eos[3 * iz] = s->cv; ma.eos[3 * iz + 1] = s->etae; ma.eos[3 * iz + 2] = s->detaedt9;
+      for (int k = 0; k < 5; ++k) ma.kcnt[5 * iz + k] = s->ktot[k];
+    }
   } else if (OP == OP_JBUILD) {
     jacobian_build_cta<STRICT>();
     if (net.tile)
@@ -806,13 +838,14 @@ void xb_ctx_destroy(xb_ctx *c) {
   for (int k = 0; k < 4; ++k) { c->a[k].release(); c->mu[k].release(); for (int r = 0; r < 4; ++r) c->nn[k][r].release(); }
   c->scratch.release(); c->phase.release(); c->counter.release();
   DevBuf<double> *db[] = {&c->m_yt, &c->m_t9t, &c->m_rhot, &c->m_ext, &c->m_yet, &c->m_csect, &c->m_qk, &c->m_ydot, &c->m_jac,
-                          &c->m_rhs, &c->m_diag, &c->m_mult, &c->z_th, &c->z_t9h, &c->z_rhoh, &c->z_tstart, &c->z_tstop,
+                          &c->m_rhs, &c->m_diag, &c->m_mult, &c->m_dcsect, &c->m_eos, &c->m_t9dot, &c->m_y, &c->m_t9,
+                          &c->m_tdel, &c->z_th, &c->z_t9h, &c->z_rhoh, &c->z_tstart, &c->z_tstop,
                           &c->z_tdelstart, &c->z_t9start, &c->z_rhostart, &c->z_yestart, &c->z_ystart, &c->z_xext, &c->z_aext,
                           &c->z_zext, &c->z_rho_scale, &c->z_rs_t, &c->z_rs_tdel, &c->z_rs_t9, &c->z_rs_rho, &c->z_rs_t9o,
                           &c->z_rs_y, &c->z_rs_yo, &c->o_y, &c->o_t, &c->o_t9, &c->o_rho, &c->o_tdel, &c->o_ht, &c->o_ht9,
                           &c->o_hrho, &c->o_htdel, &c->o_hedot, &c->o_hsqnu, &c->o_hy};
   for (auto *b : db) b->release();
-  DevBuf<int> *ib[] = {&c->m_indx, &c->m_info, &c->m_mask, &c->z_nh, &c->z_off, &c->z_nstart, &c->z_zfix, &c->z_kstep0,
+  DevBuf<int> *ib[] = {&c->m_indx, &c->m_info, &c->m_mask, &c->m_nh, &c->m_inr, &c->m_kcnt, &c->z_nh, &c->z_off, &c->z_nstart, &c->z_zfix, &c->z_kstep0,
                        &c->o_kstep, &c->o_ktot, &c->o_status, &c->o_hn, &c->o_hkstep, &c->o_hkmon};
   for (auto *b : ib) b->release();
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -843,6 +876,17 @@ static int module_state(xb_ctx *c) {
   CUDA_TRY(cudaMemset(c->m_qk.p, 0, (size_t)nz * (c->dn.nffn + 1) * 8));
   CUDA_TRY(cudaMemset(c->m_t9t.p, 0, nz * 8)); CUDA_TRY(cudaMemset(c->m_rhot.p, 0, nz * 8));
   CUDA_TRY(cudaMemset(c->m_diag.p, 0, nz * 8)); CUDA_TRY(cudaMemset(c->m_mult.p, 0, nz * 8));
+  {
+    const size_t nrt = (size_t)std::max(c->dn.nrtot, 1);
+    CUDA_TRY(c->m_dcsect.resize((size_t)nz * nrt)); CUDA_TRY(c->m_eos.resize((size_t)3 * nz)); CUDA_TRY(c->m_t9dot.resize(nz));
+    CUDA_TRY(c->m_y.resize((size_t)nz * ny)); CUDA_TRY(c->m_t9.resize(nz)); CUDA_TRY(c->m_tdel.resize(nz));
+    CUDA_TRY(c->m_nh.resize(nz)); CUDA_TRY(c->m_inr.resize(nz)); CUDA_TRY(c->m_kcnt.resize((size_t)5 * nz));
+    CUDA_TRY(cudaMemset(c->m_dcsect.p, 0, (size_t)nz * nrt * 8)); CUDA_TRY(cudaMemset(c->m_eos.p, 0, (size_t)3 * nz * 8));
+    CUDA_TRY(cudaMemset(c->m_t9dot.p, 0, nz * 8)); CUDA_TRY(cudaMemset(c->m_yet.p, 0, nz * 8));
+    CUDA_TRY(cudaMemset(c->m_y.p, 0, (size_t)nz * ny * 8)); CUDA_TRY(cudaMemset(c->m_t9.p, 0, nz * 8));
+    CUDA_TRY(cudaMemset(c->m_tdel.p, 0, nz * 8)); CUDA_TRY(cudaMemset(c->m_nh.p, 0, nz * 4));
+    CUDA_TRY(cudaMemset(c->m_inr.p, 0, nz * 4)); CUDA_TRY(cudaMemset(c->m_kcnt.p, 0, (size_t)5 * nz * 4));
+  }
   std::vector<double> ext((size_t)3 * nz, 0.0);
   for (int i = 0; i < nz; ++i) ext[3 * i + 1] = 1.0;
   CUDA_TRY(c->m_ext.put(ext));
@@ -852,8 +896,6 @@ static int module_state(xb_ctx *c) {
 static int check_slice(xb_ctx *c, int zlo, int zhi) {
   if (!c) return fail(XB_ERR_ARG, "null context");
   if (zlo < 1 || zhi < zlo || zhi > c->nzevolve) return fail(XB_ERR_ARG, "zone slice outside 1..nzevolve");
-  if (c->ctl.iheat > 0)
-    return fail(XB_ERR_UNSUPPORTED, "module-level drop-ins are built for iheat = 0; self-heating runs through xb_evolve");
   CUDA_TRY(cudaSetDevice(c->device));
   return module_state(c);
 }
@@ -871,6 +913,8 @@ static int launch_module(xb_ctx *c, int zlo, int zhi, const int32_t *mask) {
   ma.yt = c->m_yt.p; ma.t9t = c->m_t9t.p; ma.rhot = c->m_rhot.p; ma.ext = c->m_ext.p; ma.yet = c->m_yet.p;
   ma.csect = c->m_csect.p; ma.qk = c->m_qk.p; ma.ydot = c->m_ydot.p; ma.jac = c->m_jac.p; ma.rhs = c->m_rhs.p;
   ma.diag = c->m_diag.p; ma.mult = c->m_mult.p; ma.indx = c->m_indx.p; ma.info = c->m_info.p;
+  ma.dcsect = c->m_dcsect.p; ma.eos = c->m_eos.p; ma.t9dot = c->m_t9dot.p; ma.y = c->m_y.p; ma.t9 = c->m_t9.p;
+  ma.tdel = c->m_tdel.p; ma.nh = c->m_nh.p; ma.inr = c->m_inr.p; ma.kcnt = c->m_kcnt.p;
   std::lock_guard<std::mutex> lock(g_launch_mu);
   { int rcb = bind_constants(c); if (rcb) return rcb; }
   if (c->ctl.arith) {
@@ -965,18 +1009,28 @@ int xb_jacobian_bksub(xb_ctx *c, int32_t zlo, int32_t zhi, const int32_t *mask, 
                       double *dy, double *dt9) {
   int rc = check_slice(c, zlo, zhi); if (rc) return rc;
   if (!yrhs || !dy) return fail(XB_ERR_ARG, "xb_jacobian_bksub: null argument");
-  (void)t9rhs; (void)dt9;  // msize == ny in this build (iheat = 0)
-  const int nz = zhi - zlo + 1, N = c->dn.msize, z0 = zlo - 1;
-  CUDA_TRY(cudaMemcpy(c->m_rhs.p + (size_t)z0 * N, yrhs, (size_t)nz * N * 8, cudaMemcpyHostToDevice));
-  rc = launch_module<OP_BKSUB>(c, zlo, zhi, mask); if (rc) return rc;
-  if (!mask) {
-    CUDA_TRY(cudaMemcpy(dy, c->m_rhs.p + (size_t)z0 * N, (size_t)nz * N * 8, cudaMemcpyDeviceToHost));
-  } else {  // masked-out zones keep the caller's dy (xnet_jacobian_dense.F90:700-708)
-    std::vector<double> tmp((size_t)nz * N);
-    CUDA_TRY(cudaMemcpy(tmp.data(), c->m_rhs.p + (size_t)z0 * N, tmp.size() * 8, cudaMemcpyDeviceToHost));
-    for (int i = 0; i < nz; ++i)
-      if (mask[i]) std::copy(tmp.begin() + (size_t)i * N, tmp.begin() + (size_t)(i + 1) * N, dy + (size_t)i * N);
+  const int nz = zhi - zlo + 1, N = c->dn.msize, ny = c->dn.ny, z0 = zlo - 1;
+  const bool heat = N > ny;   // msize = ny + 1: the T9 equation is row ny (xnet_jacobian_dense.F90:663-676)
+  if (heat && (!t9rhs || !dt9)) return fail(XB_ERR_ARG, "xb_jacobian_bksub: t9rhs/dt9 are required when iheat > 0");
+  if (!heat) {
+    CUDA_TRY(cudaMemcpy(c->m_rhs.p + (size_t)z0 * N, yrhs, (size_t)nz * N * 8, cudaMemcpyHostToDevice));
+  } else {
+    std::vector<double> r((size_t)nz * N);
+    for (int i = 0; i < nz; ++i) {
+      std::copy(yrhs + (size_t)i * ny, yrhs + (size_t)(i + 1) * ny, r.begin() + (size_t)i * N);
+      r[(size_t)i * N + ny] = t9rhs[i];
+    }
+    CUDA_TRY(cudaMemcpy(c->m_rhs.p + (size_t)z0 * N, r.data(), r.size() * 8, cudaMemcpyHostToDevice));
   }
+  rc = launch_module<OP_BKSUB>(c, zlo, zhi, mask); if (rc) return rc;
+  // masked-out zones keep the caller's dy/dt9 (xnet_jacobian_dense.F90:700-708)
+  std::vector<double> tmp((size_t)nz * N);
+  CUDA_TRY(cudaMemcpy(tmp.data(), c->m_rhs.p + (size_t)z0 * N, tmp.size() * 8, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < nz; ++i)
+    if (!mask || mask[i]) {
+      std::copy(tmp.begin() + (size_t)i * N, tmp.begin() + (size_t)i * N + ny, dy + (size_t)i * ny);
+      if (heat) dt9[i] = tmp[(size_t)i * N + ny];
+    }
   return XB_OK;
 }
 
@@ -985,6 +1039,72 @@ int xb_jacobian_solve(xb_ctx *c, int32_t zlo, int32_t zhi, const int32_t *mask, 
   int rc = xb_jacobian_decomp(c, zlo, zhi, mask, info);
   if (rc) return rc;
   return xb_jacobian_bksub(c, zlo, zhi, mask, yrhs, t9rhs, dy, dt9);
+}
+
+// Self-heating state of the module-level path: d csect / d T9 and the EOS scalars of the last xb_cross_sect,
+// t9dot of the last xb_yderiv (module variables dcsect*, cv, etae, detaedt9, t9dot of the reference).
+int xb_get_dcsect(xb_ctx *c, int32_t zlo, int32_t zhi, double *dcsect) {
+  int rc = check_slice(c, zlo, zhi); if (rc) return rc;
+  CUDA_TRY(cudaMemcpy(dcsect, c->m_dcsect.p + (size_t)(zlo - 1) * c->dn.nrtot, (size_t)(zhi - zlo + 1) * c->dn.nrtot * 8,
+                      cudaMemcpyDeviceToHost));
+  return XB_OK;
+}
+int xb_get_eos(xb_ctx *c, int32_t zlo, int32_t zhi, double *cv, double *etae, double *detaedt9, double *t9dot) {
+  int rc = check_slice(c, zlo, zhi); if (rc) return rc;
+  const int nz = zhi - zlo + 1, z0 = zlo - 1;
+  std::vector<double> e((size_t)3 * nz);
+  CUDA_TRY(cudaMemcpy(e.data(), c->m_eos.p + (size_t)3 * z0, e.size() * 8, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < nz; ++i) {
+    if (cv) cv[i] = e[3 * i];
+    if (etae) etae[i] = e[3 * i + 1];
+    if (detaedt9) detaedt9[i] = e[3 * i + 2];
+  }
+  if (t9dot) CUDA_TRY(cudaMemcpy(t9dot, c->m_t9dot.p + z0, nz * 8, cudaMemcpyDeviceToHost));
+  return XB_OK;
+}
+
+// step_be (xnet_integrate_be.F90:233-482): the whole Newton loop of one backward-Euler step for the zones of the
+// slice with inr == 0, in ONE launch (the reference syncs with the host once per iteration, :430).
+int xb_step_be(xb_ctx *c, int32_t zlo, int32_t zhi, int32_t kstep, int32_t *inr, const double *y, double *yt,
+               const double *tdel, const double *t9, double *t9t, const double *rhot, const int32_t *nh,
+               double *ydot, double *t9dot, int32_t *kcount) {
+  (void)kstep;   // diagnostics only in the reference
+  int rc = check_slice(c, zlo, zhi); if (rc) return rc;
+  if (!inr || !y || !yt || !tdel || !t9 || !t9t || !rhot) return fail(XB_ERR_ARG, "xb_step_be: null argument");
+  const int nz = zhi - zlo + 1, ny = c->dn.ny, z0 = zlo - 1;
+  for (int i = 0; i < nz; ++i)
+    if (inr[i] == 0 && !(tdel[i] != 0.0)) return fail(XB_ERR_ARG, "xb_step_be: tdel = 0 for an active zone");
+  std::vector<int> one(nz, 2);
+  CUDA_TRY(cudaMemcpy(c->m_y.p + (size_t)z0 * ny, y, (size_t)nz * ny * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->m_yt.p + (size_t)z0 * ny, yt, (size_t)nz * ny * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->m_tdel.p + z0, tdel, nz * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->m_t9.p + z0, t9, nz * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->m_t9t.p + z0, t9t, nz * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->m_rhot.p + z0, rhot, nz * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->m_nh.p + z0, nh ? nh : one.data(), nz * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->m_inr.p + z0, inr, nz * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemset(c->m_kcnt.p + (size_t)5 * z0, 0, (size_t)5 * nz * 4));
+  rc = launch_module<OP_STEPBE>(c, zlo, zhi, nullptr); if (rc) return rc;
+  std::vector<int> inr_out(nz);
+  CUDA_TRY(cudaMemcpy(inr_out.data(), c->m_inr.p + z0, nz * 4, cudaMemcpyDeviceToHost));
+  std::vector<double> ytn((size_t)nz * ny), t9n(nz), tmp;
+  CUDA_TRY(cudaMemcpy(ytn.data(), c->m_yt.p + (size_t)z0 * ny, ytn.size() * 8, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(t9n.data(), c->m_t9t.p + z0, nz * 8, cudaMemcpyDeviceToHost));
+  if (ydot) { tmp.resize((size_t)nz * ny); CUDA_TRY(cudaMemcpy(tmp.data(), c->m_ydot.p + (size_t)z0 * ny, tmp.size() * 8, cudaMemcpyDeviceToHost)); }
+  std::vector<double> t9d(nz);
+  CUDA_TRY(cudaMemcpy(t9d.data(), c->m_t9dot.p + z0, nz * 8, cudaMemcpyDeviceToHost));
+  std::vector<int> kc((size_t)5 * nz);
+  CUDA_TRY(cudaMemcpy(kc.data(), c->m_kcnt.p + (size_t)5 * z0, kc.size() * 4, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < nz; ++i) {
+    if (inr[i] != 0) continue;   // inactive zones keep the caller's state
+    std::copy(ytn.begin() + (size_t)i * ny, ytn.begin() + (size_t)(i + 1) * ny, yt + (size_t)i * ny);
+    t9t[i] = t9n[i];
+    if (ydot) std::copy(tmp.begin() + (size_t)i * ny, tmp.begin() + (size_t)(i + 1) * ny, ydot + (size_t)i * ny);
+    if (t9dot) t9dot[i] = t9d[i];
+    if (kcount) for (int k = 0; k < 5; ++k) kcount[5 * i + k] = kc[5 * i + k];
+    inr[i] = inr_out[i];
+  }
+  return XB_OK;
 }
 
 // ---- evolve ---------------------------------------------------------------------------------------
