@@ -146,6 +146,15 @@ int xb_jacobian_solve(xb_ctx *ctx, int32_t zlo, int32_t zhi, const int32_t *mask
 int xb_get_dcsect(xb_ctx *ctx, int32_t zlo, int32_t zhi, double *dcsect);
 int xb_get_eos(xb_ctx *ctx, int32_t zlo, int32_t zhi, double *cv, double *etae, double *detaedt9, double *t9dot);
 
+/* flux (source/xnet_flux.F90:67-150): net fluxes of the mflx matched forward/reverse reaction pairs
+ * (match_react, source/xnet_preprocess.F90:108-289; mflx, nflx, ifl_orig, ifl_term through xb_net_int/xb_net_itable)
+ * from the device-resident rates of the last xb_cross_sect / xb_step_be call and yt (NULL = the abundances already
+ * on the device).  flx(mflx,nz) host; masked-out zones keep the caller's values. */
+int xb_flux(xb_ctx *ctx, int32_t zlo, int32_t zhi, const int32_t *mask, const double *yt, double *flx);
+/* fused path: record flx in the per-step history (xb_out.hist_flx); call before xb_zones_upload.  xb_evolve switches
+ * it on by itself when out->hist_flx is set. */
+int xb_set_flux_output(xb_ctx *ctx, int32_t on);
+
 /* step_be (source/xnet_integrate_be.F90:233-482): the complete Newton-Raphson loop of ONE backward-Euler step in one
  * launch -- no host synchronisation per iteration (the reference has one, :430).  Module-variable interface of the
  * reference spelled out as arguments, all host arrays over the slice:
@@ -186,6 +195,8 @@ typedef struct {
   int32_t hist_cap;          /* 0 = no per-step history                                    */
   int32_t *hist_n, *hist_kstep, *hist_kmon;
   double *hist_t, *hist_t9, *hist_rho, *hist_tdel, *hist_edot, *hist_sqnu, *hist_y;
+  double *hist_flx;          /* [nzone][hist_cap][mflx] matched-pair fluxes of each record (flx of ts_output,
+                                source/xnet_output.F90:78-79); NULL = not wanted                          */
 } xb_out;
 
 /* host buffers in, host buffers out (H2D + kernel + D2H): the end-to-end call */
@@ -194,6 +205,22 @@ int xb_evolve(xb_ctx *ctx, const xb_zones *zones, xb_out *out);
 int xb_zones_upload(xb_ctx *ctx, const xb_zones *zones, int32_t hist_cap);
 int xb_evolve_resident(xb_ctx *ctx, float *kernel_ms);   /* runs on the uploaded zones */
 int xb_results_download(xb_ctx *ctx, xb_out *out);
+/* ---- ts_<zone> output (source/net.F90:281-301 header, source/xnet_output.F90:78-79 records) ---------------
+ * Fortran sequential-unformatted file exactly as the reference writes it (gfortran record markers), so the
+ * reference's tools (tools/python/read_ts_file.py, test/compare_ts.py) read it.  Strings are blank-padded to 80. */
+typedef struct {
+  const char *descript[3];   /* run description lines of the control file              */
+  const char *data_desc;     /* description line of the network data (net_desc)        */
+  const xb_ctl *ctl;         /* kstmx,kitmx,iweak0,iscrn,iconvc,changemx,tolm,tolc,yacc,ymin,tdel_maxmult,iheat,isolv */
+  const char *inab_file, *abund_desc, *thermo_file, *thermo_desc;
+  int32_t ny; const double *zz, *aa;
+  int32_t mflx; const int32_t *ifl_orig, *ifl_term;
+} xb_ts_header;
+/* nrec records: kstep, t, t9, rho, sqnu, tdel, edot, y(ny) [nrec][ny], flx(mflx) [nrec][mflx] (NULL = zeros) */
+int xb_ts_write(const char *path, const xb_ts_header *hdr, int32_t nrec, const int32_t *kstep, const double *t,
+                const double *t9, const double *rho, const double *sqnu, const double *tdel, const double *edot,
+                const double *y, const double *flx);
+
 /* per-phase cycle counters of the last resident run (sum over CTAs), 24 values:
  * rates,yderiv,jac,lu,bksub,other,total,zones, lu_panel,lu_swap_trsm,lu_gemm,pivoting-panel fallbacks,
  * then 12 fine-grained development timers */

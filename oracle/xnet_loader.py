@@ -606,9 +606,56 @@ def load_zone(inab_path, th_path, nuc, t9nse=8.0):
     return z
 
 
+def match_react(net):
+    """Reaction-pair matching: match_react + flux_search (xnet_preprocess.F90:55-289) and flux_init
+    (xnet_flux.F90:20-65).  Adds mflx, ifl1..ifl4 (signed, 1-based), nflx [mflx,8], iwflx, qflx, dcflx [mflx,2],
+    ifl_orig, ifl_term to `net`.  Independent of the product's C++ version: sets are looked up in a dict keyed by
+    the 8-tuple (first occurrence wins, which is what the reference's linear search returns)."""
+    sets = []; index = {}; iw_of = []; q_of = []
+    ifl = [np.zeros(net['nreac'][c], np.int32) for c in range(4)]
+    for j in range(1, NCHAP + 1):
+        nreact = NREACTANT[j - 1]; nnuc = NNUCR[j - 1]; c = nreact - 1
+        N = net['n%d' % nreact]; Q = net['q%d' % nreact]; IWK = net['iwk%d' % nreact]
+        for k in range(net['chap_la'][j - 1], net['chap_le'][j - 1] + 1):
+            if k < 1 or k > net['nreac'][c]:
+                continue
+            reac = [int(v) for v in N[k - 1, :nreact]]; prod = [int(v) for v in N[k - 1, nreact:nnuc]]
+            fwd = Q[k - 1] > 0.0
+            lhs, rhs = (reac, prod) if fwd else (prod, reac)
+            key = tuple(lhs + [0] * (4 - len(lhs)) + rhs + [0] * (4 - len(rhs)))
+            iw = int(IWK[k - 1])
+            m = index.get(key) if iw == 0 else None
+            if m is None:
+                sets.append(key); iw_of.append(iw); q_of.append(abs(float(Q[k - 1])))
+                m = len(sets)
+                # only non-weak lookups may hit it later, but a weak set can be found by a later non-weak reaction:
+                # the reference searches ALL existing sets, whatever their flag
+                index.setdefault(key, m)
+            ifl[c][k - 1] = m if fwd else -m
+    mflx = len(sets)
+    nflx = np.array(sets, np.int32).reshape(mflx, 8)
+    fact = {1: 1.0, 2: 0.5, 3: 1.0 / 6.0, 4: 1.0 / 24.0, 5: 0.25}
+    dc = np.ones((mflx, 2)); orig = np.zeros(mflx, np.int32); term = np.zeros(mflx, np.int32)
+    for m in range(mflx):
+        for side in (0, 1):
+            f = nflx[m, 4 * side:4 * side + 4]
+            cnt = 1 + sum(1 for s in (1, 2, 3) if f[s] != 0 and f[s] == f[s - 1])
+            if cnt == 3 and f[1] != f[2]:
+                cnt = 5
+            dc[m, side] = fact[cnt]
+            nz = int(np.count_nonzero(f))
+            (orig if side == 0 else term)[m] = f[nz - 1] if nz else 0
+    net.update(mflx=mflx, nflx=nflx, iwflx=np.array(iw_of, np.int32), qflx=np.array(q_of), dcflx=dc,
+               ifl_orig=orig, ifl_term=term)
+    for c in range(4):
+        net['ifl%d' % (c + 1)] = ifl[c]
+    return net
+
+
 def load_network(data_dir, iweak0=1):
     nuc = read_nuclear_data(data_dir)
     net = net_preprocess(data_dir, nuc)
+    match_react(net)
     ffn = read_ffn(data_dir, net['nffn'], iweak0)
     return nuc, net, ffn
 

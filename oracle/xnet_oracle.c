@@ -733,6 +733,25 @@ static void zone_reset_scratch(zone_t *z) {
   z->cv = z->etae = z->detaedt9 = 0.0; z->t9dot = 0.0;
 }
 
+static void flux(const zone_t *z, double *flx) {
+  /* xnet_flux.F90:104-131: flx(ifl) += dcflx(dir,ifl) * sign(csect * prod yt, ifl_n(i)), classes and reactions in order */
+  const ox_net *net = z->net; int c, i, m;
+  for (m = 0; m < net->mflx; m++) flx[m] = 0.0;
+  for (c = 0; c < 4; c++) {
+    for (i = 0; i < net->nr[c]; i++) {
+      const int *ni = net->ni[c] + (size_t)i * 6;
+      int f = net->ifl[c][i], ifl = f < 0 ? -f : f, idc = f < 0 ? 1 : 0;
+      double flt;
+      if (c == 0) flt = z->csect[0][i] * z->yt[ni[0] - 1];
+      else if (c == 1) flt = z->csect[1][i] * z->yt[ni[0] - 1] * z->yt[ni[1] - 1];
+      else if (c == 2) flt = z->csect[2][i] * ((z->yt[ni[0] - 1] * z->yt[ni[1] - 1]) * z->yt[ni[2] - 1]);
+      else flt = z->csect[3][i] * (((z->yt[ni[0] - 1] * z->yt[ni[1] - 1]) * z->yt[ni[2] - 1]) * z->yt[ni[3] - 1]);
+      if (ifl == 0) continue;
+      flx[ifl - 1] = flx[ifl - 1] + net->dcflx[2 * (ifl - 1) + idc] * (f < 0 ? -fabs(flt) : fabs(flt));
+    }
+  }
+}
+
 static void hist_put(const ox_out *out, int iz, int ny, int kstep, const zone_t *z, double edot, double sqnu) {
   int n;
   if (out->hist_cap <= 0) return;
@@ -743,6 +762,10 @@ static void hist_put(const ox_out *out, int iz, int ny, int kstep, const zone_t 
     out->hist_t[o] = z->t; out->hist_t9[o] = z->t9; out->hist_rho[o] = z->rho; out->hist_tdel[o] = z->tdel;
     out->hist_edot[o] = edot; out->hist_sqnu[o] = sqnu;
     memcpy(out->hist_y + o * ny, z->y, sizeof(double) * ny);
+    if (out->hist_flx && z->net->mflx > 0) {   /* ts_output: flux() for kstep > 0, zeros in the initial record */
+      double *f = out->hist_flx + o * (size_t)z->net->mflx;
+      if (kstep > 0) flux(z, f); else memset(f, 0, sizeof(double) * z->net->mflx);
+    }
   }
   out->hist_n[iz] = n + 1;
 }
@@ -875,6 +898,18 @@ int ox_eval_point_heat(const ox_net *net, const ox_ctl *ctl, double t9, double r
     memcpy(jac, z->jac, sizeof(double) * z->msize * z->msize);
     *ye_out = z->yet; eos[0] = z->cv; eos[1] = z->etae; eos[2] = z->detaedt9; *t9dot = z->t9dot;
   }
+  zone_free(z);
+  return rc_;
+}
+
+int ox_flux_point(const ox_net *net, const ox_ctl *ctl, double t9, double rho, const double *y,
+                  double xext, double aext, double zext, double *flx) {
+  zone_t *z = zone_new(net, ctl); int k, rc_;
+  zone_reset_scratch(z);
+  z->t9t = t9; z->rhot = rho; z->xext = xext; z->aext = aext; z->zext = zext; z->nh = 2;
+  for (k = 0; k < z->ny; k++) { z->yt[k] = y[k]; z->y[k] = y[k]; }
+  rc_ = cross_sect(z);
+  if (!rc_) flux(z, flx);
   zone_free(z);
   return rc_;
 }

@@ -27,6 +27,10 @@ typedef struct {
   const int *has_logft;   /* [nffn] */
   /* Helmholtz table (only when iscrn>0 or iheat>0), see ox_eos.c; NULL otherwise */
   const double *helm;     /* 13 planes [13][201][541] : f,fd,ft,fdd,ftt,fdt,fddt,fdtt,fddtt,ef,efd,eft,efdt */
+  /* reaction-pair (flux) matching, xnet_preprocess.F90:108-289 + xnet_flux.F90:20-65; mflx = 0: no flux output */
+  int mflx;
+  const int *ifl[4];      /* [nr] signed 1-based flux-set index (+ forward, - reverse)                  */
+  const double *dcflx;    /* [mflx][2] double-counting factor of the forward / reverse direction         */
 } ox_net;
 
 typedef struct {
@@ -69,6 +73,7 @@ typedef struct {
   int *hist_kmon;   /* [nzone][cap][2] */
   double *hist_t, *hist_t9, *hist_rho, *hist_tdel, *hist_edot, *hist_sqnu; /* [nzone][cap] */
   double *hist_y;   /* [nzone][cap][ny] */
+  double *hist_flx; /* [nzone][cap][mflx] reaction fluxes of the record (xnet_flux.F90:67-150); NULL = skip */
 } ox_out;
 
 /* full_net for all zones, OpenMP over zones (nthreads<=0: default).  Returns 0. */
@@ -90,6 +95,9 @@ int ox_eval_point_heat(const ox_net *net, const ox_ctl *ctl, double t9, double r
                        double xext, double aext, double zext, double diag, double mult,
                        double *csect, double *dcsect, double *ydot, double *jac, double *ye_out, double *eos,
                        double *t9dot);
+/* flux (xnet_flux.F90:67-150) of one state: cross_sect at (t9, rho, y), then the matched-pair fluxes flx[mflx] */
+int ox_flux_point(const ox_net *net, const ox_ctl *ctl, double t9, double rho, const double *y,
+                  double xext, double aext, double zext, double *flx);
 /* one step_be call (Newton loop of one backward-Euler step) on an explicit state */
 int ox_step_be_point(const ox_net *net, const ox_ctl *ctl, const double *y, double *yt, double tdel, double t9,
                      double *t9t, double rhot, int nh, double xext, double aext, double zext,

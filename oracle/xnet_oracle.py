@@ -25,7 +25,8 @@ class OxNet(C.Structure):
                 ('mex_n', C.c_double), ('mex_p', C.c_double),
                 ('g', c_dp), ('t9i', c_dp),
                 ('ffnsum', c_dp), ('ffnenu', c_dp), ('ffn_ec', c_dp), ('ffn_beta', c_dp),
-                ('ffn_qval', c_dp), ('has_logft', c_ip), ('helm', c_dp)]
+                ('ffn_qval', c_dp), ('has_logft', c_ip), ('helm', c_dp),
+                ('mflx', C.c_int), ('ifl', c_ip * 4), ('dcflx', c_dp)]
 
 
 class OxCtl(C.Structure):
@@ -48,7 +49,7 @@ class OxOut(C.Structure):
                 ('kstep', c_ip), ('ktot', c_ip), ('status', c_ip),
                 ('hist_cap', C.c_int), ('hist_n', c_ip), ('hist_kstep', c_ip), ('hist_kmon', c_ip),
                 ('hist_t', c_dp), ('hist_t9', c_dp), ('hist_rho', c_dp), ('hist_tdel', c_dp),
-                ('hist_edot', c_dp), ('hist_sqnu', c_dp), ('hist_y', c_dp)]
+                ('hist_edot', c_dp), ('hist_sqnu', c_dp), ('hist_y', c_dp), ('hist_flx', c_dp)]
 
 
 def build(force=False):
@@ -76,6 +77,8 @@ def lib(fast=False):
         l.ox_eval_point_heat.restype = C.c_int
         l.ox_eval_point_heat.argtypes = [C.POINTER(OxNet), C.POINTER(OxCtl)] + [C.c_double] * 2 + [c_dp] + \
             [C.c_double] * 5 + [c_dp] * 7
+        l.ox_flux_point.restype = C.c_int
+        l.ox_flux_point.argtypes = [C.POINTER(OxNet), C.POINTER(OxCtl)] + [C.c_double] * 2 + [c_dp] + [C.c_double] * 3 + [c_dp]
         l.ox_step_be_point.restype = C.c_int
         l.ox_step_be_point.argtypes = [C.POINTER(OxNet), C.POINTER(OxCtl), c_dp, c_dp, C.c_double, C.c_double, c_dp,
                                        C.c_double, C.c_int] + [C.c_double] * 3 + [c_ip, c_dp, c_dp, c_ip]
@@ -150,6 +153,11 @@ class Problem:
         n.has_logft = _pi(self._k(_i(ffn['has_logft'])))
         if self.helm is not None:
             n.helm = _pd(self._k(_d(self.helm)))
+        n.mflx = int(net.get('mflx', 0))
+        if n.mflx > 0:
+            for c in range(4):
+                n.ifl[c] = _pi(self._k(_i(net['ifl%d' % (c + 1)] if net['nreac'][c] else np.zeros(1))))
+            n.dcflx = _pd(self._k(_d(net['dcflx'])))
         self.cnet = n
 
     def _build_ctl(self):
@@ -171,8 +179,16 @@ class Problem:
             yestart=_d([f['yestart'] for f in fx]), ystart=_d(np.stack([f['ystart'] for f in fx])),
             xext=_d([f['xext'] for f in fx]), aext=_d([f['aext'] for f in fx]), zext=_d([f['zext'] for f in fx]))
 
+    def flux_point(self, t9, rho, y, which='strict', xext=0.0, aext=1.0, zext=0.0):
+        """flux (xnet_flux.F90:67-150) of one state after a rate evaluation at (t9, rho, y): flx[mflx]."""
+        flx = np.zeros(max(int(self.net['mflx']), 1)); yy = _d(y)
+        rc = lib(which).ox_flux_point(C.byref(self.cnet), C.byref(self.cctl), t9, rho, _pd(yy), xext, aext, zext, _pd(flx))
+        if rc:
+            raise RuntimeError('ox_flux_point rc=%d' % rc)
+        return flx[:int(self.net['mflx'])]
+
     def run(self, nzone=None, hist_cap=0, nthreads=0, rho_scale=None, fast=False, ctl_override=None,
-            restart=None, zfix=None):
+            restart=None, zfix=None, flux=False):
         fa = self.fix_arrays
         K = len(self.fixtures)
         nzone = nzone or K
@@ -216,6 +232,9 @@ class Problem:
             o.hist_n = _pi(res['hist_n']); o.hist_kstep = _pi(res['hist_kstep']); o.hist_kmon = _pi(res['hist_kmon'])
             for nm in ('hist_t', 'hist_t9', 'hist_rho', 'hist_tdel', 'hist_edot', 'hist_sqnu', 'hist_y'):
                 setattr(o, nm, _pd(res[nm]))
+            if flux and int(self.net.get('mflx', 0)) > 0:
+                res['hist_flx'] = np.zeros((nzone, hist_cap, int(self.net['mflx'])))
+                o.hist_flx = _pd(res['hist_flx'])
         rc = lib(fast).ox_full_net(C.byref(self.cnet), C.byref(cctl), C.byref(z), C.byref(o), nthreads)
         res['rc'] = rc
         return res

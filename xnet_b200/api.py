@@ -44,7 +44,13 @@ class XbOut(C.Structure):
                 ('kstep', c_ip), ('ktot', c_ip), ('status', c_ip),
                 ('hist_cap', C.c_int32), ('hist_n', c_ip), ('hist_kstep', c_ip), ('hist_kmon', c_ip),
                 ('hist_t', c_dp), ('hist_t9', c_dp), ('hist_rho', c_dp), ('hist_tdel', c_dp),
-                ('hist_edot', c_dp), ('hist_sqnu', c_dp), ('hist_y', c_dp)]
+                ('hist_edot', c_dp), ('hist_sqnu', c_dp), ('hist_y', c_dp), ('hist_flx', c_dp)]
+
+
+class XbTsHeader(C.Structure):
+    _fields_ = [('descript', C.c_char_p * 3), ('data_desc', C.c_char_p), ('ctl', C.POINTER(XbCtl)),
+                ('inab_file', C.c_char_p), ('abund_desc', C.c_char_p), ('thermo_file', C.c_char_p), ('thermo_desc', C.c_char_p),
+                ('ny', C.c_int32), ('zz', c_dp), ('aa', c_dp), ('mflx', C.c_int32), ('ifl_orig', c_ip), ('ifl_term', c_ip)]
 
 
 _lib = None
@@ -54,7 +60,7 @@ EXPORTS = ['xb_last_error', 'xb_version', 'xb_launch_count', 'xb_net_load', 'xb_
            'xb_net_int', 'xb_net_itable', 'xb_net_dtable', 'xb_read_thermo', 'xb_read_inab', 'xb_zone_start',
            'xb_ctx_create', 'xb_ctx_destroy', 'xb_cross_sect', 'xb_get_csect', 'xb_yderiv', 'xb_jacobian_build',
            'xb_get_jac', 'xb_set_jac', 'xb_jacobian_decomp', 'xb_get_indx', 'xb_jacobian_bksub',
-           'xb_jacobian_solve', 'xb_get_dcsect', 'xb_get_eos', 'xb_step_be', 'xb_evolve', 'xb_zones_upload', 'xb_evolve_resident', 'xb_results_download',
+           'xb_jacobian_solve', 'xb_get_dcsect', 'xb_get_eos', 'xb_flux', 'xb_set_flux_output', 'xb_step_be', 'xb_ts_write', 'xb_evolve', 'xb_zones_upload', 'xb_evolve_resident', 'xb_results_download',
            'xb_phase_cycles', 'xb_last_copy_bytes', 'xb_launch_config', 'xb_measure_fp64_peak']
 
 
@@ -94,6 +100,9 @@ def lib():
         l.xb_get_eos.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_dp, c_dp, c_dp, c_dp]
         l.xb_step_be.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_ip,
                                  c_dp, c_dp, c_ip]
+        l.xb_flux.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_ip, c_dp, c_dp]
+        l.xb_set_flux_output.argtypes = [C.c_void_p, C.c_int32]
+        l.xb_ts_write.argtypes = [C.c_char_p, C.POINTER(XbTsHeader), C.c_int32, c_ip] + [c_dp] * 8
         l.xb_evolve.argtypes = [C.c_void_p, C.POINTER(XbZones), C.POINTER(XbOut)]
         l.xb_zones_upload.argtypes = [C.c_void_p, C.POINTER(XbZones), C.c_int32]
         l.xb_evolve_resident.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -209,6 +218,7 @@ class Network:
         self.nreac = [self.int('nreac%d' % k) for k in (1, 2, 3, 4)]
         self.nan = [self.int('nan%d' % k) for k in (1, 2, 3, 4)]
         self.nffn = self.int('nffn'); self.nnnu = self.int('nnnu')
+        self.mflx = self.int('mflx')     # matched reaction pairs (match_react, xnet_preprocess.F90:108-289)
         self.helm_loaded = False
 
     def load_helm(self, path=None):
@@ -302,7 +312,7 @@ def build_zone_set(fixtures, nzone=None, zfix=None, rho_scale=None, restart=None
     return z
 
 
-def _alloc_out(nzone, ny, hist_cap, pinned=False):
+def _alloc_out(nzone, ny, hist_cap, pinned=False, mflx=0):
     def arr(shape, dt):
         if pinned:
             import torch
@@ -318,6 +328,8 @@ def _alloc_out(nzone, ny, hist_cap, pinned=False):
         for nm in ('hist_t', 'hist_t9', 'hist_rho', 'hist_tdel', 'hist_edot', 'hist_sqnu'):
             r[nm] = np.zeros((nzone, hist_cap))
         r['hist_y'] = np.zeros((nzone, hist_cap, ny))
+        if mflx > 0:
+            r['hist_flx'] = np.zeros((nzone, hist_cap, mflx))
     o = XbOut()
     o.hist_cap = hist_cap
     for nm, tp in XbOut._fields_:
@@ -434,14 +446,26 @@ class Context:
         return dict(inr=inr, yt=yt, t9t=t9t, ydot=ydot, t9dot=t9dot, kcount=kc)
 
     # ---- fused evolve ----
-    def full_net(self, zones, hist_cap=0, pinned=False):
-        """xb_evolve: host buffers in, host buffers out (H2D + kernel + D2H)."""
-        res, o = _alloc_out(zones.nzone, self.net.ny, hist_cap, pinned)
+    def full_net(self, zones, hist_cap=0, pinned=False, flux=False):
+        """xb_evolve: host buffers in, host buffers out (H2D + kernel + D2H).  flux=True adds hist_flx, the
+        matched-pair reaction fluxes of every ts record (xnet_flux.F90:67-150)."""
+        res, o = _alloc_out(zones.nzone, self.net.ny, hist_cap, pinned, self.net.mflx if flux else 0)
+        _chk(lib().xb_set_flux_output(self.h, 1 if flux else 0))
         _chk(lib().xb_evolve(self.h, C.byref(zones), C.byref(o)))
         return res
 
-    def upload(self, zones, hist_cap=0):
-        self._nzone = zones.nzone; self._hist_cap = hist_cap
+    def flux(self, yt=None, nz=None, mask=None):
+        """flux(mask_in) (xnet_flux.F90:67): fluxes [nz, mflx] from the device-resident rates and yt."""
+        if yt is not None:
+            yt = _d(yt); nz = yt.shape[0]
+        flx = np.zeros((nz, max(self.net.mflx, 1)))
+        m = None if mask is None else _i(mask)
+        _chk(lib().xb_flux(self.h, 1, nz, _pi(m), _pd(yt), _pd(flx)))
+        return flx[:, :self.net.mflx]
+
+    def upload(self, zones, hist_cap=0, flux=False):
+        self._nzone = zones.nzone; self._hist_cap = hist_cap; self._flux = flux
+        _chk(lib().xb_set_flux_output(self.h, 1 if flux else 0))
         _chk(lib().xb_zones_upload(self.h, C.byref(zones), hist_cap))
 
     def run_resident(self):
@@ -450,7 +474,7 @@ class Context:
         return ms.value
 
     def download(self, pinned=False):
-        res, o = _alloc_out(self._nzone, self.net.ny, self._hist_cap, pinned)
+        res, o = _alloc_out(self._nzone, self.net.ny, self._hist_cap, pinned, self.net.mflx if getattr(self, '_flux', False) else 0)
         _chk(lib().xb_results_download(self.h, C.byref(o)))
         return res
 

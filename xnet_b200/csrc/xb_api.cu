@@ -12,7 +12,9 @@
 
 #include "../../include/xnet_b200.h"
 #include "xb_host.h"
+#ifndef XB_MAX_THREADS
 #define XB_MAX_THREADS 256
+#endif
 #include "xb_zone.cuh"
 
 using namespace xb;
@@ -84,7 +86,10 @@ struct xb_ctx {
   DevBuf<int> z_nh, z_off, z_nstart, z_zfix, z_kstep0;
   DevBuf<double> z_th, z_t9h, z_rhoh, z_tstart, z_tstop, z_tdelstart, z_t9start, z_rhostart, z_yestart, z_ystart,
       z_xext, z_aext, z_zext, z_rho_scale, z_rs_t, z_rs_tdel, z_rs_t9, z_rs_rho, z_rs_t9o, z_rs_y, z_rs_yo;
-  DevBuf<double> o_y, o_t, o_t9, o_rho, o_tdel, o_ht, o_ht9, o_hrho, o_htdel, o_hedot, o_hsqnu, o_hy;
+  DevBuf<double> o_y, o_t, o_t9, o_rho, o_tdel, o_ht, o_ht9, o_hrho, o_htdel, o_hedot, o_hsqnu, o_hy, o_hflx;
+  DevBuf<int> fl_start, fl_k;
+  DevBuf<double> fl_dc, m_flx;
+  int want_flux = 0;
   DevBuf<int> o_kstep, o_ktot, o_status, o_hn, o_hkstep, o_hkmon;
   int64_t h2d = 0, d2h = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -183,12 +188,13 @@ evolve_kernel(const __grid_constant__ DevZones zn, const __grid_constant__ DevOu
 // ------------------------------------------------------------------------------------------------
 // Module-level kernels (drop-ins for cross_sect / yderiv / jacobian_*): one CTA per zone of the
 // slice, state in HBM between calls as in the reference's OpenACC build.
-enum ModOp { OP_CSECT = 0, OP_YDERIV, OP_JBUILD, OP_DECOMP, OP_BKSUB, OP_STEPBE };
+enum ModOp { OP_CSECT = 0, OP_YDERIV, OP_JBUILD, OP_DECOMP, OP_BKSUB, OP_STEPBE, OP_FLUX };
 struct ModArgs {
   int z0, nz;            // first zone (0-based) and count
   const int *mask;       // [nzevolve] or null
   double *yt, *t9t, *rhot, *ext, *yet, *csect, *qk, *ydot, *jac, *rhs, *diag, *mult;
   double *dcsect, *eos, *t9dot;   // self-heating state: d csect/d T9 [nrtot], (cv, etae, detaedt9) [3], t9dot per zone
+  double *flx;                    // flux: [mflx] per zone
   double *y, *t9, *tdel;          // step_be: abundances and temperature at the start of the step, step size
   int *indx, *info;
   int *nh, *inr, *kcnt;           // step_be: trajectory length (nh > 1: rates are re-evaluated), inr in/out, counter increments [5]
@@ -210,11 +216,11 @@ module_kernel(const __grid_constant__ ModArgs ma, const __grid_constant__ DevScr
                 (OP == OP_STEPBE && !net.tile) ? nullptr : gj, ma.dcsect + (size_t)iz * net.nrtot);
   ZoneMem zm = zone_mem();
   ZoneScalars *s = zm.s;
-  if (OP == OP_CSECT || OP == OP_YDERIV || OP == OP_JBUILD || OP == OP_STEPBE)
+  if (OP == OP_CSECT || OP == OP_YDERIV || OP == OP_JBUILD || OP == OP_STEPBE || OP == OP_FLUX)
     for (int k = tid; k < ny; k += nt) zm.yt[k] = ma.yt[(size_t)iz * ny + k];
   if (OP == OP_STEPBE)
     for (int k = tid; k < ny; k += nt) zm.y[k] = ma.y[(size_t)iz * ny + k];
-  if (OP == OP_YDERIV || OP == OP_JBUILD || OP == OP_STEPBE)   // step_be: constant conditions keep the previous rates
+  if (OP == OP_YDERIV || OP == OP_JBUILD || OP == OP_STEPBE || OP == OP_FLUX)   // step_be: constant conditions keep the previous rates
     for (int k = net.cs_lo + tid; k < net.nrtot; k += nt) zm.cs_sm[k - net.cs_lo] = zm.csect[k];
   for (int k = tid; k < N; k += nt) { zm.orig[k] = k; zm.pos[k] = k; }   // module level: LAPACK order, no prediction
   if (tid == 0) {
@@ -241,6 +247,8 @@ module_kernel(const __grid_constant__ ModArgs ma, const __grid_constant__ DevScr
     yderiv_cta<STRICT>();
     for (int k = tid; k < ny; k += nt) ma.ydot[(size_t)iz * ny + k] = zm.ydot[k];
     if (tid == 0) ma.t9dot[iz] = s->t9dot;
+  } else if (OP == OP_FLUX) {
+    flux_cta<STRICT>(zm, ma.flx + (size_t)iz * net.mflx);
   } else if (OP == OP_STEPBE) {
     // the whole Newton loop of one BE step (xnet_integrate_be.F90:233-482) in one launch: no host sync per iteration
     step_be_cta<STRICT>();
@@ -359,7 +367,7 @@ int xb_net_int(const xb_net *net, const char *what, int32_t *value) {
   if (!net || !what || !value) return fail(XB_ERR_ARG, "xb_net_int: null argument");
   const Network &h = net->h; std::string w(what);
   if (w == "ny") *value = h.ny; else if (w == "nffn") *value = h.nffn; else if (w == "nnnu") *value = h.nnnu;
-  else if (w == "izmax") *value = h.izmax;
+  else if (w == "izmax") *value = h.izmax; else if (w == "mflx") *value = h.mflx;
   else if (w.size() == 6 && w.compare(0, 5, "nreac") == 0 && w[5] >= '1' && w[5] <= '4') *value = h.nreac[w[5] - '1'];
   else if (w.size() == 4 && w.compare(0, 3, "nan") == 0 && w[3] >= '1' && w[3] <= '4') *value = h.nan[w[3] - '1'];
   else return fail(XB_ERR_ARG, "xb_net_int: unknown key " + w);
@@ -387,6 +395,10 @@ int xb_net_itable(const xb_net *net, const char *what, int32_t *out, int64_t cap
   if (w == "chap_la") return copy_out(h.chap_la, out, cap, n);
   if (w == "chap_le") return copy_out(h.chap_le, out, cap, n);
   if (w == "has_logft") return copy_out(h.has_logft, out, cap, n);
+  if (w == "nflx") return copy_out(h.nflx, out, cap, n);
+  if (w == "iwflx") return copy_out(h.iwflx, out, cap, n);
+  if (w == "ifl_orig") return copy_out(h.ifl_orig, out, cap, n);
+  if (w == "ifl_term") return copy_out(h.ifl_term, out, cap, n);
   if (w.size() >= 3) {
     const int c = w.back() - '1';
     std::string stem = w.substr(0, w.size() - 1);
@@ -396,6 +408,7 @@ int xb_net_itable(const xb_net *net, const char *what, int32_t *out, int64_t cap
       if (stem == "iwk") return copy_out(h.iwk[c], out, cap, n);
       if (stem == "irev") return copy_out(h.irev[c], out, cap, n);
       if (stem == "ires") return copy_out(h.ires[c], out, cap, n);
+      if (stem == "ifl") return copy_out(h.ifl[c], out, cap, n);
     }
   }
   return fail(XB_ERR_ARG, "xb_net_itable: unknown key " + w);
@@ -415,6 +428,8 @@ int xb_net_dtable(const xb_net *net, const char *what, double *out, int64_t cap,
   if (w == "ffn_ec") return copy_out(h.ffn_ec, out, cap, n);
   if (w == "ffn_beta") return copy_out(h.ffn_beta, out, cap, n);
   if (w == "ffn_qval") return copy_out(h.ffn_qval, out, cap, n);
+  if (w == "qflx") return copy_out(h.qflx, out, cap, n);
+  if (w == "dcflx") return copy_out(h.dcflx, out, cap, n);
   if (w == "mex_np") { std::vector<double> v{h.mex_n, h.mex_p}; return copy_out(v, out, cap, n); }
   if (w.size() >= 2) {
     const int c = w.back() - '1';
@@ -537,6 +552,32 @@ static int upload_network(xb_ctx *c) {
     if (fn1.empty()) { fn1.push_back(0); fif.push_back(0); }
     CUDA_TRY(c->ffr_n1.put(fn1)); CUDA_TRY(c->ffr_iffn.put(fif));
     d.ffr_n1 = c->ffr_n1.p; d.ffr_iffn = c->ffr_iffn.p;
+  }
+  {  // flux plan: per matched pair the contributing reactions in reaction order (xnet_flux.F90:104-131)
+    d.mflx = h.mflx;
+    std::vector<int> start(h.mflx + 1, 0), kk; std::vector<double> dc;
+    if (h.mflx > 0) {
+      std::vector<std::vector<std::pair<int, double>>> by(h.mflx);
+      int off = 0;
+      for (int cc = 0; cc < 4; ++cc) {
+        for (int k = 0; k < h.nreac[cc]; ++k) {
+          const int f = h.ifl[cc][k];
+          if (f != 0) {
+            const int m = std::abs(f) - 1;
+            by[m].push_back({off + k, f > 0 ? h.dcflx[(size_t)2 * m] : -h.dcflx[(size_t)2 * m + 1]});
+          }
+        }
+        off += h.nreac[cc];
+      }
+      for (int m = 0; m < h.mflx; ++m) {
+        start[m] = (int)kk.size();
+        for (auto &e : by[m]) { kk.push_back(e.first); dc.push_back(e.second); }
+      }
+      start[h.mflx] = (int)kk.size();
+    }
+    if (kk.empty()) { kk.push_back(0); dc.push_back(0.0); }
+    CUDA_TRY(c->fl_start.put(start)); CUDA_TRY(c->fl_k.put(kk)); CUDA_TRY(c->fl_dc.put(dc));
+    d.fl_start = c->fl_start.p; d.fl_k = c->fl_k.p; d.fl_dc = c->fl_dc.p;
   }
   CUDA_TRY(c->aa.put(h.aa)); CUDA_TRY(c->zz.put(h.zz)); CUDA_TRY(c->mex.put(h.mex)); CUDA_TRY(c->be.put(h.be));
   CUDA_TRY(c->g.put(h.g)); CUDA_TRY(c->t9i.put(h.t9i));
@@ -843,11 +884,13 @@ void xb_ctx_destroy(xb_ctx *c) {
                           &c->z_tdelstart, &c->z_t9start, &c->z_rhostart, &c->z_yestart, &c->z_ystart, &c->z_xext, &c->z_aext,
                           &c->z_zext, &c->z_rho_scale, &c->z_rs_t, &c->z_rs_tdel, &c->z_rs_t9, &c->z_rs_rho, &c->z_rs_t9o,
                           &c->z_rs_y, &c->z_rs_yo, &c->o_y, &c->o_t, &c->o_t9, &c->o_rho, &c->o_tdel, &c->o_ht, &c->o_ht9,
-                          &c->o_hrho, &c->o_htdel, &c->o_hedot, &c->o_hsqnu, &c->o_hy};
+                          &c->o_hrho, &c->o_htdel, &c->o_hedot, &c->o_hsqnu, &c->o_hy,
+                          &c->o_hflx, &c->fl_dc, &c->m_flx};
   for (auto *b : db) b->release();
   DevBuf<int> *ib[] = {&c->m_indx, &c->m_info, &c->m_mask, &c->m_nh, &c->m_inr, &c->m_kcnt, &c->z_nh, &c->z_off, &c->z_nstart, &c->z_zfix, &c->z_kstep0,
                        &c->o_kstep, &c->o_ktot, &c->o_status, &c->o_hn, &c->o_hkstep, &c->o_hkmon};
   for (auto *b : ib) b->release();
+  c->fl_start.release(); c->fl_k.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   delete c;
@@ -914,7 +957,7 @@ static int launch_module(xb_ctx *c, int zlo, int zhi, const int32_t *mask) {
   ma.csect = c->m_csect.p; ma.qk = c->m_qk.p; ma.ydot = c->m_ydot.p; ma.jac = c->m_jac.p; ma.rhs = c->m_rhs.p;
   ma.diag = c->m_diag.p; ma.mult = c->m_mult.p; ma.indx = c->m_indx.p; ma.info = c->m_info.p;
   ma.dcsect = c->m_dcsect.p; ma.eos = c->m_eos.p; ma.t9dot = c->m_t9dot.p; ma.y = c->m_y.p; ma.t9 = c->m_t9.p;
-  ma.tdel = c->m_tdel.p; ma.nh = c->m_nh.p; ma.inr = c->m_inr.p; ma.kcnt = c->m_kcnt.p;
+  ma.tdel = c->m_tdel.p; ma.nh = c->m_nh.p; ma.inr = c->m_inr.p; ma.kcnt = c->m_kcnt.p; ma.flx = c->m_flx.p;
   std::lock_guard<std::mutex> lock(g_launch_mu);
   { int rcb = bind_constants(c); if (rcb) return rcb; }
   if (c->ctl.arith) {
@@ -1063,6 +1106,28 @@ int xb_get_eos(xb_ctx *c, int32_t zlo, int32_t zhi, double *cv, double *etae, do
   return XB_OK;
 }
 
+// flux (xnet_flux.F90:67-150): matched-pair reaction fluxes from the device-resident rates of the last xb_cross_sect /
+// xb_step_be call and the abundances yt; flx(mflx,nz) on the host.  Masked-out zones keep the caller's values.
+int xb_flux(xb_ctx *c, int32_t zlo, int32_t zhi, const int32_t *mask, const double *yt, double *flx) {
+  int rc = check_slice(c, zlo, zhi); if (rc) return rc;
+  if (!flx) return fail(XB_ERR_ARG, "xb_flux: null output");
+  const int nz = zhi - zlo + 1, ny = c->dn.ny, z0 = zlo - 1, mflx = c->dn.mflx;
+  if (mflx <= 0) return XB_OK;
+  CUDA_TRY(c->m_flx.resize((size_t)c->nzevolve * mflx));
+  if (yt) CUDA_TRY(cudaMemcpy(c->m_yt.p + (size_t)z0 * ny, yt, (size_t)nz * ny * 8, cudaMemcpyHostToDevice));
+  rc = launch_module<OP_FLUX>(c, zlo, zhi, mask); if (rc) return rc;
+  std::vector<double> tmp((size_t)nz * mflx);
+  CUDA_TRY(cudaMemcpy(tmp.data(), c->m_flx.p + (size_t)z0 * mflx, tmp.size() * 8, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < nz; ++i)
+    if (!mask || mask[i]) std::copy(tmp.begin() + (size_t)i * mflx, tmp.begin() + (size_t)(i + 1) * mflx, flx + (size_t)i * mflx);
+  return XB_OK;
+}
+int xb_set_flux_output(xb_ctx *c, int32_t on) {
+  if (!c) return fail(XB_ERR_ARG, "null context");
+  c->want_flux = on ? 1 : 0;
+  return XB_OK;
+}
+
 // step_be (xnet_integrate_be.F90:233-482): the whole Newton loop of one backward-Euler step for the zones of the
 // slice with inr == 0, in ONE launch (the reference syncs with the host once per iteration, :430).
 int xb_step_be(xb_ctx *c, int32_t zlo, int32_t zhi, int32_t kstep, int32_t *inr, const double *y, double *yt,
@@ -1164,6 +1229,10 @@ int xb_zones_upload(xb_ctx *c, const xb_zones *z, int32_t hist_cap) {
     CUDA_TRY(c->o_hedot.resize(hn)); CUDA_TRY(c->o_hsqnu.resize(hn)); CUDA_TRY(c->o_hy.resize(hn * ny));
     o.hist_n = c->o_hn.p; o.hist_kstep = c->o_hkstep.p; o.hist_kmon = c->o_hkmon.p; o.hist_t = c->o_ht.p; o.hist_t9 = c->o_ht9.p;
     o.hist_rho = c->o_hrho.p; o.hist_tdel = c->o_htdel.p; o.hist_edot = c->o_hedot.p; o.hist_sqnu = c->o_hsqnu.p; o.hist_y = c->o_hy.p;
+    if (c->want_flux && c->dn.mflx > 0) {
+      CUDA_TRY(c->o_hflx.resize(hn * (size_t)c->dn.mflx));
+      o.hist_flx = c->o_hflx.p;
+    }
   }
   return XB_OK;
 }
@@ -1213,12 +1282,17 @@ int xb_results_download(xb_ctx *c, xb_out *out) {
     GET(out->hist_t, c->o_ht, hn); GET(out->hist_t9, c->o_ht9, hn); GET(out->hist_rho, c->o_hrho, hn);
     GET(out->hist_tdel, c->o_htdel, hn); GET(out->hist_edot, c->o_hedot, hn); GET(out->hist_sqnu, c->o_hsqnu, hn);
     GET(out->hist_y, c->o_hy, hn * ny);
+    if (out->hist_flx) {
+      if (!c->dout.hist_flx) return fail(XB_ERR_ARG, "flux history was not recorded (xb_set_flux_output before the upload)");
+      GET(out->hist_flx, c->o_hflx, hn * (size_t)c->dn.mflx);
+    }
   }
   return XB_OK;
 }
 
 int xb_evolve(xb_ctx *c, const xb_zones *zones, xb_out *out) {
   if (!out) return fail(XB_ERR_ARG, "xb_evolve: null output");
+  if (c && out->hist_flx) c->want_flux = 1;
   int rc = xb_zones_upload(c, zones, out->hist_cap); if (rc) return rc;
   rc = xb_evolve_resident(c, nullptr); if (rc) return rc;
   return xb_results_download(c, out);

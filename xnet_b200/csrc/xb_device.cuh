@@ -65,6 +65,11 @@ struct DevNet {
   const double *sc_zw, *sc_zi;    // [nrtot] reaction charge parameters zeta_w, zeta_i (0 for one-reactant reactions)
   const int2 *sc_iz;         // [nrtot] x = iz1 | iz2<<8 | iz3<<16 | iz4<<24, y = composite charge
   int nzs;                   // entries of the per-charge strong-screening table
+  // matched-pair fluxes (xnet_flux.F90:67-150): set m sums entries [fl_start[m], fl_start[m+1]) in reaction order
+  int mflx;
+  const int *fl_start;       // [mflx+1]
+  const int *fl_k;           // [nrtot] reaction index (concatenated csect order)
+  const double *fl_dc;       // [nrtot] signed double-counting factor: +dcflx(1,m) forward, -dcflx(2,m) reverse
 };
 
 struct DevCtl {
@@ -89,6 +94,7 @@ struct DevOut {
   int hist_cap;
   int *hist_n, *hist_kstep, *hist_kmon;
   double *hist_t, *hist_t9, *hist_rho, *hist_tdel, *hist_edot, *hist_sqnu, *hist_y;
+  double *hist_flx;          // [nzone][cap][mflx] or null
 };
 
 // per-CTA scratch in global memory (L2 resident)

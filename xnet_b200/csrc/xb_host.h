@@ -31,6 +31,14 @@ struct Network {
   std::vector<int32_t> la, le;                // [4][ny] class-major
   std::vector<int32_t> mu[4];                 // [nan]
   std::vector<double> a[4];                   // [nan]
+  // reaction-pair ("flux") matching of match_react (xnet_preprocess.F90:108-289) and flux_init (xnet_flux.F90:20-65)
+  int mflx = 0;
+  std::vector<int32_t> ifl[4];                // [nreac] signed 1-based flux index: + forward (Q > 0), - reverse
+  std::vector<int32_t> nflx;                  // [mflx][8] reactants (slots 0-3) and products (4-7), 1-based, 0 = blank
+  std::vector<int32_t> iwflx;                 // [mflx] weak flag of the pair
+  std::vector<double> qflx;                   // [mflx] |Q|
+  std::vector<double> dcflx;                  // [mflx][2] double-counting factors (forward, reverse)
+  std::vector<int32_t> ifl_orig, ifl_term;    // [mflx] originating / terminating species (1-based)
   // FFN tables [nffn][143]
   std::vector<double> ffnsum, ffnenu, ffn_ec, ffn_beta, ffn_qval;
   std::vector<int32_t> has_logft;
@@ -40,6 +48,8 @@ struct Network {
 
 // throws std::runtime_error on malformed input
 void load_network(const std::string &data_dir, int iweak0, Network &net);
+// fills mflx, ifl, nflx, iwflx, qflx, dcflx, ifl_orig, ifl_term from chap_la/chap_le, ni, q, iwk
+void match_react(Network &net);
 int index_from_name(const Network &net, const std::string &name);
 void load_helm_table(const std::string &path, Network &net);
 

@@ -314,6 +314,62 @@ void preprocess_reactions(const std::string &dir, Network &net) {
     if (net.iwk[0][k] == 2 || net.iwk[0][k] == 3) net.iffn[k] = (int32_t)std::lrint(net.rc[0][(size_t)k * 7]);
 }
 
+}  // namespace (anonymous)
+
+// match_react (xnet_preprocess.F90:108-289) with flux_search (:55-106): every reaction is assigned to a flux set
+// keyed by its (reactants | products) written in the exoergic direction; non-weak reactions share the set of their
+// reverse, weak reactions (iwk != 0) always open a new one.  Then flux_init (xnet_flux.F90:20-65): double-counting
+// factors and the originating / terminating species of each set.
+void match_react(Network &net) {
+  net.mflx = 0; net.nflx.clear(); net.iwflx.clear(); net.qflx.clear();
+  for (int c = 0; c < 4; ++c) net.ifl[c].assign(net.nreac[c], 0);
+  if (net.chap_la.size() != (size_t)kNChap) return;   // networks built from arrays carry no chapter extents
+  for (int j = 0; j < kNChap; ++j) {
+    const int nreact = kNreactant[j], nnuc = kNnucr[j], nprod = nnuc - nreact, c = nreact - 1;
+    for (int k = net.chap_la[j]; k <= net.chap_le[j]; ++k) {
+      if (k < 1 || k > net.nreac[c]) continue;
+      const int32_t *n = &net.ni[c][(size_t)(k - 1) * 6];
+      const double q = net.q[c][k - 1];
+      const int iw = net.iwk[c][k - 1];
+      int32_t t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const bool fwd = q > 0.0;
+      if (fwd) {
+        for (int s = 0; s < nreact; ++s) t[s] = n[s];
+        for (int s = 0; s < nprod; ++s) t[4 + s] = n[nreact + s];
+      } else {
+        for (int s = 0; s < nprod; ++s) t[s] = n[nreact + s];
+        for (int s = 0; s < nreact; ++s) t[4 + s] = n[s];
+      }
+      int found = 0;
+      if (iw == 0)
+        for (int m = 0; m < net.mflx; ++m)
+          if (std::equal(t, t + 8, &net.nflx[(size_t)m * 8])) { found = m + 1; break; }
+      if (!found) {
+        net.nflx.insert(net.nflx.end(), t, t + 8);
+        net.qflx.push_back(std::fabs(q));
+        net.iwflx.push_back(iw);
+        found = ++net.mflx;
+      }
+      net.ifl[c][k - 1] = fwd ? found : -found;
+    }
+  }
+  const double fact[5] = {1.0, 1.0 / 2.0, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 4.0};
+  net.dcflx.assign((size_t)2 * net.mflx, 1.0); net.ifl_orig.assign(net.mflx, 0); net.ifl_term.assign(net.mflx, 0);
+  for (int m = 0; m < net.mflx; ++m) {
+    const int32_t *f = &net.nflx[(size_t)m * 8];
+    int cf = 1, cr = 1, nf = 0, nr = 0;
+    for (int s = 1; s < 4; ++s) if (f[s] != 0 && f[s] == f[s - 1]) ++cf;
+    for (int s = 5; s < 8; ++s) if (f[s] != 0 && f[s] == f[s - 1]) ++cr;
+    if (cf == 3 && f[1] != f[2]) cf = 5;
+    if (cr == 3 && f[5] != f[6]) cr = 5;
+    net.dcflx[(size_t)2 * m] = fact[cf - 1]; net.dcflx[(size_t)2 * m + 1] = fact[cr - 1];
+    for (int s = 0; s < 4; ++s) { if (f[s] != 0) ++nf; if (f[4 + s] != 0) ++nr; }
+    net.ifl_orig[m] = nf ? f[nf - 1] : 0;
+    net.ifl_term[m] = nr ? f[4 + nr - 1] : 0;
+  }
+}
+
+namespace {
 void read_ffn(const std::string &dir, int iweak0, Network &net) {
   const int nf = std::max(net.nffn, 1);
   net.ffnsum.assign((size_t)nf * kNGrid, 0.0); net.ffnenu.assign((size_t)nf * kNGrid, 0.0);
@@ -376,6 +432,7 @@ void load_network(const std::string &data_dir, int iweak0, Network &net) {
   read_nuclear(data_dir, net);
   preprocess_reactions(data_dir, net);
   read_ffn(data_dir, iweak0, net);
+  match_react(net);
 }
 
 void read_thermo_file(const std::string &path, Thermo &th) {

@@ -1096,13 +1096,46 @@ __device__ __forceinline__ void enudot_cta(const ZoneMem &zm, const double *y, d
   }
 }
 
+// flux (xnet_flux.F90:104-131): one thread per matched reaction pair; the pair's reactions are summed in reaction
+// order (classes 1..4, index ascending), each term dcflx * sign(csect * prod yt, ifl) with the reference's products.
+// Rates are those of the last cross_sect call, abundances zm.yt (= the accepted y when called from ts_output).
+template <bool STRICT>
+__device__ __forceinline__ void flux_cta(const ZoneMem &zm, double *__restrict__ flx) {
+  using A = Ar<STRICT>;
+  const DevNet &net = c_net;
+  const double *yt = zm.yt;
+  for (int m = threadIdx.x; m < net.mflx; m += blockDim.x) {
+    double acc = 0.0;
+    for (int e = net.fl_start[m]; e < net.fl_start[m + 1]; ++e) {
+      const int k = net.fl_k[e];
+      const int *ni = net.ni + (size_t)k * 6;
+      const double cs = cs_fetch(zm.csect, zm.cs_sm, net.cs_lo, (unsigned)k);
+      double flt;
+      if (k < net.roff[1]) flt = A::mul(cs, yt[ni[0] - 1]);
+      else if (k < net.roff[2]) flt = A::mul(A::mul(cs, yt[ni[0] - 1]), yt[ni[1] - 1]);
+      else if (k < net.roff[3]) flt = A::mul(cs, A::mul(A::mul(yt[ni[0] - 1], yt[ni[1] - 1]), yt[ni[2] - 1]));
+      else flt = A::mul(cs, A::mul(A::mul(A::mul(yt[ni[0] - 1], yt[ni[1] - 1]), yt[ni[2] - 1]), yt[ni[3] - 1]));
+      const double dc = net.fl_dc[e];
+      // dcflx * sign(flt, ifl): the magnitude of the term, signed by the direction of the reaction
+      acc = A::add(acc, A::mul(fabs(dc), dc < 0.0 ? -fabs(flt) : fabs(flt)));
+    }
+    flx[m] = acc;
+  }
+}
+
+template <bool STRICT>
 __device__ inline void hist_put(const DevOut &out, int iz, int ny, int kstep, const ZoneMem &zm) {
-  // all threads call; record = one ts_output record (xnet_output.F90:78-79 without the flux block)
+  // all threads call; record = one ts_output record (xnet_output.F90:78-79), flux block when requested
   if (out.hist_cap <= 0) return;
   const int n = out.hist_n[iz];
   if (n < out.hist_cap) {
     const size_t o = (size_t)iz * out.hist_cap + n;
     for (int k = threadIdx.x; k < ny; k += blockDim.x) out.hist_y[o * ny + k] = zm.y[k];
+    if (out.hist_flx && c_net.mflx > 0) {   // ts_output: flux() for kstep > 0, zeros in the initial record
+      double *f = out.hist_flx + o * (size_t)c_net.mflx;
+      if (kstep > 0) flux_cta<STRICT>(zm, f);
+      else for (int m = threadIdx.x; m < c_net.mflx; m += blockDim.x) f[m] = 0.0;
+    }
     if (threadIdx.x == 0) {
       const ZoneScalars *s = zm.s;
       out.hist_kstep[o] = kstep; out.hist_kmon[2 * o] = s->kmon[0]; out.hist_kmon[2 * o + 1] = s->kmon[1];
@@ -1170,7 +1203,7 @@ __device__ __forceinline__ void full_net_cta(const DevZones &zn, const DevOut &o
   benuc_cta<STRICT>(zm, zm.y, &s->enm);
   if (tid == 0) s->enold = restart ? s->enm : 0.0;
   __syncthreads();
-  if (!restart) hist_put(out, iz, ny, 0, zm);
+  if (!restart) hist_put<STRICT>(out, iz, ny, 0, zm);
   int mykstep = 0;
   bool lzsolve = true;
   for (int kstep = kstep0 + 1; kstep <= kstep0 + ctl.kstmx; ++kstep) {
@@ -1189,7 +1222,7 @@ __device__ __forceinline__ void full_net_cta(const DevZones &zn, const DevOut &o
       enudot_cta<STRICT>(zm, zm.yt, &s->sqnu);
       if (tid == 0) s->edot = -A::div(A::sub(s->enm, s->enold), s->tdel);
       __syncthreads();
-      hist_put(out, iz, ny, kstep, zm);
+      hist_put<STRICT>(out, iz, ny, kstep, zm);
     }
     if (!lzsolve) break;
   }
