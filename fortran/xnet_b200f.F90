@@ -64,6 +64,23 @@ Module xnet_b200f
     Integer(C_INT) Function xb_jacobian_solve(ctx,zlo,zhi,mask,yrhs,t9rhs,dy,dt9,info) Bind(C,name="xb_jacobian_solve")
       Import ; Type(C_PTR), Value :: ctx, mask, yrhs, t9rhs, dy, dt9, info ; Integer(C_INT32_T), Value :: zlo, zhi
     End Function
+    ! self-heating state mirrors (dcsect*, cv/etae/detaedt9, t9dot)
+    Integer(C_INT) Function xb_get_dcsect(ctx,zlo,zhi,dcsect) Bind(C,name="xb_get_dcsect")
+      Import ; Type(C_PTR), Value :: ctx, dcsect ; Integer(C_INT32_T), Value :: zlo, zhi
+    End Function
+    Integer(C_INT) Function xb_get_eos(ctx,zlo,zhi,cv,etae,detaedt9,t9dot) Bind(C,name="xb_get_eos")
+      Import ; Type(C_PTR), Value :: ctx, cv, etae, detaedt9, t9dot ; Integer(C_INT32_T), Value :: zlo, zhi
+    End Function
+    ! flux (xnet_flux.F90:67) from the device-resident rates
+    Integer(C_INT) Function xb_flux(ctx,zlo,zhi,mask,yt,flx) Bind(C,name="xb_flux")
+      Import ; Type(C_PTR), Value :: ctx, mask, yt, flx ; Integer(C_INT32_T), Value :: zlo, zhi
+    End Function
+    ! step_be (xnet_integrate_be.F90:233): the whole Newton loop in one launch
+    Integer(C_INT) Function xb_step_be(ctx,zlo,zhi,kstep,inr,y,yt,tdel,t9,t9t,rhot,nh,ydot,t9dot,kcount) &
+        & Bind(C,name="xb_step_be")
+      Import ; Type(C_PTR), Value :: ctx, inr, y, yt, tdel, t9, t9t, rhot, nh, ydot, t9dot, kcount
+      Integer(C_INT32_T), Value :: zlo, zhi, kstep
+    End Function
     Integer(C_INT) Function xb_evolve(ctx,zones,out) Bind(C,name="xb_evolve")
       Import ; Type(C_PTR), Value :: ctx, zones, out
     End Function

@@ -157,4 +157,33 @@ Contains
       & c_loc(yrhs),c_loc(t9rhs),c_loc(dy),c_loc(dt9),c_loc(info(zb_lo))),'xb_jacobian_solve')
   End Subroutine jacobian_solve
 
+  ! -------------------------------------------------------------------------------------------------
+  ! Optional fused drop-ins: same argument lists as the reference procedures they stand in for.
+  ! step_be_b200 replaces step_be (xnet_integrate_be.F90:233-482): point the call in solve_be
+  ! (xnet_integrate_be.F90:98) at it to run the whole Newton loop in one launch.
+  Subroutine step_be_b200(kstep,inr)
+    Use nuclear_data, Only: ny
+    Use xnet_abundances, Only: y, yt, ydot
+    Use xnet_conditions, Only: t9, t9t, rhot, tdel, nh, t9dot
+    Use xnet_controls, Only: zb_lo, zb_hi, ktot
+    Integer, Intent(in) :: kstep
+    Integer, Target, Intent(inout) :: inr(zb_lo:zb_hi)
+    Integer(C_INT), Target :: kc(5,zb_lo:zb_hi)
+    Call xb_check(xb_step_be(xb_ctx,int(zb_lo,C_INT),int(zb_hi,C_INT),int(kstep,C_INT),c_loc(inr), &
+      & c_loc(y(1,zb_lo)),c_loc(yt(1,zb_lo)),c_loc(tdel(zb_lo)),c_loc(t9(zb_lo)),c_loc(t9t(zb_lo)),c_loc(rhot(zb_lo)), &
+      & c_loc(nh(zb_lo)),c_loc(ydot(1,zb_lo)),c_loc(t9dot(zb_lo)),c_loc(kc)),'xb_step_be')
+    ktot(3:5,zb_lo:zb_hi) = ktot(3:5,zb_lo:zb_hi) + kc(3:5,:)   ! Jacobian builds, yderiv and cross_sect calls
+  End Subroutine step_be_b200
+
+  ! flux_b200 replaces the summation loop of flux (xnet_flux.F90:104-131); flx_int is accumulated by the caller
+  Subroutine flux_b200(flx,mask_in)
+    Use xnet_abundances, Only: yt
+    Use xnet_controls, Only: zb_lo, zb_hi
+    Real(dp), Target, Intent(inout) :: flx(:,:)
+    Logical, Optional, Intent(in) :: mask_in(zb_lo:zb_hi)
+    Integer(C_INT), Target :: m(zb_lo:zb_hi)
+    Call xb_check(xb_flux(xb_ctx,int(zb_lo,C_INT),int(zb_hi,C_INT),mask_ptr(mask_in,m),c_loc(yt(1,zb_lo)),c_loc(flx)), &
+      & 'xb_flux')
+  End Subroutine flux_b200
+
 End Module xnet_jacobian
