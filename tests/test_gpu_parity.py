@@ -185,7 +185,17 @@ def test_module_chain(gpu_problem, oracle_problem, name, arith):
             scale = np.abs(oj).max()
             assert np.abs(ydot[z] - oyd).max() <= 1e-11 * max(np.abs(oyd).max(), 1e-300) + 1e-12 * scale * np.abs(y[z]).max()
             assert np.abs(jac[z] - oj).max() <= 1e-11 * scale
-            assert np.array_equal(piv[z], opiv)
+            # fast arithmetic accepts the diagonal by threshold pivoting (tau = 0.25, xb_lu.cuh PivTau), so ipiv may differ
+            # from DGETRF's: check that it is a valid interchange sequence and that P L U reproduces the matrix
+            assert (piv[z] >= np.arange(1, ny + 1)).all() and (piv[z] <= ny).all()
+            f = lu[z].T; Lm = np.tril(f, -1) + np.eye(ny); Um = np.triu(f)
+            pa = oj.T.copy()
+            for k in range(ny):
+                p = piv[z][k] - 1
+                if p != k:
+                    pa[[k, p]] = pa[[p, k]]
+            assert np.abs(Lm).max() <= 4.0 * (1 + 1e-12)                 # multipliers bounded by 1/tau
+            assert np.abs(Lm @ Um - pa).max() <= 1e-10 * np.abs(pa).max()
             a = oj.T
             assert np.abs(a @ dy[z] - oyd).max() <= 1e-9 * (np.abs(a).max() * np.abs(dy[z]).max() + np.abs(oyd).max())
     ctx.close()
