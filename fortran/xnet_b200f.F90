@@ -21,6 +21,10 @@ Module xnet_b200f
     Real(C_DOUBLE) :: mex_n, mex_p
     Type(C_PTR) :: g, t9i, ffnsum, ffnenu
     Type(C_PTR) :: ffn_ec = C_NULL_PTR, ffn_beta = C_NULL_PTR, ffn_qval = C_NULL_PTR, has_logft = C_NULL_PTR
+    ! reaction pairs of Module xnet_match (mflx = 0: no flux output); dcflx may stay NULL
+    Integer(C_INT32_T) :: mflx = 0
+    Type(C_PTR) :: ifl(4) = C_NULL_PTR
+    Type(C_PTR) :: nflx = C_NULL_PTR, iwflx = C_NULL_PTR, qflx = C_NULL_PTR, dcflx = C_NULL_PTR
   End Type xb_net_arrays
 
   ! struct xb_ctl (include/xnet_b200.h:71-77)

@@ -40,6 +40,7 @@ Contains
     Use nuclear_data, Only: ny, aa, zz, mex, be, mex_n, mex_p, g, t9i
     Use reaction_data
     Use xnet_ffn, Only: ffnsum, ffnenu
+    Use xnet_match, Only: mflx, nflx, iwflx, qflx, ifl1, ifl2, ifl3, ifl4
     Use xnet_controls
     Implicit None
     Character(*), Intent(in) :: data_dir
@@ -66,6 +67,10 @@ Contains
     arr%mex_n = mex_n ; arr%mex_p = mex_p
     arr%g = c_loc(g) ; arr%t9i = c_loc(t9i)
     arr%ffnsum = c_loc(ffnsum) ; arr%ffnenu = c_loc(ffnenu)
+    ! reaction pairs (read_match_data, xnet_match.F90:230-257, runs before read_jacobian_data in net.F90)
+    arr%mflx = mflx
+    arr%ifl = [ c_loc(ifl1), c_loc(ifl2), c_loc(ifl3), c_loc(ifl4) ]
+    arr%nflx = c_loc(nflx) ; arr%iwflx = c_loc(iwflx) ; arr%qflx = c_loc(qflx)
     Call xb_check(xb_net_from_arrays(c_loc(arr),xb_net),'xb_net_from_arrays')
 
     ctl%iweak0 = iweak0 ; ctl%iscrn = iscrn ; ctl%iheat = iheat ; ctl%isolv = isolv

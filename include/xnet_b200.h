@@ -67,6 +67,13 @@ typedef struct {
   const double *t9i;         /* t9i(24)                                              */
   const double *ffnsum, *ffnenu; /* (nffn,143) Fortran order: rate index fastest     */
   const double *ffn_ec, *ffn_beta, *ffn_qval; const int32_t *has_logft; /* may be NULL */
+  /* optional reaction-pair matching of Module xnet_match (source/xnet_match.F90): mflx = 0 / NULL = no flux output.
+   * ifl_n(nreac_n) signed 1-based pair index, nflx(8,mflx), iwflx(mflx), qflx(mflx) (may be NULL); the double-counting
+   * factors dcflx(2,mflx) of xnet_flux may be NULL: they are then formed as flux_init does (xnet_flux.F90:36-50). */
+  int32_t mflx;
+  const int32_t *ifl[4];
+  const int32_t *nflx, *iwflx;
+  const double *qflx, *dcflx;
 } xb_net_arrays;
 
 /* Controls (xnet_controls.F90:20-62) */

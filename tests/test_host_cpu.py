@@ -107,3 +107,39 @@ def test_product_never_imports_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.cpp', '.h')):
                 s = open(os.path.join(dp, f)).read()
                 assert 'oracle' not in s.replace('the oracle', '').replace("oracle's", '').replace('CPU oracle', ''), f
+
+
+@pytest.mark.parametrize('net,iweak0', [('torch47', 1), ('SN160', 1), ('SN231_logft', 2)])
+def test_network_from_fortran_arrays_round_trip(built, net, iweak0):
+    """xb_net_from_arrays (the entry the Fortran shim uses: tables in Fortran layout, including the reaction pairs of
+    Module xnet_match) reproduces the network that xb_net_load builds from the files, table by table; the
+    double-counting factors are formed by the library when the caller passes none."""
+    import xnet_b200 as X
+    d = os.path.join(DATA, 'Data_' + net)
+    n = X.Network(d, iweak0)
+    ny = n.ny
+    t = dict(ny=ny, nffn=n.nffn, nnnu=n.nnnu, nreac=n.nreac, nan=n.nan, mex_n=n.dtable('mex_np')[0], mex_p=n.dtable('mex_np')[1])
+    for c in range(1, 5):
+        ni = n.itable('n%di' % c).reshape(-1, 6)
+        t['n%di' % c] = np.ascontiguousarray(ni[:, :5]) if c == 1 else ni          # n1i(5,nr1) in Fortran
+        for k in ('rc', 'iwk', 'irev', 'mu', 'a', 'ifl'):
+            t['%s%d' % (k, c)] = n.itable('%s%d' % (k, c)) if k in ('iwk', 'irev', 'mu', 'ifl') else n.dtable('%s%d' % (k, c))
+    t['la'] = n.itable('la').reshape(4, ny).T.copy(); t['le'] = n.itable('le').reshape(4, ny).T.copy()   # la(4,ny): class fastest
+    for k in ('aa', 'zz', 'mex', 'be', 'g', 't9i', 'ffn_qval'):
+        t[k] = n.dtable(k)
+    nf = max(n.nffn, 1)
+    for k in ('ffnsum', 'ffnenu', 'ffn_ec', 'ffn_beta'):
+        t[k] = n.dtable(k).reshape(nf, 143)[:n.nffn].T.copy()                        # (nffn,143): rate index fastest
+    t['has_logft'] = n.itable('has_logft')
+    t.update(mflx=n.mflx, nflx=n.itable('nflx'), iwflx=n.itable('iwflx'), qflx=n.dtable('qflx'))
+    m = X.Network.from_fortran_arrays(t, iweak0)
+    assert (m.ny, m.nreac, m.nan, m.nffn, m.mflx) == (n.ny, n.nreac, n.nan, n.nffn, n.mflx)
+    for key in ['la', 'le', 'iffn', 'has_logft', 'nflx', 'iwflx', 'ifl_orig', 'ifl_term'] + \
+            ['%s%d' % (k, c) for k in ('mu', 'iwk', 'irev', 'ifl') for c in range(1, 5)] + ['n%di' % c for c in range(1, 5)]:
+        assert np.array_equal(m.itable(key), n.itable(key)), key
+    for key in ['aa', 'zz', 'mex', 'be', 'g', 't9i', 'ffnsum', 'ffnenu', 'ffn_ec', 'ffn_beta', 'ffn_qval', 'qflx', 'dcflx'] + \
+            ['%s%d' % (k, c) for k in ('a', 'rc') for c in range(1, 5)]:
+        assert np.array_equal(m.dtable(key), n.dtable(key)), key
+    bad = dict(t); bad['ifl2'] = t['ifl2'].copy(); bad['ifl2'][0] = n.mflx + 5
+    with pytest.raises(Exception):
+        X.Network.from_fortran_arrays(bad, iweak0)

@@ -47,6 +47,17 @@ class XbOut(C.Structure):
                 ('hist_edot', c_dp), ('hist_sqnu', c_dp), ('hist_y', c_dp), ('hist_flx', c_dp)]
 
 
+class XbNetArrays(C.Structure):
+    """struct xb_net_arrays: the network tables as XNet's Fortran modules hold them (what the Fortran shim passes)."""
+    _fields_ = [('ny', C.c_int32), ('nffn', C.c_int32), ('nnnu', C.c_int32), ('nreac', C.c_int32 * 4), ('nan', C.c_int32 * 4),
+                ('rc', c_dp * 4), ('ni', c_ip * 4), ('ni_ld', C.c_int32 * 4), ('iwk', c_ip * 4), ('irev', c_ip * 4),
+                ('la', c_ip), ('le', c_ip), ('mu', c_ip * 4), ('a', c_dp * 4),
+                ('aa', c_dp), ('zz', c_dp), ('mex', c_dp), ('be', c_dp), ('mex_n', C.c_double), ('mex_p', C.c_double),
+                ('g', c_dp), ('t9i', c_dp), ('ffnsum', c_dp), ('ffnenu', c_dp),
+                ('ffn_ec', c_dp), ('ffn_beta', c_dp), ('ffn_qval', c_dp), ('has_logft', c_ip),
+                ('mflx', C.c_int32), ('ifl', c_ip * 4), ('nflx', c_ip), ('iwflx', c_ip), ('qflx', c_dp), ('dcflx', c_dp)]
+
+
 class XbTsHeader(C.Structure):
     _fields_ = [('descript', C.c_char_p * 3), ('data_desc', C.c_char_p), ('ctl', C.POINTER(XbCtl)),
                 ('inab_file', C.c_char_p), ('abund_desc', C.c_char_p), ('thermo_file', C.c_char_p), ('thermo_desc', C.c_char_p),
@@ -77,6 +88,7 @@ def lib():
         l.xb_launch_count.argtypes = [C.c_int]
         l.xb_net_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
         l.xb_net_free.argtypes = [C.c_void_p]
+        l.xb_net_from_arrays.argtypes = [C.POINTER(XbNetArrays), C.POINTER(C.c_void_p)]
         l.xb_net_load_helm.argtypes = [C.c_void_p, C.c_char_p]
         l.xb_net_int.argtypes = [C.c_void_p, C.c_char_p, c_ip]
         l.xb_net_itable.argtypes = [C.c_void_p, C.c_char_p, c_ip, C.c_int64, C.POINTER(C.c_int64)]
@@ -220,6 +232,57 @@ class Network:
         self.nffn = self.int('nffn'); self.nnnu = self.int('nnnu')
         self.mflx = self.int('mflx')     # matched reaction pairs (match_react, xnet_preprocess.F90:108-289)
         self.helm_loaded = False
+
+    @classmethod
+    def from_fortran_arrays(cls, t, iweak0=1):
+        """xb_net_from_arrays: builds a Network from tables laid out as the Fortran modules hold them (the path the
+        Fortran shim takes, fortran/xnet_jacobian_b200.F90 read_jacobian_data).  `t` maps the field names of
+        xb_net_arrays to arrays: rc1..4 (7,nr) column-major i.e. shape [nr,7]; n1i..n4i shape [nr,ld] with ld = 5,6,6,6;
+        la/le shape [ny,4]; ffn tables shape [143,nffn]; optional ifl1..4, nflx [mflx,8], iwflx, qflx, dcflx [mflx,2]."""
+        a = XbNetArrays(); keep = []
+
+        def pd(x):
+            v = _d(x); keep.append(v); return _pd(v)
+
+        def pi(x):
+            v = _i(x); keep.append(v); return _pi(v)
+        a.ny = int(t['ny']); a.nffn = int(t['nffn']); a.nnnu = int(t.get('nnnu', 0))
+        for c in range(4):
+            a.nreac[c] = int(t['nreac'][c]); a.nan[c] = int(t['nan'][c])
+            a.rc[c] = pd(t['rc%d' % (c + 1)]); ni = _i(t['n%di' % (c + 1)]); keep.append(ni)
+            a.ni[c] = _pi(ni); a.ni_ld[c] = ni.shape[1] if ni.ndim == 2 and ni.size else (5 if c == 0 else 6)
+            a.iwk[c] = pi(t['iwk%d' % (c + 1)]); a.irev[c] = pi(t['irev%d' % (c + 1)])
+            a.mu[c] = pi(t['mu%d' % (c + 1)]); a.a[c] = pd(t['a%d' % (c + 1)])
+        a.la = pi(t['la']); a.le = pi(t['le'])
+        for nm in ('aa', 'zz', 'mex', 'be', 'g', 't9i', 'ffnsum', 'ffnenu'):
+            setattr(a, nm, pd(t[nm]))
+        a.mex_n = float(t['mex_n']); a.mex_p = float(t['mex_p'])
+        for nm in ('ffn_ec', 'ffn_beta', 'ffn_qval'):
+            if t.get(nm) is not None:
+                setattr(a, nm, pd(t[nm]))
+        if t.get('has_logft') is not None:
+            a.has_logft = pi(t['has_logft'])
+        if t.get('mflx'):
+            a.mflx = int(t['mflx'])
+            for c in range(4):
+                a.ifl[c] = pi(t['ifl%d' % (c + 1)])
+            a.nflx = pi(t['nflx'])
+            if t.get('iwflx') is not None:
+                a.iwflx = pi(t['iwflx'])
+            if t.get('qflx') is not None:
+                a.qflx = pd(t['qflx'])
+            if t.get('dcflx') is not None:
+                a.dcflx = pd(t['dcflx'])
+        self = cls.__new__(cls)
+        self.h = C.c_void_p()
+        _chk(lib().xb_net_from_arrays(C.byref(a), C.byref(self.h)))
+        self.data_dir = t.get('data_dir', '')
+        self.ny = self.int('ny')
+        self.nreac = [self.int('nreac%d' % k) for k in (1, 2, 3, 4)]
+        self.nan = [self.int('nan%d' % k) for k in (1, 2, 3, 4)]
+        self.nffn = self.int('nffn'); self.nnnu = self.int('nnnu'); self.mflx = self.int('mflx')
+        self.helm_loaded = False
+        return self
 
     def load_helm(self, path=None):
         """Helmholtz table for screening / self-heating (XNet reads helm_table.dat from the run directory);

@@ -350,7 +350,30 @@ int xb_net_from_arrays(const xb_net_arrays *A, xb_net **net) {
       h.ffnsum[(size_t)k * kNGrid + j] = A->ffnsum[(size_t)j * h.nffn + k];
       h.ffnenu[(size_t)k * kNGrid + j] = A->ffnenu[(size_t)j * h.nffn + k];
     }
+  if (A->ffn_ec && A->ffn_beta)
+    for (int k = 0; k < h.nffn; ++k)
+      for (int j = 0; j < kNGrid; ++j) {
+        h.ffn_ec[(size_t)k * kNGrid + j] = A->ffn_ec[(size_t)j * h.nffn + k];
+        h.ffn_beta[(size_t)k * kNGrid + j] = A->ffn_beta[(size_t)j * h.nffn + k];
+      }
+  if (A->ffn_qval) std::copy(A->ffn_qval, A->ffn_qval + h.nffn, h.ffn_qval.begin());
+  if (A->has_logft) std::copy(A->has_logft, A->has_logft + h.nffn, h.has_logft.begin());
   h.chap_la.assign(kNChap, 0); h.chap_le.assign(kNChap, 0);
+  // reaction pairs as matched by the caller (Module xnet_match); without them there is no flux output
+  h.mflx = 0;
+  for (int c = 0; c < 4; ++c) h.ifl[c].assign(h.nreac[c], 0);
+  if (A->mflx > 0 && A->nflx && A->ifl[0] && A->ifl[1] && A->ifl[2] && A->ifl[3]) {
+    h.mflx = A->mflx;
+    for (int c = 0; c < 4; ++c) h.ifl[c].assign(A->ifl[c], A->ifl[c] + h.nreac[c]);
+    h.nflx.assign(A->nflx, A->nflx + (size_t)8 * h.mflx);
+    if (A->iwflx) h.iwflx.assign(A->iwflx, A->iwflx + h.mflx); else h.iwflx.assign(h.mflx, 0);
+    if (A->qflx) h.qflx.assign(A->qflx, A->qflx + h.mflx); else h.qflx.assign(h.mflx, 0.0);
+    for (int c = 0; c < 4; ++c)
+      for (int k = 0; k < h.nreac[c]; ++k)
+        if (std::abs(h.ifl[c][k]) > h.mflx) { delete n; return fail(XB_ERR_ARG, "xb_net_from_arrays: ifl refers to a pair beyond mflx"); }
+    flux_init(h);
+    if (A->dcflx) h.dcflx.assign(A->dcflx, A->dcflx + (size_t)2 * h.mflx);
+  }
   *net = n;
   return XB_OK;
 }

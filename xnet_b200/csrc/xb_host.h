@@ -50,6 +50,8 @@ struct Network {
 void load_network(const std::string &data_dir, int iweak0, Network &net);
 // fills mflx, ifl, nflx, iwflx, qflx, dcflx, ifl_orig, ifl_term from chap_la/chap_le, ni, q, iwk
 void match_react(Network &net);
+// dcflx, ifl_orig, ifl_term from mflx/nflx (second half of match_react; also used for networks built from arrays)
+void flux_init(Network &net);
 int index_from_name(const Network &net, const std::string &name);
 void load_helm_table(const std::string &path, Network &net);
 

@@ -353,6 +353,11 @@ void match_react(Network &net) {
       net.ifl[c][k - 1] = fwd ? found : -found;
     }
   }
+  flux_init(net);
+}
+
+// flux_init (xnet_flux.F90:20-65): double-counting factors and originating / terminating species of every pair
+void flux_init(Network &net) {
   const double fact[5] = {1.0, 1.0 / 2.0, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 4.0};
   net.dcflx.assign((size_t)2 * net.mflx, 1.0); net.ifl_orig.assign(net.mflx, 0); net.ifl_term.assign(net.mflx, 0);
   for (int m = 0; m < net.mflx; ++m) {
