@@ -78,3 +78,26 @@ def gpu_problem(built):
             cache[name] = (ctl, net, fx)
         return cache[name]
     return get
+
+
+def fortran_tables(n):
+    """The tables of a loaded Network re-laid out as XNet's Fortran modules hold them (what the Fortran shim hands to
+    xb_net_from_arrays): n1i(5,nr1), la/le(4,ny) class index fastest, FFN tables (nffn,143) rate index fastest, and the
+    reaction pairs of Module xnet_match."""
+    import numpy as np
+    ny = n.ny
+    t = dict(ny=ny, nffn=n.nffn, nnnu=n.nnnu, nreac=n.nreac, nan=n.nan, mex_n=n.dtable('mex_np')[0], mex_p=n.dtable('mex_np')[1])
+    for c in range(1, 5):
+        ni = n.itable('n%di' % c).reshape(-1, 6)
+        t['n%di' % c] = np.ascontiguousarray(ni[:, :5]) if c == 1 else ni
+        for k in ('rc', 'iwk', 'irev', 'mu', 'a', 'ifl'):
+            t['%s%d' % (k, c)] = n.itable('%s%d' % (k, c)) if k in ('iwk', 'irev', 'mu', 'ifl') else n.dtable('%s%d' % (k, c))
+    t['la'] = n.itable('la').reshape(4, ny).T.copy(); t['le'] = n.itable('le').reshape(4, ny).T.copy()
+    for k in ('aa', 'zz', 'mex', 'be', 'g', 't9i', 'ffn_qval'):
+        t[k] = n.dtable(k)
+    nf = max(n.nffn, 1)
+    for k in ('ffnsum', 'ffnenu', 'ffn_ec', 'ffn_beta'):
+        t[k] = n.dtable(k).reshape(nf, 143)[:n.nffn].T.copy()
+    t['has_logft'] = n.itable('has_logft')
+    t.update(mflx=n.mflx, nflx=n.itable('nflx'), iwflx=n.itable('iwflx'), qflx=n.dtable('qflx'))
+    return t

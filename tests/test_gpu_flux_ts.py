@@ -89,3 +89,24 @@ def test_fast_ts_file_against_oracle_prefix(gpu_problem, oracle_problem, tmp_pat
     r = X.compare_ts(a, b, rtol=1e-10, floor=1e-20)
     assert r['ok'], {k: v for k, v in r.items() if not hasattr(v, 'shape')}
     ctx.close()
+
+
+@pytest.mark.parametrize('name', ['torch47', 'sn160_heat'])
+def test_network_from_fortran_arrays_runs_identically(gpu_problem, name):
+    """The Fortran shim's route: a network handed over as module arrays (xb_net_from_arrays) gives bit-identical
+    trajectories and fluxes to the network the library loads from the files itself."""
+    import xnet_b200 as X
+    from conftest import fortran_tables
+    ctl, net, fx = gpu_problem(name)
+    net2 = X.Network.from_fortran_arrays(fortran_tables(net), ctl['iweak0'])
+    net2.data_dir = net.data_dir            # where load_helm looks for the Helmholtz table
+    out = []
+    for n in (net, net2):
+        ctx = X.Context(n, ctl, nzevolve=2, arith=1, kstmx=300)
+        out.append(ctx.full_net(X.build_zone_set(fx, nzone=2), hist_cap=320, flux=True))
+        ctx.close()
+    a, b = out
+    k = int(a['hist_n'][0])
+    assert k == int(b['hist_n'][0]) and 10 < k <= 301
+    for key in ('hist_y', 'hist_t', 'hist_tdel', 'hist_t9', 'hist_flx', 'hist_edot', 'y', 'ktot'):
+        assert np.array_equal(a[key], b[key]), key

@@ -116,22 +116,9 @@ def test_network_from_fortran_arrays_round_trip(built, net, iweak0):
     double-counting factors are formed by the library when the caller passes none."""
     import xnet_b200 as X
     d = os.path.join(DATA, 'Data_' + net)
+    from conftest import fortran_tables
     n = X.Network(d, iweak0)
-    ny = n.ny
-    t = dict(ny=ny, nffn=n.nffn, nnnu=n.nnnu, nreac=n.nreac, nan=n.nan, mex_n=n.dtable('mex_np')[0], mex_p=n.dtable('mex_np')[1])
-    for c in range(1, 5):
-        ni = n.itable('n%di' % c).reshape(-1, 6)
-        t['n%di' % c] = np.ascontiguousarray(ni[:, :5]) if c == 1 else ni          # n1i(5,nr1) in Fortran
-        for k in ('rc', 'iwk', 'irev', 'mu', 'a', 'ifl'):
-            t['%s%d' % (k, c)] = n.itable('%s%d' % (k, c)) if k in ('iwk', 'irev', 'mu', 'ifl') else n.dtable('%s%d' % (k, c))
-    t['la'] = n.itable('la').reshape(4, ny).T.copy(); t['le'] = n.itable('le').reshape(4, ny).T.copy()   # la(4,ny): class fastest
-    for k in ('aa', 'zz', 'mex', 'be', 'g', 't9i', 'ffn_qval'):
-        t[k] = n.dtable(k)
-    nf = max(n.nffn, 1)
-    for k in ('ffnsum', 'ffnenu', 'ffn_ec', 'ffn_beta'):
-        t[k] = n.dtable(k).reshape(nf, 143)[:n.nffn].T.copy()                        # (nffn,143): rate index fastest
-    t['has_logft'] = n.itable('has_logft')
-    t.update(mflx=n.mflx, nflx=n.itable('nflx'), iwflx=n.itable('iwflx'), qflx=n.dtable('qflx'))
+    t = fortran_tables(n)
     m = X.Network.from_fortran_arrays(t, iweak0)
     assert (m.ny, m.nreac, m.nan, m.nffn, m.mflx) == (n.ny, n.nreac, n.nan, n.nffn, n.mflx)
     for key in ['la', 'le', 'iffn', 'has_logft', 'nflx', 'iwflx', 'ifl_orig', 'ifl_term'] + \
