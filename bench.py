@@ -214,6 +214,8 @@ def main():
     res = ctx.download()
     ph = ctx.phase_cycles()
     newton = float(res['ktot'][:, 1].sum()); nlu = float(res['ktot'][:, 2].sum())
+    nts = float(res['ktot'][:, 0].sum())       # time-step attempts (ktot(1)); accepted steps = kstep per zone
+    nacc = float(np.where(res['status'] == -1, res['kstep'], args.kstmx or 0).sum())
     t_dev = sum(kern_ms) * 1e-3
     t_dev_max, newton_all = reduce_max_sum(world, t_dev, newton * args.steps)
     value = newton_all / t_dev_max
@@ -262,6 +264,9 @@ def main():
         'e2e': {'value': newton_e2e / t_e2e_max, 'unit': 'zone-Newton-iterations/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'steps': e2e_steps},
         'gpu_launches': int(launches),
+        # the same run in the reference's other counters (this rank's zones, device-resident timing)
+        'also': {'accepted_steps_per_s': nacc * args.steps / t_dev, 'timestep_attempts_per_s': nts * args.steps / t_dev,
+                 'lu_factorizations_per_s': nlu * args.steps / t_dev, 'scope': 'rank 0'},
         'clocks': sampler.summary(),
         'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak / 1e12, 'unit': 'TFLOP/s',
                      'frac': achieved / (fp64_peak / 1e12), 'traffic': None,
