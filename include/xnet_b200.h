@@ -228,6 +228,14 @@ int xb_ts_write(const char *path, const xb_ts_header *hdr, int32_t nrec, const i
                 const double *t9, const double *rho, const double *sqnu, const double *tdel, const double *edot,
                 const double *y, const double *flx);
 
+/* ASCII evolution file ev_<zone> (itsout >= 2): header of source/net.F90:311-314, one line per output step in the
+ * reference's format (i4,1es15.8,2es10.3,3es10.2,<nout>es9.2,2i2) (source/xnet_output.F90:72,83-85): kstep, t, t9, rho,
+ * edot, sqnu, tdel, the mass fractions xout[nrec][nout] = aa*y of the nout selected species (names5: nout x 5
+ * characters, as nname), kmon[nrec][2]. */
+int xb_ev_write(const char *path, int32_t nrec, const int32_t *kstep, const double *t, const double *t9,
+                const double *rho, const double *edot, const double *sqnu, const double *tdel, int32_t nout,
+                const char *names5, const double *xout, const int32_t *kmon);
+
 /* per-phase cycle counters of the last resident run (sum over CTAs), 24 values:
  * rates,yderiv,jac,lu,bksub,other,total,zones, lu_panel,lu_swap_trsm,lu_gemm,pivoting-panel fallbacks,
  * then 12 fine-grained development timers */

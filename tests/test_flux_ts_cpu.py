@@ -202,3 +202,35 @@ def test_compare_ts_semantics(built, oracle_problem, tmp_path):
     open(c, 'wb').write(raw[:-5])
     with pytest.raises(ValueError):
         X.read_ts(c)
+
+
+def test_ev_writer_fortran_formats(built, oracle_problem, tmp_path):
+    """xb_ev_write: header (a4,a15,5a10,<n>a9,a4) and lines (i4,1es15.8,2es10.3,3es10.2,<n>es9.2,2i2) as Fortran prints
+    them: ES editing with one digit before the point, three-digit exponents without the letter E, asterisks on
+    overflow of the field, right-justified character fields."""
+    import xnet_b200 as X
+    name = 'alpha'
+    op = oracle_problem(name)
+    ctl = X.read_controls(control_text(*PROBLEMS[name]))
+    net = X.Network(os.path.join(DATA, ctl['data_dir']), ctl['iweak0'])
+    h = op.run(nzone=1, hist_cap=4000)
+    # hand-made values in the first records to pin the formats
+    h['hist_kstep'][0, :4] = [0, 7, 9999, 10000]
+    h['hist_t'][0, 1] = 1.23456789123e-5; h['hist_t9'][0, 1] = 9.9996; h['hist_rho'][0, 1] = 1.0e7
+    h['hist_edot'][0, 1] = -3.14159e17; h['hist_sqnu'][0, 1] = 0.0; h['hist_tdel'][0, 1] = 2.5e-112
+    h['hist_kmon'][0, 1] = [1, 3]
+    h['hist_y'][0, 1, :] = 0.0
+    names = net.names()
+    i_he4 = [s.strip() for s in names].index('he4'); i_c12 = [s.strip() for s in names].index('c12')
+    h['hist_y'][0, 1, i_he4] = 0.25 / 4.0; h['hist_y'][0, 1, i_c12] = 1.0e-120 / 12.0
+    path = str(tmp_path / 'ev_1')
+    n = X.write_ev(path, net, h, zone=0, names=['he4', 'c12'])
+    lines = open(path).read().split('\n')
+    assert len(lines) == n + 2 and lines[-1] == ''
+    assert lines[0] == '  k ' + '          Time ' + '    T(GK) ' + ' Density '.rjust(10) + '    dE/dt ' + '     sqnu ' + ' Timestep ' + \
+        '      he4' + '      c12' + ' It '
+    assert lines[2] == '   7' + ' 1.23456789E-05' + ' 1.000E+01' + ' 1.000E+07' + ' -3.14E+17' + '  0.00E+00' + ' 2.50-112' .rjust(10) + \
+        ' 2.50E-01' + ' 1.00-120' .rjust(9) + ' 1' + ' 3'
+    assert lines[3].startswith('9999') and lines[4].startswith('****')
+    w = 4 + 15 + 2 * 10 + 3 * 10 + 2 * 9 + 2 * 2
+    assert all(len(ln) == w for ln in lines[:-1])

@@ -4,7 +4,7 @@ bench.py; the product is libxnet_b200.so.  There is no CPU fallback: without the
 a CUDA device every compute call raises."""
 from .api import (Network, Context, Controls, Fixture, XnetB200Error, lib, lib_path, read_controls,
                   build_zone_set, load_fixture)
-from .ts_io import write_ts, read_ts, compare_ts, name_ordered
+from .ts_io import write_ts, write_ev, read_ts, compare_ts, name_ordered
 
 __all__ = ['Network', 'Context', 'Controls', 'Fixture', 'XnetB200Error', 'lib', 'lib_path',
-           'read_controls', 'build_zone_set', 'load_fixture', 'write_ts', 'read_ts', 'compare_ts', 'name_ordered']
+           'read_controls', 'build_zone_set', 'load_fixture', 'write_ts', 'write_ev', 'read_ts', 'compare_ts', 'name_ordered']

@@ -71,7 +71,7 @@ EXPORTS = ['xb_last_error', 'xb_version', 'xb_launch_count', 'xb_net_load', 'xb_
            'xb_net_int', 'xb_net_itable', 'xb_net_dtable', 'xb_read_thermo', 'xb_read_inab', 'xb_zone_start',
            'xb_ctx_create', 'xb_ctx_destroy', 'xb_cross_sect', 'xb_get_csect', 'xb_yderiv', 'xb_jacobian_build',
            'xb_get_jac', 'xb_set_jac', 'xb_jacobian_decomp', 'xb_get_indx', 'xb_jacobian_bksub',
-           'xb_jacobian_solve', 'xb_get_dcsect', 'xb_get_eos', 'xb_flux', 'xb_set_flux_output', 'xb_step_be', 'xb_ts_write', 'xb_evolve', 'xb_zones_upload', 'xb_evolve_resident', 'xb_results_download',
+           'xb_jacobian_solve', 'xb_get_dcsect', 'xb_get_eos', 'xb_flux', 'xb_set_flux_output', 'xb_step_be', 'xb_ts_write', 'xb_ev_write', 'xb_evolve', 'xb_zones_upload', 'xb_evolve_resident', 'xb_results_download',
            'xb_phase_cycles', 'xb_last_copy_bytes', 'xb_launch_config', 'xb_measure_fp64_peak']
 
 
@@ -115,6 +115,7 @@ def lib():
         l.xb_flux.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_ip, c_dp, c_dp]
         l.xb_set_flux_output.argtypes = [C.c_void_p, C.c_int32]
         l.xb_ts_write.argtypes = [C.c_char_p, C.POINTER(XbTsHeader), C.c_int32, c_ip] + [c_dp] * 8
+        l.xb_ev_write.argtypes = [C.c_char_p, C.c_int32, c_ip] + [c_dp] * 6 + [C.c_int32, C.c_char_p, c_dp, c_ip]
         l.xb_evolve.argtypes = [C.c_void_p, C.POINTER(XbZones), C.POINTER(XbOut)]
         l.xb_zones_upload.argtypes = [C.c_void_p, C.POINTER(XbZones), C.c_int32]
         l.xb_evolve_resident.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -295,6 +296,14 @@ class Network:
             path = next((p for p in cands if os.path.exists(p)), cands[0])
         _chk(lib().xb_net_load_helm(self.h, path.encode()))
         self.helm_loaded = True
+
+    def names(self):
+        """Species names in network order (the sunet file of the data directory, xnet_data.F90:285-324)."""
+        with open(os.path.join(self.data_dir, 'sunet')) as f:
+            nm = [ln[:5] for ln in f.read().split('\n') if ln.strip()]
+        if len(nm) != self.ny:
+            raise XnetB200Error('sunet lists %d species, the network has %d' % (len(nm), self.ny))
+        return nm
 
     def int(self, what):
         v = C.c_int32()

@@ -73,3 +73,63 @@ extern "C" int xb_ts_write(const char *path, const xb_ts_header *h, int32_t nrec
   ok = (std::fclose(f) == 0) && ok;
   return ok ? XB_OK : XB_ERR_IO;
 }
+
+// ---- ASCII evolution file `ev_<zone>` (itsout >= 2) --------------------------------------------------------------
+// Header: net.F90:311-314, format (a4,a15,5a10,<n>a9,a4); one line per output step: xnet_output.F90:72 and :83-85,
+// format (i4,1es15.8,2es10.3,3es10.2,<n>es9.2,2i2) = kstep, t, t9, rho, edot, sqnu, tdel, aa*y of the nnucout selected
+// species, kmon(1:2).
+namespace {
+
+// Fortran ESw.d edit descriptor: one digit before the point, exponent E+ee, or +eee without the letter when it needs
+// three digits; right-justified in w columns, asterisks when it does not fit.
+std::string fortran_es(double v, int w, int d) {
+  char buf[64];
+  std::string s;
+  if (v != v) s = "NaN";
+  else if (v > 1.7976931348623157e308) s = "Infinity";
+  else if (v < -1.7976931348623157e308) s = "-Infinity";
+  else {
+    std::snprintf(buf, sizeof buf, "%.*E", d, v);
+    s = buf;
+    const size_t e = s.find('E');
+    if (e != std::string::npos && s.size() - e - 2 > 2) s.erase(e, 1);   // three exponent digits: the E is dropped
+  }
+  if ((int)s.size() > w) return std::string((size_t)w, '*');
+  return std::string((size_t)w - s.size(), ' ') + s;
+}
+std::string fortran_i(long v, int w) {
+  std::string s = std::to_string(v);
+  if ((int)s.size() > w) return std::string((size_t)w, '*');
+  return std::string((size_t)w - s.size(), ' ') + s;
+}
+// Fortran Aw output of a string of length n: right-justified when shorter than w, the leftmost w characters otherwise
+std::string fortran_a(const std::string &s, int w) {
+  if ((int)s.size() >= w) return s.substr(0, (size_t)w);
+  return std::string((size_t)w - s.size(), ' ') + s;
+}
+
+}  // namespace
+
+extern "C" int xb_ev_write(const char *path, int32_t nrec, const int32_t *kstep, const double *t, const double *t9,
+                           const double *rho, const double *edot, const double *sqnu, const double *tdel, int32_t nout,
+                           const char *names5, const double *xout, const int32_t *kmon) {
+  if (!path || nrec < 0 || nout < 0 || (nout > 0 && (!names5 || !xout)) ||
+      (nrec > 0 && (!kstep || !t || !t9 || !rho || !edot || !sqnu || !tdel || !kmon)))
+    return XB_ERR_ARG;
+  FILE *f = std::fopen(path, "w");
+  if (!f) return XB_ERR_IO;
+  std::string line = fortran_a("k ", 4) + fortran_a(" Time ", 15) + fortran_a(" T(GK) ", 10) + fortran_a(" Density ", 10) +
+                     fortran_a(" dE/dt ", 10) + fortran_a(" sqnu ", 10) + fortran_a(" Timestep ", 10);
+  for (int i = 0; i < nout; ++i) line += fortran_a(std::string(names5 + (size_t)5 * i, 5), 9);
+  line += fortran_a(" It ", 4);
+  bool ok = std::fprintf(f, "%s\n", line.c_str()) > 0;
+  for (int32_t n = 0; ok && n < nrec; ++n) {
+    line = fortran_i(kstep[n], 4) + fortran_es(t[n], 15, 8) + fortran_es(t9[n], 10, 3) + fortran_es(rho[n], 10, 3) +
+           fortran_es(edot[n], 10, 2) + fortran_es(sqnu[n], 10, 2) + fortran_es(tdel[n], 10, 2);
+    for (int i = 0; i < nout; ++i) line += fortran_es(xout[(size_t)n * nout + i], 9, 2);
+    line += fortran_i(kmon[2 * n], 2) + fortran_i(kmon[2 * n + 1], 2);
+    ok = std::fprintf(f, "%s\n", line.c_str()) > 0;
+  }
+  ok = (std::fclose(f) == 0) && ok;
+  return ok ? XB_OK : XB_ERR_IO;
+}

@@ -52,6 +52,29 @@ def write_ts(path, net, controls, fixture, hist, zone=0, descript=('', '', ''), 
     return n
 
 
+def write_ev(path, net, hist, zone=0, names=()):
+    """ASCII evolution file ev_<zone> (itsout >= 2; net.F90:303-314, xnet_output.F90:72,83-85): one line per record with
+    the mass fractions of the species in `names` (the control file's output nuclei; 5-character names as in sunet,
+    matched after stripping blanks)."""
+    n = int(hist['hist_n'][zone])
+    aa = net.dtable('aa')
+    known = [s.strip().lower() for s in net.names()] if hasattr(net, 'names') else None
+    idx = []
+    for nm in names:
+        if known is None:
+            raise ValueError('species names are not available for this network')
+        idx.append(known.index(nm.strip().lower()))
+    y = hist['hist_y'][zone, :n]
+    xout = np.ascontiguousarray(y[:, idx] * aa[idx]) if idx else None
+    names5 = ''.join(nm.strip().rjust(5)[:5] for nm in names).encode()
+    col = {k: np.ascontiguousarray(hist['hist_' + k][zone, :n]) for k in ('kstep', 't', 't9', 'rho', 'edot', 'sqnu', 'tdel')}
+    kmon = np.ascontiguousarray(hist['hist_kmon'][zone, :n])
+    api._chk(api.lib().xb_ev_write(os.fsencode(path), n, api._pi(api._i(col['kstep'])), api._pd(col['t']), api._pd(col['t9']),
+                                   api._pd(col['rho']), api._pd(col['edot']), api._pd(col['sqnu']), api._pd(col['tdel']),
+                                   len(idx), names5, api._pd(xout), api._pi(api._i(kmon))))
+    return n
+
+
 def _records(buf):
     """Splits a Fortran sequential-unformatted byte string into payloads, checking both record markers."""
     out = []; p = 0
