@@ -19,13 +19,14 @@ from oracle import xnet_oracle as O                 # noqa: E402
 def lu_stats(a, tau=1.0):
     """Right-looking LU with (threshold) partial pivoting that skips structural zeros; returns (nnz(L+U), flops)."""
     a = a.copy(); n = a.shape[0]; flops = 0
+    rowp = np.arange(n)
     for k in range(n - 1):
         col = np.abs(a[k:, k])
         p = k + int(np.argmax(col))
         if tau * col[p - k] <= col[0] and col[0] > 0:
             p = k
         if p != k:
-            a[[k, p]] = a[[p, k]]
+            a[[k, p]] = a[[p, k]]; rowp[[k, p]] = rowp[[p, k]]
         if a[k, k] == 0.0:
             continue
         rows = np.nonzero(a[k + 1:, k])[0] + k + 1
@@ -35,7 +36,7 @@ def lu_stats(a, tau=1.0):
         if len(rows) and len(cols):
             a[np.ix_(rows, cols)] -= np.outer(a[rows, k], a[k, cols])
             flops += 2 * len(rows) * len(cols)
-    return int(np.count_nonzero(a)), flops, a
+    return int(np.count_nonzero(a)), flops, a, rowp
 
 
 def profile_storage(lu):
@@ -63,11 +64,17 @@ def main():
             for label, pm in (('natural order', list(range(ny))), ('light particles last', perm)):
                 a = jac[np.ix_(pm, pm)]
                 for tau in (1.0, 0.25):
-                    nnz, fl, lu = lu_stats(a, tau)
+                    nnz, fl, lu, rowp = lu_stats(a, tau)
                     growth = np.abs(np.triu(lu)).max() / np.abs(a).max()
-                    print('  step %4d T9 %.2f  %-22s tau %.2f: nnz(A) %5d (%.2f)  nnz(L+U) %6d (%.2f)  flops %.3g (%.3f of dense)  skyline %6d doubles (%.2f)  max|U|/max|A| %.2f'
+                    from scipy.linalg import solve_triangular
+                    b = yd[pm][rowp]
+                    xs = solve_triangular(np.triu(lu), solve_triangular(np.tril(lu, -1) + np.eye(ny), b, lower=True))
+                    x = np.empty(ny); x[pm] = xs
+                    big = np.abs(x_ref) > 1e-10 * np.abs(x_ref).max()
+                    dsol = np.abs(x[big] / x_ref[big] - 1).max()
+                    print('  step %4d T9 %.2f  %-22s tau %.2f: nnz(A) %5d (%.2f)  nnz(L+U) %6d (%.2f)  flops %.3g (%.3f of dense)  skyline %6d doubles (%.2f)  max|U|/max|A| %.2f  max rel. diff. of the solution vs dense DGESV %.1e'
                           % (k, t9, label, tau, np.count_nonzero(a), np.count_nonzero(a) / ny ** 2, nnz, nnz / ny ** 2, fl,
-                             fl / (2.0 / 3.0 * ny ** 3), profile_storage(lu), profile_storage(lu) / ny ** 2, growth))
+                             fl / (2.0 / 3.0 * ny ** 3), profile_storage(lu), profile_storage(lu) / ny ** 2, growth, dsol))
             del x_ref
 
 
