@@ -130,3 +130,37 @@ def test_network_from_fortran_arrays_round_trip(built, net, iweak0):
     bad = dict(t); bad['ifl2'] = t['ifl2'].copy(); bad['ifl2'][0] = n.mflx + 5
     with pytest.raises(Exception):
         X.Network.from_fortran_arrays(bad, iweak0)
+
+
+@pytest.mark.parametrize('name,net,frac', [('torch47', 'torch47', 0.60), ('sn160', 'SN160', 0.25), ('xrb304', 'XRB304', 0.20)])
+def test_structured_lu_plan_envelope(built, oracle_problem, name, net, frac):
+    """Groundwork for the structured LU: with the light particles ordered last, the skyline envelope the
+    loader derives from the species <-> reaction maps (a) contains every non-zero of the assembled Jacobian, (b) is not
+    left by an LU without interchanges (the numeric factors stay inside it), (c) is a small fraction of N^2."""
+    import xnet_b200 as X
+    n = X.Network(os.path.join(DATA, 'Data_' + net), 1)
+    ny = n.ny
+    perm = n.itable('slu_perm') - 1; rf = n.itable('slu_rowfirst') - 1; cf = n.itable('slu_colfirst') - 1
+    assert np.array_equal(np.sort(perm), np.arange(ny))
+    zz = n.dtable('zz'); aa = n.dtable('aa')
+    light = (zz[perm] <= 2) & (aa[perm] <= 4)
+    nl = int(light.sum())
+    assert 3 <= nl <= 6 and light[-nl:].all() and not light[:-nl].any()
+    assert (rf <= np.arange(ny)).all() and (cf <= np.arange(ny)).all()
+    assert n.int('slu_doubles') == ny + int((np.arange(ny) - rf).sum() + (np.arange(ny) - cf).sum())
+    assert n.int('slu_doubles') <= frac * ny * ny
+    inside = np.zeros((ny, ny), bool)
+    for i in range(ny):
+        inside[i, rf[i]:i + 1] = True; inside[cf[i]:i + 1, i] = True
+    op = oracle_problem(name)
+    h = op.run(nzone=1, hist_cap=4000)
+    k = int(h['hist_n'][0]) - 2
+    cs, yd, jac, ye = op.eval_point(h['hist_t9'][0, k], h['hist_rho'][0, k], h['hist_y'][0, k], 1.0 / h['hist_tdel'][0, k], -1.0)
+    a = jac[np.ix_(perm, perm)]                       # [row, col] in the structured order
+    assert not (a != 0)[~inside].any()
+    lu = a.copy()
+    for c in range(ny - 1):                            # LU without interchanges
+        assert lu[c, c] != 0.0
+        lu[c + 1:, c] /= lu[c, c]
+        lu[c + 1:, c + 1:] -= np.outer(lu[c + 1:, c], lu[c, c + 1:])
+    assert not (lu != 0)[~inside].any()

@@ -359,6 +359,7 @@ int xb_net_from_arrays(const xb_net_arrays *A, xb_net **net) {
   if (A->ffn_qval) std::copy(A->ffn_qval, A->ffn_qval + h.nffn, h.ffn_qval.begin());
   if (A->has_logft) std::copy(A->has_logft, A->has_logft + h.nffn, h.has_logft.begin());
   h.chap_la.assign(kNChap, 0); h.chap_le.assign(kNChap, 0);
+  structured_lu_plan(h);
   // reaction pairs as matched by the caller (Module xnet_match); without them there is no flux output
   h.mflx = 0;
   for (int c = 0; c < 4; ++c) h.ifl[c].assign(h.nreac[c], 0);
@@ -391,6 +392,7 @@ int xb_net_int(const xb_net *net, const char *what, int32_t *value) {
   const Network &h = net->h; std::string w(what);
   if (w == "ny") *value = h.ny; else if (w == "nffn") *value = h.nffn; else if (w == "nnnu") *value = h.nnnu;
   else if (w == "izmax") *value = h.izmax; else if (w == "mflx") *value = h.mflx;
+  else if (w == "slu_doubles") *value = (int32_t)h.slu_doubles;
   else if (w.size() == 6 && w.compare(0, 5, "nreac") == 0 && w[5] >= '1' && w[5] <= '4') *value = h.nreac[w[5] - '1'];
   else if (w.size() == 4 && w.compare(0, 3, "nan") == 0 && w[3] >= '1' && w[3] <= '4') *value = h.nan[w[3] - '1'];
   else return fail(XB_ERR_ARG, "xb_net_int: unknown key " + w);
@@ -419,6 +421,9 @@ int xb_net_itable(const xb_net *net, const char *what, int32_t *out, int64_t cap
   if (w == "chap_le") return copy_out(h.chap_le, out, cap, n);
   if (w == "has_logft") return copy_out(h.has_logft, out, cap, n);
   if (w == "nflx") return copy_out(h.nflx, out, cap, n);
+  if (w == "slu_perm") return copy_out(h.slu_perm, out, cap, n);
+  if (w == "slu_rowfirst") return copy_out(h.slu_rowfirst, out, cap, n);
+  if (w == "slu_colfirst") return copy_out(h.slu_colfirst, out, cap, n);
   if (w == "iwflx") return copy_out(h.iwflx, out, cap, n);
   if (w == "ifl_orig") return copy_out(h.ifl_orig, out, cap, n);
   if (w == "ifl_term") return copy_out(h.ifl_term, out, cap, n);

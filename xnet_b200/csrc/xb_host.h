@@ -39,6 +39,13 @@ struct Network {
   std::vector<double> qflx;                   // [mflx] |Q|
   std::vector<double> dcflx;                  // [mflx][2] double-counting factors (forward, reverse)
   std::vector<int32_t> ifl_orig, ifl_term;    // [mflx] originating / terminating species (1-based)
+  // structured-LU plan (groundwork, not yet used by a kernel): species order with the light particles
+  // (Z <= 2, A <= 4) last, and the skyline envelope of the Jacobian's structural pattern in that order, which an LU
+  // without interchanges never leaves
+  std::vector<int32_t> slu_perm;              // [ny] new position -> original species (1-based)
+  std::vector<int32_t> slu_rowfirst;          // [ny] first structural column of row i (1-based, permuted order, <= i)
+  std::vector<int32_t> slu_colfirst;          // [ny] first structural row of column j (1-based, permuted order, <= j)
+  int64_t slu_doubles = 0;                    // skyline storage: sum (i - rowfirst) + (j - colfirst) + ny
   // FFN tables [nffn][143]
   std::vector<double> ffnsum, ffnenu, ffn_ec, ffn_beta, ffn_qval;
   std::vector<int32_t> has_logft;
@@ -52,6 +59,8 @@ void load_network(const std::string &data_dir, int iweak0, Network &net);
 void match_react(Network &net);
 // dcflx, ifl_orig, ifl_term from mflx/nflx (second half of match_react; also used for networks built from arrays)
 void flux_init(Network &net);
+// fills slu_perm, slu_rowfirst, slu_colfirst, slu_doubles from the species <-> reaction maps
+void structured_lu_plan(Network &net);
 int index_from_name(const Network &net, const std::string &name);
 void load_helm_table(const std::string &path, Network &net);
 

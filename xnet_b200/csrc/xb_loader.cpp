@@ -374,6 +374,43 @@ void flux_init(Network &net) {
   }
 }
 
+// Structural pattern of the Jacobian from the maps (d ydot_i / d y_j is structurally non-zero iff j is a reactant of a
+// reaction registered with species i, xnet_jacobian_dense.F90:311-341), the light-particles-last order, its envelope.
+void structured_lu_plan(Network &net) {
+  const int ny = net.ny;
+  std::vector<int> light, heavy;
+  for (int i = 0; i < ny; ++i) ((net.zz[i] <= 2.0 && net.aa[i] <= 4.0) ? light : heavy).push_back(i);
+  net.slu_perm.clear();
+  for (int i : heavy) net.slu_perm.push_back(i + 1);
+  for (int i : light) net.slu_perm.push_back(i + 1);
+  std::vector<int> pos(ny);
+  for (int p = 0; p < ny; ++p) pos[net.slu_perm[p] - 1] = p;
+  std::vector<int> rowfirst(ny), colfirst(ny);
+  for (int p = 0; p < ny; ++p) { rowfirst[p] = p; colfirst[p] = p; }
+  for (int c = 0; c < 4; ++c) {
+    if (net.la.size() != (size_t)4 * ny) break;
+    for (int i = 0; i < ny; ++i) {
+      for (int t = net.la[(size_t)c * ny + i]; t <= net.le[(size_t)c * ny + i]; ++t) {
+        if (t < 1 || t > (int)net.mu[c].size()) continue;
+        const int k = net.mu[c][t - 1] - 1;
+        for (int r = 0; r <= c; ++r) {
+          const int j = net.ni[c][(size_t)k * 6 + r] - 1;
+          if (j < 0 || j >= ny) continue;
+          const int pi = pos[i], pj = pos[j];
+          if (pj < pi) rowfirst[pi] = std::min(rowfirst[pi], pj);
+          else if (pi < pj) colfirst[pj] = std::min(colfirst[pj], pi);
+        }
+      }
+    }
+  }
+  net.slu_rowfirst.resize(ny); net.slu_colfirst.resize(ny);
+  net.slu_doubles = ny;
+  for (int p = 0; p < ny; ++p) {
+    net.slu_rowfirst[p] = rowfirst[p] + 1; net.slu_colfirst[p] = colfirst[p] + 1;
+    net.slu_doubles += (p - rowfirst[p]) + (p - colfirst[p]);
+  }
+}
+
 namespace {
 void read_ffn(const std::string &dir, int iweak0, Network &net) {
   const int nf = std::max(net.nffn, 1);
@@ -438,6 +475,7 @@ void load_network(const std::string &data_dir, int iweak0, Network &net) {
   preprocess_reactions(data_dir, net);
   read_ffn(data_dir, iweak0, net);
   match_react(net);
+  structured_lu_plan(net);
 }
 
 void read_thermo_file(const std::string &path, Thermo &th) {
