@@ -7,7 +7,9 @@ The fast-arithmetic path (FMA, CUDA libm) is compared against the libm oracle wi
 the problem's conditioning allows (DESIGN.md "parity"): 1e-10 relative on Y>1e-20 per step for as
 long as two CPU builds of the oracle itself agree to that level, kernel outputs to 1e-12 of the sum
 of term magnitudes, one-step restarts to 1e-9 of max(Y), end states to 1e-2 on X>1e-6 (two CPU builds of the
-oracle itself differ by ~1e-3 there: distinct accepted-step sequences, first-order BE).
+oracle itself differ by ~1e-3 there: distinct accepted-step sequences, first-order BE).  Pivot sequences are compared with
+DGETRF's only in strict arithmetic; fast arithmetic accepts the predicted pivot by threshold (tau = 0.25) and is checked
+through P L U = A, |L| <= 1/tau and residuals instead.
 """
 import os
 
