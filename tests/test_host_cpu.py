@@ -164,3 +164,25 @@ def test_structured_lu_plan_envelope(built, oracle_problem, name, net, frac):
         lu[c + 1:, c] /= lu[c, c]
         lu[c + 1:, c + 1:] -= np.outer(lu[c + 1:, c], lu[c, c + 1:])
     assert not (lu != 0)[~inside].any()
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    """The bench line committed under profiles/ (measured on a B200 this round) carries every key of the bench contract:
+    headline metric, e2e with per-step copy bytes, launch count, clocks, the roofline object and the CPU baseline."""
+    import glob
+    import json
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_bench_default_*.json')))
+    assert files
+    d = json.load(open(files[-1]))
+    for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
+              'dtype', 'data', 'config', 'e2e', 'gpu_launches', 'clocks', 'roofline', 'cpu_baseline'):
+        assert k in d, k
+    assert d['metric'] == 'zone-Newton-iters/sec' and d['dtype'] == 'f64' and d['scaling'] == 'weak' and d['warmup'] >= 3
+    assert 'workload' in d['config'] and d['config']['zones_per_gpu'] == 16384 and d['config']['all_zones_finished']
+    assert set(('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step')) <= set(d['e2e']) and d['e2e']['h2d_bytes_per_step'] > 0
+    assert d['gpu_launches'] > 0 and not d['clocks']['reasons']
+    r = d['roofline']
+    assert set(('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic')) <= set(r) and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-12
+    c = d['cpu_baseline']
+    assert set(('value', 'unit', 'cores', 'kind', 'sample')) <= set(c) and c['kind'] in ('port', 'reference')
+    assert d['value'] > 10 * c['value']
