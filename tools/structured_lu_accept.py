@@ -3,7 +3,7 @@
 Along complete oracle trajectories (every `stride`-th accepted step) the Jacobian is permuted, eliminated without
 interchanges, and every column is tested with the fast mode's acceptance rule tau*max|a(i,k)| <= |a(k,k)|, tau = 0.25.
 Reports the fraction of factorisations with no violated column, the violated columns per factorisation and where they are.
-usage: python tools/structured_lu_accept.py [stride] > profiles/rNN_structured_lu_accept.txt"""
+usage: python tools/structured_lu_accept.py [stride [tau]] > profiles/rNN_structured_lu_accept.txt"""
 import os
 import sys
 
@@ -18,7 +18,7 @@ import xnet_b200 as X                                # noqa: E402  (host-side lo
 
 def main():
     stride = int(sys.argv[1]) if len(sys.argv) > 1 else 10
-    tau = 0.25
+    tau = float(sys.argv[2]) if len(sys.argv) > 2 else 0.25
     for name, net in (('torch47', 'torch47'), ('sn160', 'SN160'), ('sn160_scrn', 'SN160'), ('xrb304', 'XRB304')):
         op = O.Problem.from_control(control_text(*PROBLEMS[name]), DATA)
         ny = op.nuc['ny']
