@@ -31,7 +31,7 @@ Module xnet_b200f
   Type, Bind(C) :: xb_ctl_t
     Integer(C_INT32_T) :: iweak0, iscrn, iheat, isolv, kstmx, kitmx, ijac, iconvc
     Real(C_DOUBLE) :: changemx, changemxt, yacc, tolm, tolc, tolt9, ymin, tdel_maxmult
-    Integer(C_INT32_T) :: arith, reserved
+    Integer(C_INT32_T) :: arith, solver
   End Type xb_ctl_t
 
   Interface

@@ -77,7 +77,7 @@ Contains
     ctl%kstmx = kstmx ; ctl%kitmx = kitmx ; ctl%ijac = ijac ; ctl%iconvc = iconvc
     ctl%changemx = changemx ; ctl%changemxt = changemxt ; ctl%yacc = yacc ; ctl%tolm = tolm
     ctl%tolc = tolc ; ctl%tolt9 = tolt9 ; ctl%ymin = ymin ; ctl%tdel_maxmult = tdel_maxmult
-    ctl%arith = 0 ; ctl%reserved = 0
+    ctl%arith = 0 ; ctl%solver = 0
     Call xb_check(xb_ctx_create(xb_net,c_loc(ctl),int(nzevolve,C_INT),int(mod(myid,max(1,ngpu)),C_INT),xb_ctx), &
       & 'xb_ctx_create')
     Return

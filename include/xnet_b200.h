@@ -82,7 +82,14 @@ typedef struct {
   double changemx, changemxt, yacc, tolm, tolc, tolt9, ymin, tdel_maxmult;
   int32_t arith;             /* 0 = fast (FMA contraction, CUDA libm); 1 = strict (no FMA,
                                 portable elementary functions: bit-reproducible vs the oracle) */
-  int32_t reserved;
+  int32_t solver;            /* linear solver of the fused evolve (xb_evolve*) in fast arithmetic:
+                                0 = dense LU with (threshold) partial pivoting, DGETRF's algorithm;
+                                1 = structured LU: species reordered light-particles-last, skyline envelope from the
+                                    reaction maps (what sparse_check finds, source/xnet_preprocess.F90:291-503; the
+                                    reference's answer is xnet_jacobian_MA48.F90), elimination without interchanges
+                                    verified column by column (tau |a_ik| <= |a_kk|), partial pivoting inside the
+                                    light-particle border, dense partial-pivoting fallback for a factorisation that
+                                    fails the test.  Ignored (dense) with arith = 1 and by the module-level drop-ins. */
 } xb_ctl;
 
 const char *xb_last_error(void);
@@ -242,6 +249,21 @@ int xb_ev_write(const char *path, int32_t nrec, const int32_t *kstep, const doub
 int xb_phase_cycles(xb_ctx *ctx, double *cycles24);
 /* bytes moved host->device / device->host by the last xb_evolve call */
 int xb_last_copy_bytes(xb_ctx *ctx, int64_t *h2d, int64_t *d2h);
+/* duration (ms, CUDA events on the launching stream) of the last kernel this context launched: a module-level
+ * drop-in (xb_cross_sect ... xb_step_be) or the evolve kernel */
+int xb_last_kernel_ms(xb_ctx *ctx, float *ms);
+/* structured solver of this context: info8 = active (0/1), msize, doubles of the skyline store, flops of one
+ * factorisation (2 per multiply-add), zones resident per SM, rows/columns of the pivoted border, warps that
+ * factor, reaction rates cached in shared memory */
+int xb_solver_info(xb_ctx *ctx, double *info8);
+/* structured-LU index tables of a network (heat = 1: with the T9 equation); what = "perm","pos","rf","cf","lo","uo",
+ * "rstart","cstart","rlist","clist","sizes" -- see SluTables in xnet_b200/csrc/xb_host.h */
+int xb_slu_table(const xb_net *net, int32_t heat, const char *what, int32_t *out, int64_t cap, int64_t *n);
+/* nz dense systems a[nz][n*n] (column-major, equation order, zero outside the structural envelope) solved with the
+ * structured LU of a solver = 1 context: mode 0 = right-hand side carried through the factorisation, 1 = factor, then
+ * forward + backward solve, 2 / 3 = the dense fallback likewise.  flags[nz]: bit 0 = threshold test failed, bit 1 = a
+ * non-zero outside the envelope was dropped, bit 2 = singular (dense fallback). */
+int xb_slu_solve(xb_ctx *ctx, int32_t nz, const double *a, const double *b, double *x, int32_t *flags, int32_t mode);
 /* cfg6 = grid, threads per CTA, dynamic smem bytes, jacobian-in-smem flag, SM count, msize */
 int xb_launch_config(xb_ctx *ctx, int32_t *cfg6);
 /* measured FP64 FMA peak of this device (microbenchmark, FLOP/s) */

@@ -799,6 +799,10 @@ static int full_net_zone(zone_t *z, const ox_zones *zn, int iz, ox_out *out) {
     z->t9t = z->t9; z->rhoo = z->rho; z->rhot = z->rho; z->yeo = z->ye; z->yet = z->ye;
     benuc(z, z->y, &enb, &enm);
     enold = enm; edot = 0.0; sqnu = 0.0;
+    /* constant thermodynamic conditions without self-heating: the reference evaluates the rates once, in the first
+     * timestep call (tdel = 0, xnet_integrate.F90:58-62), and step_be never again (xnet_integrate_be.F90:307-313);
+     * a restarted zone has tdel != 0, so the rates of its state are evaluated here */
+    if (z->nh == 1 && ctl->iheat == 0) { rc_ = cross_sect(z); if (rc_) return rc_; }
   } else {
   benuc(z, z->y, &enb, &enm);
   z->tdel_old = z->tdel; z->tdel_next = z->tdel; z->nto = z->nt; z->ntt = z->nt; z->to = z->t; z->tt = z->t;

@@ -1,0 +1,178 @@
+"""Structured LU, host side: the index tables of xb_loader.cpp drive a numpy restatement of the device
+algorithm (xnet_b200/csrc/xb_slu.cuh: skyline store, elimination without interchanges over the heavy part with the
+threshold test, partial pivoting inside the light-particle border, unscaled multipliers, forward/backward solves) on
+Jacobians the oracle assembles along real trajectories.  Checks: every structural non-zero lies inside the envelope,
+the elimination never leaves it, and the solution agrees with LAPACK's dense solve to the conditioning of the system.
+CPU only: the CUDA kernels are checked against the same dense solves in tests/test_gpu_slu.py."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import DATA, PROBLEMS, control_text
+
+TAU = 0.1
+
+
+class Slu:
+    """numpy mirror of slu_factor / slu_solve"""
+    def __init__(self, net, heat):
+        self.heat = heat
+        t = {k: net.slu_table(k, heat) for k in ('perm', 'pos', 'rf', 'cf', 'lo', 'uo', 'sizes')}
+        self.n, self.nstore, self.nb = int(t['sizes'][0]), int(t['sizes'][1]), int(t['sizes'][2])
+        self.perm, self.pos, self.rf, self.cf, self.lo, self.uo = (t[k].astype(int) for k in ('perm', 'pos', 'rf', 'cf', 'lo', 'uo'))
+        n, nh = self.n, self.n - self.nb
+        self.nh = nh
+        # rhi / chi exactly as xb_slu_configure forms them
+        self.rhi = np.arange(n); self.chi = np.arange(n)
+        for p in range(n):
+            for i in range(p + 1, nh):
+                if self.rf[i] <= p:
+                    self.rhi[p] = i
+                if self.cf[i] <= p:
+                    self.chi[p] = i
+
+    def addr(self, i, j):
+        return self.uo[j] + i if i <= j else self.lo[i] + j
+
+    def inside(self, i, j):
+        return self.cf[j] <= i if i <= j else self.rf[i] <= j
+
+    def rows(self, k):
+        c = list(range(k + 1, self.rhi[k] + 1)) + list(range(self.nh, self.n))
+        return [i for i in c if self.rf[i] <= k]
+
+    def cols(self, k):
+        c = list(range(k + 1, self.chi[k] + 1)) + list(range(self.nh, self.n))
+        return [j for j in c if self.cf[j] <= k]
+
+    def scatter(self, a):
+        """a[row, col] in equation order -> store; asserts nothing non-zero falls outside the envelope"""
+        S = np.zeros(self.nstore)
+        used = np.zeros(self.nstore, bool)
+        for r in range(self.n):
+            for c in range(self.n):
+                pi, pj = self.pos[r], self.pos[c]
+                if self.inside(pi, pj):
+                    ad = self.addr(pi, pj)
+                    assert 0 <= ad < self.nstore and not used[ad]
+                    used[ad] = True; S[ad] = a[r, c]
+                else:
+                    assert a[r, c] == 0.0, 'non-zero outside the envelope at (%d,%d)' % (r, c)
+        assert used.all(), 'store has unaddressed slots'
+        return S
+
+    def factor(self, S, b=None):
+        n, nh, nb = self.n, self.nh, self.nb
+        rinv = np.zeros(n); fail = False
+        b = None if b is None else b.copy()
+        for k in range(nh):
+            piv = S[self.uo[k] + k]
+            rinv[k] = 1.0 / piv
+            for i in self.rows(k):
+                a = S[self.lo[i] + k]
+                if i < n - self.heat and TAU * abs(a) > abs(piv):   # the T9 row is exempt (xb_slu.cuh)
+                    fail = True
+                l = a * rinv[k]
+                for j in self.cols(k):
+                    S[self.addr(i, j)] -= l * S[self.uo[j] + k]
+                if b is not None:
+                    b[i] -= l * b[k]
+        # border block with partial pivoting (registers on the device)
+        v = np.array([[S[self.addr(nh + r, nh + c)] for c in range(nb)] for r in range(nb)])
+        vb = None if b is None else b[nh:].copy()
+        ipb = list(range(nb))
+        for j in range(nb):
+            p = j + int(np.argmax(np.abs(v[j:, j])))
+            ipb[j] = p
+            if p != j:
+                v[[j, p]] = v[[p, j]]
+                if vb is not None:
+                    vb[[j, p]] = vb[[p, j]]
+            rinv[nh + j] = 1.0 / v[j, j]
+            for r in range(j + 1, nb):
+                lr = v[r, j] * rinv[nh + j]
+                v[r, j + 1:] -= lr * v[j, j + 1:]
+                if vb is not None:
+                    vb[r] -= lr * vb[j]
+        for r in range(nb):
+            for c in range(nb):
+                S[self.addr(nh + r, nh + c)] = v[r, c]
+        if b is not None:
+            b[nh:] = vb
+        for j in range(nb):
+            if ipb[j] != j:
+                la, lb = self.lo[nh + j], self.lo[nh + ipb[j]]
+                tmp = S[la:la + nh].copy(); S[la:la + nh] = S[lb:lb + nh]; S[lb:lb + nh] = tmp
+        return rinv, ipb, fail, b
+
+    def solve(self, S, rinv, ipb, b, fwd_done):
+        n, nh, nb = self.n, self.nh, self.nb
+        b = b.copy()
+        if not fwd_done:
+            for j in range(nb):
+                p = ipb[j]
+                if p != j:
+                    b[[nh + j, nh + p]] = b[[nh + p, nh + j]]
+            for k in range(n):
+                f = b[k] * rinv[k]
+                rows = self.rows(k) if k < nh else range(k + 1, n)
+                for i in rows:
+                    b[i] -= S[self.lo[i] + k] * f
+        for k in range(n - 1, -1, -1):
+            x = b[k] * rinv[k]
+            b[k] = x
+            for i in range(self.cf[k], k):
+                b[i] -= S[self.uo[k] + i] * x
+        return b
+
+
+def _systems(op, name, heat, nsamp=5):
+    """(a[row, col], rhs) in equation order at nsamp accepted steps of the oracle's trajectory"""
+    from oracle import xnet_oracle as O
+    h = op.run(nzone=1, hist_cap=6000)
+    n = int(h['hist_n'][0])
+    out = []
+    for k in np.linspace(2, n - 2, nsamp).astype(int):
+        rdt = 1.0 / h['hist_tdel'][0, k + 1]
+        if heat:
+            r = O.eval_point_heat(op, h['hist_t9'][0, k], h['hist_rho'][0, k], h['hist_y'][0, k], rdt, -1.0)
+            a = r['jac'].T.copy()                   # [row, col]
+            rhs = np.concatenate([r['ydot'], [r['t9dot']]])
+        else:
+            cs, yd, jac, ye = op.eval_point(h['hist_t9'][0, k], h['hist_rho'][0, k], h['hist_y'][0, k], rdt, -1.0)
+            a, rhs = jac, yd
+        out.append((a, rhs))
+    return out
+
+
+@pytest.mark.parametrize('name', ['alpha', 'torch47', 'sn160_scrn', 'torch47_heat', 'sn160_heat', 'xrb304'])
+def test_structured_lu_restatement(name, oracle_problem, gpu_problem):
+    op = oracle_problem(name)
+    ctl, net, fx = gpu_problem(name)
+    heat = 1 if ctl['iheat'] > 0 else 0
+    slu = Slu(net, heat)
+    n = slu.n
+    assert n == net.ny + heat and slu.nb >= 1 and slu.nstore < 65536
+    assert sorted(slu.perm.tolist()) == list(range(n)) and (slu.pos[slu.perm] == np.arange(n)).all()
+    if heat:
+        assert slu.perm[n - 1] == net.ny           # T9 stays the last equation
+    nfail = 0
+    for a, rhs in _systems(op, name, heat, 3 if n > 200 else 5):
+        S = slu.scatter(a)
+        x_ref = np.linalg.solve(a, rhs)
+        rinv, ipb, fail, bf = slu.factor(S.copy(), rhs[slu.perm])
+        nfail += fail
+        Sf = S.copy()
+        rinv2, ipb2, fail2, _ = slu.factor(Sf)
+        x1 = slu.solve(Sf, rinv2, ipb2, bf, True)[slu.pos]            # carried right-hand side
+        x2 = slu.solve(Sf, rinv2, ipb2, rhs[slu.perm], False)[slu.pos]   # separate forward solve
+        scale = np.abs(x_ref).max()
+        cond = np.linalg.cond(a)
+        tol = max(1e-13 * cond, 1e-12) * scale
+        assert np.abs(x1 - x_ref).max() <= tol, (name, np.abs(x1 - x_ref).max() / scale, cond)
+        assert np.abs(x2 - x1).max() <= 1e-12 * scale + 1e-3 * tol
+        # residual of the structured solve is as small as LAPACK's
+        r1 = np.abs(a @ x1 - rhs).max(); r0 = np.abs(a @ x_ref - rhs).max()
+        assert r1 <= 50 * r0 + 1e-14 * np.abs(rhs).max()
+    assert nfail == 0, 'threshold test (tau = %.2f) failed on %d sampled systems' % (TAU, nfail)

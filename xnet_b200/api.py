@@ -26,7 +26,7 @@ def lib_path():
 class XbCtl(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ('iweak0', 'iscrn', 'iheat', 'isolv', 'kstmx', 'kitmx', 'ijac', 'iconvc')] + \
                [(n, C.c_double) for n in ('changemx', 'changemxt', 'yacc', 'tolm', 'tolc', 'tolt9', 'ymin', 'tdel_maxmult')] + \
-               [('arith', C.c_int32), ('reserved', C.c_int32)]
+               [('arith', C.c_int32), ('solver', C.c_int32)]
 
 
 class XbZones(C.Structure):
@@ -72,7 +72,7 @@ EXPORTS = ['xb_last_error', 'xb_version', 'xb_launch_count', 'xb_net_load', 'xb_
            'xb_ctx_create', 'xb_ctx_destroy', 'xb_cross_sect', 'xb_get_csect', 'xb_yderiv', 'xb_jacobian_build',
            'xb_get_jac', 'xb_set_jac', 'xb_jacobian_decomp', 'xb_get_indx', 'xb_jacobian_bksub',
            'xb_jacobian_solve', 'xb_get_dcsect', 'xb_get_eos', 'xb_flux', 'xb_set_flux_output', 'xb_step_be', 'xb_ts_write', 'xb_ev_write', 'xb_evolve', 'xb_zones_upload', 'xb_evolve_resident', 'xb_results_download',
-           'xb_phase_cycles', 'xb_last_copy_bytes', 'xb_launch_config', 'xb_measure_fp64_peak']
+           'xb_phase_cycles', 'xb_last_copy_bytes', 'xb_launch_config', 'xb_measure_fp64_peak', 'xb_last_kernel_ms', 'xb_solver_info', 'xb_slu_table', 'xb_slu_solve']
 
 
 def lib():
@@ -124,6 +124,10 @@ def lib():
         l.xb_last_copy_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         l.xb_launch_config.argtypes = [C.c_void_p, c_ip]
         l.xb_measure_fp64_peak.argtypes = [C.c_int32, c_dp]
+        l.xb_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        l.xb_solver_info.argtypes = [C.c_void_p, c_dp]
+        l.xb_slu_table.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, c_ip, C.c_int64, C.POINTER(C.c_int64)]
+        l.xb_slu_solve.argtypes = [C.c_void_p, C.c_int32, c_dp, c_dp, c_dp, c_ip, C.c_int32]
         _lib = l
     return _lib
 
@@ -152,13 +156,14 @@ def _pi(a):
 # --------------------------------------------------------------------------------------------------
 class Controls(dict):
     """Parsed `control` file (keys named as the xnet_controls module variables)."""
-    def to_struct(self, arith=0, **override):
+    def to_struct(self, arith=0, solver=0, **override):
         c = XbCtl()
         for nm, _ in XbCtl._fields_:
-            if nm in ('arith', 'reserved'):
+            if nm in ('arith', 'solver'):
                 continue
             setattr(c, nm, override.get(nm, self[nm]))
         c.arith = arith
+        c.solver = solver
         return c
 
 
@@ -310,6 +315,14 @@ class Network:
         _chk(lib().xb_net_int(self.h, what.encode(), C.byref(v)))
         return v.value
 
+    def slu_table(self, what, heat=0):
+        """structured-LU index tables (xb_slu_table)"""
+        n = C.c_int64()
+        _chk(lib().xb_slu_table(self.h, heat, what.encode(), None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 1), np.int32)
+        _chk(lib().xb_slu_table(self.h, heat, what.encode(), _pi(out), out.size, C.byref(n)))
+        return out[:n.value]
+
     def itable(self, what):
         n = C.c_int64()
         _chk(lib().xb_net_itable(self.h, what.encode(), None, 0, C.byref(n)))
@@ -353,8 +366,16 @@ def load_fixture(net, inab_path, th_path):
                    xext=scal[1], aext=scal[2], zext=scal[3])
 
 
-def build_zone_set(fixtures, nzone=None, zfix=None, rho_scale=None, restart=None):
-    """Packs fixtures into the xb_zones layout; zone z uses fixture z mod K unless zfix is given."""
+def _pin(a):
+    """copy of a numpy array in page-locked host memory (torch is the allocator; the product path itself does not use it)"""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a)).clone().pin_memory()
+    return t.numpy()
+
+
+def build_zone_set(fixtures, nzone=None, zfix=None, rho_scale=None, restart=None, pinned=False):
+    """Packs fixtures into the xb_zones layout; zone z uses fixture z mod K unless zfix is given.  pinned: the arrays
+    are placed in page-locked memory (the host buffers of an end-to-end xb_evolve call)."""
     K = len(fixtures)
     nzone = nzone or K
     a = dict(
@@ -375,6 +396,8 @@ def build_zone_set(fixtures, nzone=None, zfix=None, rho_scale=None, restart=None
         for nm in ('t', 'tdel', 't9', 'rho', 't9o', 'y', 'yo'):
             a['rs_' + nm] = _d(restart[nm])
         a['rs_kstep0'] = _i(restart['kstep0'])
+    if pinned:
+        a = {k: _pin(v) for k, v in a.items()}
     z = XbZones()
     z.nfix = K; z.nzone = nzone
     for nm, tp in XbZones._fields_:
@@ -412,9 +435,12 @@ def _alloc_out(nzone, ny, hist_cap, pinned=False, mflx=0):
 
 class Context:
     """Device-resident state for `nzevolve` zones (what read_jacobian_data + be_init allocate)."""
-    def __init__(self, net, controls, nzevolve=1, device=0, arith=0, **override):
+    def __init__(self, net, controls, nzevolve=1, device=0, arith=0, solver=0, **override):
+        """arith: 0 = fast, 1 = strict (bit-reproducible).  solver (fused evolve, fast arithmetic only): 0 = dense
+        partial-pivoting LU (DGETRF order), 1 = structured LU (light particles last, skyline envelope, threshold-checked
+        elimination without interchanges, partial pivoting inside the light-particle border, dense fallback)."""
         self.net = net
-        self.ctl = controls.to_struct(arith=arith, **override)
+        self.ctl = controls.to_struct(arith=arith, solver=solver, **override)
         if self.ctl.iscrn > 0 or self.ctl.iheat > 0:
             net.load_helm()
         self.h = C.c_void_p()
@@ -518,13 +544,24 @@ class Context:
         return dict(inr=inr, yt=yt, t9t=t9t, ydot=ydot, t9dot=t9dot, kcount=kc)
 
     # ---- fused evolve ----
-    def full_net(self, zones, hist_cap=0, pinned=False, flux=False):
+    def full_net(self, zones, hist_cap=0, pinned=False, flux=False, check=True):
         """xb_evolve: host buffers in, host buffers out (H2D + kernel + D2H).  flux=True adds hist_flx, the
         matched-pair reaction fluxes of every ts record (xnet_flux.F90:67-150)."""
         res, o = _alloc_out(zones.nzone, self.net.ny, hist_cap, pinned, self.net.mflx if flux else 0)
         _chk(lib().xb_set_flux_output(self.h, 1 if flux else 0))
         _chk(lib().xb_evolve(self.h, C.byref(zones), C.byref(o)))
+        if check:
+            self.check_status(res)
         return res
+
+    @staticmethod
+    def check_status(res):
+        """The reference stops the run when a zone cannot continue ('Evolution failed to converge',
+        xnet_evolve.F90:226-237: its = 1 after ten time-step retries).  status: -1 = reached tstop, 0 = still evolving
+        when kstmx steps were taken (callers that cap kstmx on purpose), 2 = failed to converge."""
+        bad = np.nonzero(res['status'] > 0)[0]
+        if bad.size:
+            raise XnetB200Error('evolution failed to converge in %d zone(s), first: %d' % (bad.size, int(bad[0])))
 
     def flux(self, yt=None, nz=None, mask=None):
         """flux(mask_in) (xnet_flux.F90:67): fluxes [nz, mflx] from the device-resident rates and yt."""
@@ -556,6 +593,32 @@ class Context:
         names = ('rates', 'yderiv', 'jac', 'lu', 'bksub', 'other', 'total', 'zones',
                  'lu_panel', 'lu_swap_trsm', 'lu_gemm', 'spare') + tuple('dbg%d' % k for k in range(12))
         return dict(zip(names, c))
+
+    def solver_info(self):
+        """None with the dense solver, else the structured solver's sizes (xb_solver_info)."""
+        v = np.zeros(8)
+        _chk(lib().xb_solver_info(self.h, _pd(v)))
+        if v[0] == 0:
+            return None
+        return dict(msize=int(v[1]), skyline_doubles=int(v[2]), flops=float(v[3]), zones_per_sm=int(v[4]), border=int(v[5]),
+                    lu_warps=int(v[6]), rates_cached=int(v[7]))
+
+    def slu_solve(self, a, b, mode=0):
+        """xb_slu_solve: a [nz, n, n] as [zone, col, row] (column-major per zone, equation order), b [nz, n] -> (x, flags)"""
+        a = _d(a); b = _d(b); nz = a.shape[0]
+        x = np.zeros_like(b); fl = np.zeros(nz, np.int32)
+        _chk(lib().xb_slu_solve(self.h, nz, _pd(a), _pd(b), _pd(x), _pi(fl), mode))
+        return x, fl
+
+    @property
+    def kernel_name(self):
+        return 'evolve_slu_kernel' if self.solver_info() else ('evolve_kernel<strict>' if self.ctl.arith else 'evolve_kernel<fast>')
+
+    def last_kernel_ms(self):
+        """CUDA-event duration of the last kernel launched by this context (module-level drop-in or evolve)."""
+        ms = C.c_float()
+        _chk(lib().xb_last_kernel_ms(self.h, C.byref(ms)))
+        return ms.value
 
     def copy_bytes(self):
         a = C.c_int64(); b = C.c_int64()

@@ -19,81 +19,12 @@
 
 using namespace xb;
 
-// ------------------------------------------------------------------------------------------------
+#include "xb_ctx.h"
+
 static thread_local std::string g_err;
 static long long g_launches = 0;
-static int fail(int code, const std::string &msg) { g_err = msg; return code; }
-#define CUDA_TRY(expr)                                                                          \
-  do {                                                                                          \
-    cudaError_t e_ = (expr);                                                                    \
-    if (e_ != cudaSuccess)                                                                      \
-      return fail(XB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));             \
-  } while (0)
-
-struct xb_net { Network h; };
-
-template <class T>
-struct DevBuf {
-  T *p = nullptr; size_t n = 0;
-  cudaError_t put(const T *src, size_t count) {
-    cudaError_t e = resize(count);
-    if (e != cudaSuccess) return e;
-    if (count == 0) return cudaSuccess;
-    return cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice);
-  }
-  cudaError_t put(const std::vector<T> &v) { return put(v.data(), v.size()); }
-  cudaError_t resize(size_t count) {
-    if (count <= n && p) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr; n = 0;
-    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
-    if (e == cudaSuccess) n = std::max<size_t>(count, 1);
-    return e;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
-};
-
-struct xb_ctx {
-  const xb_net *net = nullptr;
-  xb_ctl ctl{};
-  int device = 0, nzevolve = 0, nsm = 0;
-  DevNet dn{};
-  DevCtl dc{};
-  // network tables
-  DevBuf<double> rcT, a[4], aa, zz, mex, be, g, lng, dlng, t9i, ffnsum, ffnenu;
-  DevBuf<int> ni, iwk, irev, iffn, la, le, mu[4], nn[4][4], ffr_n1, ffr_iffn;
-  DevBuf<double> helm, helm_t, helm_d, zzi, zseq53, sc_zw, sc_zi, z_zexti, ffn_ec, ffn_beta, ffn_qval;
-  DevBuf<int> has_logft;
-  DevBuf<int2> sc_iz;
-  // term plans (ydot, Jacobian)
-  struct PlanBufs { DevBuf<double> a; DevBuf<uint2> nn, mc; DevBuf<int> seg_start, seg_dest, multi_start, multi_dest; } pby, pbj;
-  int ld = 0, npart = 0;
-  // launch configuration
-  int threads = 256, grid = 0, jac_in_smem = 1;
-  size_t smem_bytes = 0;
-  DevScratch scr{};
-  DevBuf<double> scratch;
-  DevBuf<unsigned long long> phase;
-  DevBuf<int> counter;
-  // module-level per-zone state (HBM)
-  DevBuf<double> m_yt, m_t9t, m_rhot, m_ext, m_yet, m_csect, m_qk, m_ydot, m_jac, m_rhs, m_diag, m_mult;
-  DevBuf<double> m_dcsect, m_eos, m_t9dot, m_y, m_t9, m_tdel;
-  DevBuf<int> m_indx, m_info, m_mask, m_nh, m_inr, m_kcnt;
-  // evolve: zones + outputs
-  DevZones dz{};
-  DevOut dout{};
-  int nzone = 0, hist_cap = 0;
-  DevBuf<int> z_nh, z_off, z_nstart, z_zfix, z_kstep0;
-  DevBuf<double> z_th, z_t9h, z_rhoh, z_tstart, z_tstop, z_tdelstart, z_t9start, z_rhostart, z_yestart, z_ystart,
-      z_xext, z_aext, z_zext, z_rho_scale, z_rs_t, z_rs_tdel, z_rs_t9, z_rs_rho, z_rs_t9o, z_rs_y, z_rs_yo;
-  DevBuf<double> o_y, o_t, o_t9, o_rho, o_tdel, o_ht, o_ht9, o_hrho, o_htdel, o_hedot, o_hsqnu, o_hy, o_hflx;
-  DevBuf<int> fl_start, fl_k;
-  DevBuf<double> fl_dc, m_flx;
-  int want_flux = 0;
-  DevBuf<int> o_kstep, o_ktot, o_status, o_hn, o_hkstep, o_hkmon;
-  int64_t h2d = 0, d2h = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-};
+int xb_fail(int code, const std::string &msg) { g_err = msg; return code; }
+void xb_count_launch() { ++g_launches; }
 
 // ------------------------------------------------------------------------------------------------
 // shared-memory carve-up of one zone
@@ -683,134 +614,6 @@ static int upload_network(xb_ctx *c) {
 template <bool STRICT>
 static const void *evolve_fn() { return (const void *)evolve_kernel<STRICT>; }
 
-// ---- term plans ------------------------------------------------------------------------------------
-namespace {
-struct PlanRec { double a; int mu; int n[4]; int fseg; int fdest; int sseg; };
-struct PlanHost {
-  int nrec = 0, L = 0, nseg = 0, nmulti = 0, npart = 0;
-  std::vector<double> a; std::vector<uint2> nn, mc;
-  std::vector<int> seg_start, seg_dest, multi_start, multi_dest;
-};
-
-// recs sorted by segment (fseg non-decreasing, sseg non-decreasing); fdest = (destination<<1)|diag of
-// the record's fast segment; strict segments are [sseg_start[i], sseg_start[i+1]) with sseg_dest[i].
-PlanHost make_plan(const std::vector<PlanRec> &recs, int NT, int dummy, std::vector<int> sseg_start,
-                   std::vector<int> sseg_dest) {
-  PlanHost P;
-  P.nrec = (int)recs.size();
-  P.L = std::max(1, (P.nrec + NT - 1) / NT);
-  P.L = (P.L + kPlanU - 1) / kPlanU * kPlanU;
-  const size_t tot = (size_t)P.L * NT;
-  const unsigned dd = (unsigned)dummy | ((unsigned)dummy << 16);
-  P.a.assign(tot, 0.0); P.nn.assign(tot, make_uint2(dd, dd)); P.mc.assign(tot, make_uint2(0u, 0u));
-  P.nseg = (int)sseg_dest.size();
-  P.seg_start = std::move(sseg_start); P.seg_dest = std::move(sseg_dest);
-  // extent of every fast segment
-  std::vector<int> first, last;   // by fseg
-  for (int r = 0; r < P.nrec; ++r) {
-    const int g = recs[r].fseg;
-    if (g >= (int)first.size()) { first.resize(g + 1, -1); last.resize(g + 1, -1); }
-    if (first[g] < 0) first[g] = r;
-    last[g] = r;
-  }
-  int open_multi = -1;
-  for (int t = 0; t < NT; ++t) {
-    const int b = t * P.L, e = std::min(P.nrec, (t + 1) * P.L);
-    for (int r = b; r < e; ++r) {
-      const PlanRec &R = recs[r];
-      const size_t at = (size_t)(r - b) * NT + t;
-      P.a[at] = R.a;
-      P.nn[at] = make_uint2((unsigned)R.n[0] | ((unsigned)R.n[1] << 16), (unsigned)R.n[2] | ((unsigned)R.n[3] << 16));
-      unsigned ctl = 0;
-      const bool piece_end = (r + 1 == e) || recs[r + 1].fseg != R.fseg;
-      if (piece_end) {
-        int pb = r;
-        while (pb > b && recs[pb - 1].fseg == R.fseg) --pb;
-        const bool complete = (pb == first[R.fseg]) && (r == last[R.fseg]);
-        if (complete) ctl = 1u | ((unsigned)(R.fdest & 1) << 2) | ((unsigned)(R.fdest >> 1) << 3);
-        else {
-          if (open_multi != R.fseg) { P.multi_start.push_back(P.npart); P.multi_dest.push_back(R.fdest); open_multi = R.fseg; }
-          ctl = 2u | ((unsigned)P.npart << 3);
-          ++P.npart;
-        }
-      }
-      P.mc[at] = make_uint2((unsigned)R.mu, ctl);
-    }
-  }
-  P.nmulti = (int)P.multi_dest.size();
-  P.multi_start.push_back(P.npart);
-  return P;
-}
-}  // namespace
-
-static int upload_plan(xb_ctx::PlanBufs &B, DevPlan &D, const PlanHost &P) {
-  CUDA_TRY(B.a.put(P.a)); CUDA_TRY(B.nn.put(P.nn)); CUDA_TRY(B.mc.put(P.mc));
-  std::vector<int> ss(P.seg_start), sd(P.seg_dest), ms(P.multi_start), md(P.multi_dest);
-  if (sd.empty()) sd.push_back(0);
-  if (md.empty()) md.push_back(0);
-  CUDA_TRY(B.seg_start.put(ss)); CUDA_TRY(B.seg_dest.put(sd)); CUDA_TRY(B.multi_start.put(ms)); CUDA_TRY(B.multi_dest.put(md));
-  D.nrec = P.nrec; D.L = P.L; D.nseg = P.nseg; D.nmulti = P.nmulti; D.npart = P.npart;
-  D.a = B.a.p; D.nn = B.nn.p; D.mc = B.mc.p; D.seg_start = B.seg_start.p; D.seg_dest = B.seg_dest.p;
-  D.multi_start = B.multi_start.p; D.multi_dest = B.multi_dest.p;
-  return XB_OK;
-}
-
-// ydot plan: species-major, reaction class, ascending la..le (xnet_integrate.F90:409-469).
-// Jacobian plan: contributions generated in the order of the reference scatter loop
-// (xnet_jacobian_dense.F90:303-341), then grouped by element (stable): element (i0, col) of jac.
-static int build_plans(xb_ctx *c, int NT, int ld) {
-  const Network &h = c->net->h;
-  const DevNet &d = c->dn;
-  const int ny = h.ny, N = d.msize;
-  std::vector<PlanRec> ry, rj;
-  std::vector<int> ys_start, ys_dest;
-  for (int i = 0; i < ny; ++i)
-    for (int cI = 0; cI < 4; ++cI) {
-      ys_start.push_back((int)ry.size()); ys_dest.push_back(4 * i + cI);
-      for (int j = h.la[(size_t)cI * ny + i] - 1; j < h.le[(size_t)cI * ny + i]; ++j) {
-        const int k = h.mu[cI][j] - 1;
-        PlanRec R{}; R.a = h.a[cI][j]; R.mu = d.roff[cI] + k;
-        for (int r = 0; r < 4; ++r) R.n[r] = (r <= cI) ? h.ni[cI][(size_t)k * 6 + r] - 1 : ny;
-        R.fseg = i; R.fdest = i << 1; R.sseg = 4 * i + cI;
-        ry.push_back(R);
-        // Jacobian contributions of this term, slot by slot
-        for (int sl = 0; sl <= cI; ++sl) {
-          PlanRec Q{}; Q.a = R.a; Q.mu = R.mu;
-          for (int r = 0; r < 4; ++r) Q.n[r] = ny;
-          for (int r = 0; r < cI; ++r) Q.n[r] = R.n[(sl + 1 + r) % (cI + 1)];
-          const int col = R.n[sl];
-          Q.fseg = i * N + col;   // element key, replaced by a dense id below
-          rj.push_back(Q);
-        }
-      }
-    }
-  ys_start.push_back((int)ry.size());
-  for (int i = 0; i < ny; ++i) {   // every diagonal element exists (jac = mult*d + diag)
-    bool have = false;
-    for (const PlanRec &Q : rj) if (Q.fseg == i * N + i) { have = true; break; }
-    if (!have) { PlanRec Q{}; Q.a = 0.0; Q.mu = 0; for (int r = 0; r < 4; ++r) Q.n[r] = ny; Q.fseg = i * N + i; rj.push_back(Q); }
-  }
-  std::stable_sort(rj.begin(), rj.end(), [](const PlanRec &x, const PlanRec &y) { return x.fseg < y.fseg; });
-  std::vector<int> js_start, js_dest;
-  int id = -1, prev = -1;
-  for (size_t r = 0; r < rj.size(); ++r) {
-    const int key = rj[r].fseg;
-    if (key != prev) {
-      ++id; prev = key;
-      const int i0 = key / N, col = key % N;
-      js_start.push_back((int)r); js_dest.push_back(((col << 10 | i0) << 1) | (i0 == col ? 1 : 0));   // device: column*ld + slot(row)
-    }
-    rj[r].fseg = id; rj[r].sseg = id; rj[r].fdest = js_dest.back();
-  }
-  js_start.push_back((int)rj.size());
-  PlanHost py = make_plan(ry, NT, ny, ys_start, ys_dest), pj = make_plan(rj, NT, ny, js_start, js_dest);
-  int rc = upload_plan(c->pby, c->dn.py, py); if (rc) return rc;
-  rc = upload_plan(c->pbj, c->dn.pj, pj); if (rc) return rc;
-  c->ld = ld; c->dn.ld = ld;
-  c->npart = std::max(std::max(py.npart, pj.npart), std::max(2 * std::max(ny, c->dn.nffr) + 2, 128));
-  return XB_OK;
-}
-
 extern "C" {
 static int configure_launch(xb_ctx *c) {
   const int ny = c->dn.ny, N = c->dn.msize;
@@ -823,11 +626,13 @@ static int configure_launch(xb_ctx *c) {
   // leading dimension of the shared tile: 4 (mod 8) makes the DMMA fragment accesses of the trailing update
   // (and the column accesses everywhere else) bank-conflict free
   int ld_tile = N; while ((ld_tile & 7) != 4) ++ld_tile;
-  int rc = build_plans(c, c->threads, ld_tile); if (rc) return rc;
+  int rc = build_plans(c, c->dn, c->pby, c->pbj, c->threads, ld_tile, &c->npart, nullptr); if (rc) return rc;
+  c->ld = c->dn.ld;
   SmemOff L = smem_layout(ny, N, c->ld, c->npart, true, c->dn.nzs);
   c->jac_in_smem = (N <= 192 && c->threads >= ((N + 31) / 32) * 32 && (size_t)L.total + 64 <= max_smem) ? 1 : 0;
   if (!c->jac_in_smem) {
-    rc = build_plans(c, c->threads, N); if (rc) return rc;
+    rc = build_plans(c, c->dn, c->pby, c->pbj, c->threads, N, &c->npart, nullptr); if (rc) return rc;
+    c->ld = c->dn.ld;
     L = smem_layout(ny, N, c->ld, c->npart, false, c->dn.nzs);
   }
   {  // whatever shared memory is left caches csect (the tail of the reaction list: 2-, 3-, 4-body rates first)
@@ -886,9 +691,19 @@ int xb_ctx_create(const xb_net *net, const xb_ctl *ctl, int32_t nzevolve, int32_
   dc.kitmx = ctl->kitmx; dc.ijac = ctl->ijac; dc.iconvc = ctl->iconvc; dc.changemx = ctl->changemx;
   dc.changemxt = ctl->changemxt; dc.yacc = ctl->yacc; dc.tolm = ctl->tolm; dc.tolc = ctl->tolc; dc.tolt9 = ctl->tolt9;
   dc.ymin = ctl->ymin; dc.tdel_maxmult = ctl->tdel_maxmult;
+  // limits of the kernels: the global-memory LU covers blockDim*2 >= msize+1 rows, the Jacobian plans pack the row of a
+  // destination in 10 bits, species indices of the term plans in 16
+  const int msize = net->h.ny + (ctl->iheat > 0 ? 1 : 0);
+  if (msize + 1 > XB_MAX_THREADS * 2 || msize > 1023) {
+    delete c;
+    return fail(XB_ERR_UNSUPPORTED, "networks with more than " + std::to_string(XB_MAX_THREADS * 2 - 1) +
+                                        " equations per zone are not supported by this build (msize = " + std::to_string(msize) + ")");
+  }
   int rc = upload_network(c);
   if (rc == XB_OK) rc = configure_launch(c);
-  if (rc != XB_OK) { delete c; return rc; }
+  // structured LU for the fused evolve (fast arithmetic only; the module-level drop-ins stay dense, LAPACK semantics)
+  if (rc == XB_OK && ctl->solver == 1 && ctl->arith == 0) rc = xb_slu_configure(c);
+  if (rc != XB_OK) { std::string msg = g_err; xb_ctx_destroy(c); g_err = msg; return rc; }
   cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
   *ctx = c;
   return XB_OK;
@@ -906,6 +721,7 @@ void xb_ctx_destroy(xb_ctx *c) {
   c->irev.release(); c->iffn.release(); c->la.release(); c->le.release();
   for (int k = 0; k < 4; ++k) { c->a[k].release(); c->mu[k].release(); for (int r = 0; r < 4; ++r) c->nn[k][r].release(); }
   c->scratch.release(); c->phase.release(); c->counter.release();
+  xb_slu_release(c);
   DevBuf<double> *db[] = {&c->m_yt, &c->m_t9t, &c->m_rhot, &c->m_ext, &c->m_yet, &c->m_csect, &c->m_qk, &c->m_ydot, &c->m_jac,
                           &c->m_rhs, &c->m_diag, &c->m_mult, &c->m_dcsect, &c->m_eos, &c->m_t9dot, &c->m_y, &c->m_t9,
                           &c->m_tdel, &c->z_th, &c->z_t9h, &c->z_rhoh, &c->z_tstart, &c->z_tstop,
@@ -988,6 +804,7 @@ static int launch_module(xb_ctx *c, int zlo, int zhi, const int32_t *mask) {
   ma.tdel = c->m_tdel.p; ma.nh = c->m_nh.p; ma.inr = c->m_inr.p; ma.kcnt = c->m_kcnt.p; ma.flx = c->m_flx.p;
   std::lock_guard<std::mutex> lock(g_launch_mu);
   { int rcb = bind_constants(c); if (rcb) return rcb; }
+  CUDA_TRY(cudaEventRecord(c->ev0));
   if (c->ctl.arith) {
     CUDA_TRY(cudaFuncSetAttribute(module_kernel<true, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     module_kernel<true, OP><<<nz, c->threads, c->smem_bytes>>>(ma, c->scr);
@@ -997,6 +814,7 @@ static int launch_module(xb_ctx *c, int zlo, int zhi, const int32_t *mask) {
   }
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(c->ev1));
   return XB_OK;
 }
 
@@ -1268,11 +1086,15 @@ int xb_zones_upload(xb_ctx *c, const xb_zones *z, int32_t hist_cap) {
 int xb_evolve_resident(xb_ctx *c, float *kernel_ms) {
   if (!c || c->nzone < 1) return fail(XB_ERR_ARG, "xb_evolve_resident: no zones uploaded");
   CUDA_TRY(cudaSetDevice(c->device));
+  if (c->slu_on) return xb_slu_evolve(c, kernel_ms);
   CUDA_TRY(cudaMemsetAsync(c->counter.p, 0, sizeof(int)));
   CUDA_TRY(cudaMemsetAsync(c->phase.p, 0, PH_COUNT * sizeof(unsigned long long)));
   const int grid = std::min(c->grid, c->nzone);
   std::unique_lock<std::mutex> lock(g_launch_mu);
   { int rcb = bind_constants(c); if (rcb) return rcb; }
+  // the attribute belongs to the function, not to the context: another live context may have lowered it
+  CUDA_TRY(cudaFuncSetAttribute(c->ctl.arith ? evolve_fn<true>() : evolve_fn<false>(),
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
   CUDA_TRY(cudaEventRecord(c->ev0));
   if (c->ctl.arith)
     evolve_kernel<true><<<grid, c->threads, c->smem_bytes>>>(c->dz, c->dout, c->scr, c->counter.p);
@@ -1340,10 +1162,61 @@ int xb_last_copy_bytes(xb_ctx *c, int64_t *h2d, int64_t *d2h) {
   return XB_OK;
 }
 
+// duration of the last kernel this context launched (module-level drop-in or evolve), CUDA events on its stream
+int xb_last_kernel_ms(xb_ctx *c, float *ms) {
+  if (!c || !ms) return fail(XB_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaEventSynchronize(c->ev1));
+  CUDA_TRY(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return XB_OK;
+}
+
+int xb_solver_info(xb_ctx *c, double *info8) {
+  if (!c || !info8) return fail(XB_ERR_ARG, "null argument");
+  for (int k = 0; k < 8; ++k) info8[k] = 0.0;
+  if (c->slu_on) {
+    info8[0] = 1.0; info8[1] = c->slu_tab.n; info8[2] = c->slu_tab.nstore; info8[3] = c->slu_tab.flops;
+    info8[4] = c->slu_per_sm; info8[5] = c->slu_tab.nbord; info8[6] = c->dn_slu.slu.nwl; info8[7] = c->dn_slu.nrtot - c->dn_slu.cs_lo;
+  }
+  return XB_OK;
+}
+
+// Structured-LU tables of a network (tests): heat = 1 adds the T9 equation.  what = "perm","pos","rf","cf","lo","uo",
+// "rstart","cstart","rlist","clist" (pairs), "sizes" (n, nstore, nbord)
+int xb_slu_table(const xb_net *net, int32_t heat, const char *what, int32_t *out, int64_t cap, int64_t *n) {
+  if (!net || !what) return fail(XB_ERR_ARG, "xb_slu_table: null argument");
+  SluTables t;
+  structured_lu_tables(net->h, heat, t);
+  std::string w(what);
+  if (w == "perm") return copy_out(t.perm, out, cap, n);
+  if (w == "pos") return copy_out(t.pos, out, cap, n);
+  if (w == "rf") return copy_out(t.rf, out, cap, n);
+  if (w == "cf") return copy_out(t.cf, out, cap, n);
+  if (w == "lo") return copy_out(t.lo, out, cap, n);
+  if (w == "uo") return copy_out(t.uo, out, cap, n);
+  if (w == "rstart") return copy_out(t.rstart, out, cap, n);
+  if (w == "cstart") return copy_out(t.cstart, out, cap, n);
+  if (w == "rlist") return copy_out(t.rlist, out, cap, n);
+  if (w == "clist") return copy_out(t.clist, out, cap, n);
+  if (w == "sizes") { std::vector<int32_t> v{t.n, t.nstore, t.nbord, (int32_t)t.flops}; return copy_out(v, out, cap, n); }
+  return fail(XB_ERR_ARG, "xb_slu_table: unknown key " + w);
+}
+
+// Solves nz dense systems a[nz][n*n] (column-major, equation order; entries outside the structural envelope must be
+// zero) x = b with the structured LU of this context (tests / diagnostics).  mode: 0 = right-hand side carried through
+// the factorisation, 1 = factor then solve, 2/3 = the dense fallback likewise.  flags[nz]: bit 0 = threshold test
+// failed, bit 1 = a non-zero outside the envelope was dropped, bit 2 = singular in the dense fallback.
+int xb_slu_solve(xb_ctx *c, int32_t nz, const double *a, const double *b, double *x, int32_t *flags, int32_t mode) {
+  if (!c || !a || !b || !x || !flags) return fail(XB_ERR_ARG, "xb_slu_solve: null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  return xb_slu_solve_dense_test(c, nz, a, b, x, flags, mode);
+}
+
 int xb_launch_config(xb_ctx *c, int32_t *cfg6) {
   if (!c || !cfg6) return fail(XB_ERR_ARG, "null argument");
   cfg6[0] = c->grid; cfg6[1] = c->threads; cfg6[2] = (int32_t)c->smem_bytes; cfg6[3] = c->jac_in_smem; cfg6[4] = c->nsm;
   cfg6[5] = c->dn.msize;
+  if (c->slu_on) { cfg6[0] = c->slu_grid; cfg6[1] = c->slu_threads; cfg6[2] = (int32_t)c->slu_smem; cfg6[3] = 1; }   // the evolve launch
   return XB_OK;
 }
 

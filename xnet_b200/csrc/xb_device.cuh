@@ -32,6 +32,15 @@ struct DevPlan {
 // byte offsets of the zone working set inside the CTA's dynamic shared memory
 struct SmemOff { int scal, jac, y, yt, ydot, rhs, rdiag, part, prow, indx, orig, pos, fhs, lu_s, lu_u, lds2, cs, total; };
 
+// structured LU (xb_slu.cuh): sizes, the 16-bit index tables staged into every CTA's shared memory, species -> position
+struct DevSlu {
+  int ntest;                                 // rows 0..ntest-1 are subject to the threshold test (all but the T9 row)
+  int on, n, nstore, nbord, nwl, force_fb;   // nwl: warps that factor; force_fb > 0: every force_fb-th LU takes the dense fallback (tests)
+  int off_tab;                               // byte offset of the staged tables in shared memory
+  const unsigned short *tab16;               // [6][n]: rf, cf, lo, uo, rhi, chi
+  const int *pos;                            // [n] equation (species, then T9) -> position in the reordered system
+};
+
 struct DevNet {
   int ny, nrtot, nffn, msize, ld, nffr, tile;
   int cs_lo;                 // reactions [cs_lo, nrtot) have their rate cached in shared memory
@@ -65,6 +74,7 @@ struct DevNet {
   const double *sc_zw, *sc_zi;    // [nrtot] reaction charge parameters zeta_w, zeta_i (0 for one-reactant reactions)
   const int2 *sc_iz;         // [nrtot] x = iz1 | iz2<<8 | iz3<<16 | iz4<<24, y = composite charge
   int nzs;                   // entries of the per-charge strong-screening table
+  DevSlu slu;                // structured-LU variant only (xb_slu.cu)
   // matched-pair fluxes (xnet_flux.F90:67-150): set m sums entries [fl_start[m], fl_start[m+1]) in reaction order
   int mflx;
   const int *fl_start;       // [mflx+1]
@@ -107,8 +117,9 @@ struct DevScratch {
 
 // Zone-invariant state lives in constant memory (uploaded before every launch of a context): device
 // code reads it through the constant bank instead of chasing kernel-parameter pointers.
-__constant__ DevNet c_net;
-__constant__ DevCtl c_ctl;
+// one copy per translation unit (the dense kernels and the structured-LU kernel bind their own)
+static __constant__ DevNet c_net;
+static __constant__ DevCtl c_ctl;
 extern __shared__ __align__(16) unsigned char xb_smem[];
 
 enum Phase { PH_RATES = 0, PH_YDERIV, PH_JAC, PH_LU, PH_BKSUB, PH_OTHER, PH_TOTAL, PH_ZONES,

@@ -61,6 +61,20 @@ void match_react(Network &net);
 void flux_init(Network &net);
 // fills slu_perm, slu_rowfirst, slu_colfirst, slu_doubles from the species <-> reaction maps
 void structured_lu_plan(Network &net);
+// Tables of the structured LU for a system of N = ny (+1 with self-heating: the T9 equation is the last row and
+// column, both full) equations in the light-particles-last order.  Storage ("skyline"): for every column j the part
+// of U in rows cf[j]..j, for every row i the part of L in columns rf[i]..i-1; element (i,j) of the permuted matrix
+// lives at  i <= j ? uo[j] + i : lo[i] + j.  Elimination without interchanges never leaves this envelope.
+struct SluTables {
+  int n = 0, nstore = 0, nbord = 0;           // order, doubles of the store, trailing rows/columns factored with pivoting
+  std::vector<int32_t> perm, pos;             // [n] position -> equation, equation -> position (0-based; equation ny = T9)
+  std::vector<int32_t> rf, cf;                // [n] first stored column of row i / first stored row of column j
+  std::vector<int32_t> lo, uo;                // [n] address bases (see above)
+  std::vector<int32_t> rstart, cstart;        // [n+1] per pivot k: rows i > k with rf[i] <= k / columns j > k with cf[j] <= k
+  std::vector<int32_t> rlist, clist;          // [2 * count] pairs (i, lo[i]) / (j, uo[j]), ascending
+  double flops = 0;                           // of one factorisation (2 per multiply-add, 1 per scaled multiplier)
+};
+void structured_lu_tables(const Network &net, int heat, SluTables &t);
 int index_from_name(const Network &net, const std::string &name);
 void load_helm_table(const std::string &path, Network &net);
 

@@ -411,6 +411,43 @@ void structured_lu_plan(Network &net) {
   }
 }
 
+// Everything the structured-LU kernels index with (see SluTables).  The pattern is the structural one of
+// structured_lu_plan (species i depends on every reactant of every reaction registered with it); with self-heating the
+// T9 row and column are full.  The light particles and T9 form the pivoted border.
+void structured_lu_tables(const Network &net, int heat, SluTables &t) {
+  const int ny = net.ny, n = ny + (heat ? 1 : 0);
+  t = SluTables();
+  t.n = n;
+  int nlight = 0;
+  for (int i = 0; i < ny; ++i) if (net.zz[i] <= 2.0 && net.aa[i] <= 4.0) ++nlight;
+  t.nbord = nlight + (heat ? 1 : 0);
+  t.perm.resize(n); t.pos.resize(n);
+  for (int p = 0; p < ny; ++p) t.perm[p] = net.slu_perm[p] - 1;
+  if (heat) t.perm[ny] = ny;
+  for (int p = 0; p < n; ++p) t.pos[t.perm[p]] = p;
+  t.rf.resize(n); t.cf.resize(n);
+  for (int p = 0; p < ny; ++p) { t.rf[p] = net.slu_rowfirst[p] - 1; t.cf[p] = net.slu_colfirst[p] - 1; }
+  if (heat) { t.rf[ny] = 0; t.cf[ny] = 0; }
+  // the border rows and columns are stored in full: the pivoting inside the border exchanges whole rows
+  for (int p = n - t.nbord; p < n; ++p) { t.rf[p] = 0; t.cf[p] = 0; }
+  t.lo.resize(n); t.uo.resize(n);
+  int o = 0;
+  for (int p = 0; p < n; ++p) {
+    t.uo[p] = o - t.cf[p]; o += p - t.cf[p] + 1;     // rows cf..p of column p
+    t.lo[p] = o - t.rf[p]; o += p - t.rf[p];         // columns rf..p-1 of row p
+  }
+  t.nstore = o;
+  t.rstart.assign(n + 1, 0); t.cstart.assign(n + 1, 0);
+  for (int k = 0; k < n; ++k) {
+    t.rstart[k] = (int)t.rlist.size() / 2; t.cstart[k] = (int)t.clist.size() / 2;
+    for (int i = k + 1; i < n; ++i) if (t.rf[i] <= k) { t.rlist.push_back(i); t.rlist.push_back(t.lo[i]); }
+    for (int j = k + 1; j < n; ++j) if (t.cf[j] <= k) { t.clist.push_back(j); t.clist.push_back(t.uo[j]); }
+    const double nr = (double)(t.rlist.size() / 2 - t.rstart[k]), nc = (double)(t.clist.size() / 2 - t.cstart[k]);
+    t.flops += nr + 2.0 * nr * nc;
+  }
+  t.rstart[n] = (int)t.rlist.size() / 2; t.cstart[n] = (int)t.clist.size() / 2;
+}
+
 namespace {
 void read_ffn(const std::string &dir, int iweak0, Network &net) {
   const int nf = std::max(net.nffn, 1);

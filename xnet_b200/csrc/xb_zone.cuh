@@ -6,6 +6,9 @@
 #include "xb_math.cuh"
 #include "xb_lu.cuh"
 #include "xb_eos.cuh"
+#ifdef XB_SLU
+#include "xb_slu.cuh"
+#endif
 
 namespace xb {
 
@@ -28,6 +31,8 @@ struct ZoneScalars {
   int kmon[5], ktot[5];
   int inr, its, flag, piv, info, tile_ctr;
   int rhs_in_jac;            // global-memory Jacobian: the right-hand side rides as column N of the per-CTA scratch (fused path)
+  int slu_fail, lu_dense, nlu_zone;   // structured LU: threshold test failed / factors are the dense fallback's / factorisations so far
+  int slu_ipb[8];            // interchanges of the border block
   long long ph[PH_COUNT];    // see enum Phase
   long long tmark, dmark;
 };
@@ -826,12 +831,92 @@ __device__ __forceinline__ void jacobian_build_impl(const DevNet &net, const Zon
     __syncthreads();
   }
 }
+#ifdef XB_SLU
+// Structured variant: the same term plan, destinations = addresses in the skyline store (static reordering, no slots).
+template <bool STRICT>
+__device__ __noinline__ void jacobian_build_cta() {
+  static_assert(!STRICT, "the structured LU is a fast-arithmetic path");
+  XB_ZONE_PROLOGUE
+  const DevSlu &D = net.slu;
+  const DevPlan &P = net.pj;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double *S = zm.jac, *part = zm.part;
+  XB_ASSUME_SHARED(S);
+  const bool heat = ctl.iheat > 0;
+  const double diag = heat ? 0.0 : zm.s->rdt, mult = heat ? 1.0 : zm.s->mult;
+  {
+    const int n2 = D.nstore >> 1;
+    double2 *S2 = reinterpret_cast<double2 *>(S);
+    for (int e = tid; e < n2; e += nt) S2[e] = make_double2(0.0, 0.0);
+    if (tid == 0 && (D.nstore & 1)) S[D.nstore - 1] = 0.0;
+  }
+  __syncthreads();
+  plan_run_fast(P, zm.csect, zm.cs_sm, net.cs_lo, zm.yt, [&](unsigned ctl_, double acc) {
+    if ((ctl_ & 3u) == 1u) S[ctl_ >> 3] = fma(mult, acc, (ctl_ & 4u) ? diag : 0.0);
+    else part[ctl_ >> 3] = acc;
+  });
+  __syncthreads();
+  for (int m = tid; m < P.nmulti; m += nt) {
+    double sm = 0.0;
+    for (int q = P.multi_start[m]; q < P.multi_start[m + 1]; ++q) sm += part[q];
+    const int d = P.multi_dest[m];
+    S[d >> 1] = fma(mult, sm, (d & 1) ? diag : 0.0);
+  }
+  if (tid == 0) zm.s->ktot[2] += 1;
+  __syncthreads();
+  if (heat) {
+    const SluIdx I = slu_idx();
+    const int n = I.n, ny = net.ny, nh = I.nh;
+    const DevPlan &Py = net.py;
+    const int uoT = (int)I.uo[n - 1];       // column n-1: d ydot_i / d T9 (xnet_jacobian_dense.F90:343-399)
+    const int *__restrict__ spos = D.pos;
+    plan_run_fast(Py, zm.dcsect, zm.cs_sm, net.nrtot, zm.yt, [&](unsigned ctl_, double acc) {
+      if ((ctl_ & 3u) == 1u) S[uoT + spos[ctl_ >> 3]] = acc; else part[ctl_ >> 3] = acc;
+    });
+    __syncthreads();
+    for (int m = tid; m < Py.nmulti; m += nt) {
+      double sm = 0.0;
+      for (int q = Py.multi_start[m]; q < Py.multi_start[m + 1]; ++q) sm += part[q];
+      S[uoT + spos[Py.multi_dest[m] >> 1]] = sm;
+    }
+    __syncthreads();
+    // row n-1: d t9dot / d(y_j, T9) = - sum_i mex_i dydotdy(i, j) / cv over the stored rows of column j
+    double *mexp = part;                    // mass excesses in position order, 0 for the T9 row
+    for (int i = tid; i < n; i += nt) mexp[i] = 0.0;
+    __syncthreads();
+    for (int i = tid; i < ny; i += nt) mexp[spos[i]] = net.mex[i];
+    __syncthreads();
+    const double cv = zm.s->cv;
+    for (int pj = tid; pj < n; pj += nt) {
+      double s0 = 0.0;
+      const int uoj = (int)I.uo[pj];
+      for (int r = (int)I.cf[pj]; r <= pj; ++r) s0 = fma(mexp[r], S[uoj + r], s0);
+      if (pj < nh) {
+        for (int i = pj + 1; i <= (int)I.rhi[pj]; ++i) if ((int)I.rf[i] <= pj) s0 = fma(mexp[i], S[(int)I.lo[i] + pj], s0);
+        for (int i = nh; i < n; ++i) s0 = fma(mexp[i], S[(int)I.lo[i] + pj], s0);
+      } else {
+        for (int i = pj + 1; i < n; ++i) s0 = fma(mexp[i], S[(int)I.lo[i] + pj], s0);
+      }
+      const double v = -s0 / cv;
+      if (pj < n - 1) S[(int)I.lo[n - 1] + pj] = v; else S[uoj + pj] = v;
+    }
+    __syncthreads();
+    // jacobian_scale: jac = mult * dydotdy^T + diag on the diagonal
+    const double rdt = zm.s->rdt, m = zm.s->mult;
+    for (int e = tid; e < D.nstore; e += nt) S[e] *= m;
+    __syncthreads();
+    for (int p = tid; p < n; p += nt) S[(int)I.uo[p] + p] += rdt;
+    __syncthreads();
+  }
+}
+#else
 template <bool STRICT>
 __device__ __noinline__ void jacobian_build_cta() {
   XB_ZONE_PROLOGUE
   if (net.tile) jacobian_build_impl<STRICT, true>(net, zm, zm.jac);
   else jacobian_build_impl<STRICT, false>(net, zm, zm.jac);
 }
+#endif
 
 // with_rhs: zm.rhs rides through the factorisation as column N of the tile (forward solve for free)
 template <bool STRICT>
@@ -889,6 +974,42 @@ __device__ __noinline__ void step_be_cta() {
       jacobian_build_cta<STRICT>();
       XB_PHASE_END(zm, PH_JAC);
     }
+#ifdef XB_SLU
+    // structured LU: equation k sits at position spos[k] of the reordered system (T9 last); the solution comes back in
+    // the same order
+    const int *__restrict__ spos = net.slu.pos;
+    auto fill_rhs = [&]() {
+      if (kit > 1) {
+        for (int k = tid; k < ny; k += nt) zm.rhs[spos[k]] = A::mad(A::sub(zm.y[k], zm.yt[k]), rdt, zm.ydot[k]);
+        if (ctl.iheat > 0 && tid == 0) zm.rhs[N - 1] = A::mad(A::sub(s->t9, s->t9t), rdt, s->t9dot);
+      } else {
+        for (int k = tid; k < ny; k += nt) zm.rhs[spos[k]] = zm.ydot[k];
+        if (ctl.iheat > 0 && tid == 0) zm.rhs[N - 1] = s->t9dot;
+      }
+    };
+    fill_rhs();
+    if (tid == 0 && rebuild) { s->slu_fail = 0; s->nlu_zone += 1; }
+    __syncthreads();
+    if (rebuild) {
+      slu_factor(zm.jac, zm.rhs, zm.rdiag, s->slu_ipb, &s->slu_fail, true, net.slu.nwl);
+      __syncthreads();
+      const bool forced = net.slu.force_fb > 0 && (s->nlu_zone % net.slu.force_fb) == 0;
+      if (s->slu_fail != 0 || forced) {
+        // a column failed the threshold test: this factorisation is redone by the dense partial-pivoting LU
+        jacobian_build_cta<STRICT>();
+        fill_rhs();
+        if (tid == 0) { s->ktot[2] -= 1; s->lu_dense = 1; s->ph[PH_SPARE] += 1; }
+        __syncthreads();
+        slu_dense_factor(zm.jac, zm.rhs, s->g_jac, reinterpret_cast<int *>(s->g_jac + (size_t)(N + 1) * N), zm.part, &s->info);
+      } else if (tid == 0) s->lu_dense = 0;
+      __syncthreads();
+      XB_PHASE_END(zm, PH_LU);
+    }
+    if (s->lu_dense) slu_dense_solve(s->g_jac, reinterpret_cast<const int *>(s->g_jac + (size_t)(N + 1) * N), zm.rhs, rebuild);
+    else slu_solve(zm.jac, zm.rhs, zm.rdiag, s->slu_ipb, rebuild);
+    __syncthreads();
+    XB_PHASE_END(zm, PH_BKSUB);
+#else
     if (kit > 1) {
       for (int k = tid; k < ny; k += nt) zm.rhs[zm.pos[k]] = A::mad(A::sub(zm.y[k], zm.yt[k]), rdt, zm.ydot[k]);
       if (ctl.iheat > 0 && tid == 0) zm.rhs[zm.pos[ny]] = A::mad(A::sub(s->t9, s->t9t), rdt, s->t9dot);
@@ -903,13 +1024,18 @@ __device__ __noinline__ void step_be_cta() {
     }
     bksub_cta<STRICT>(zm, N, rebuild && (zm.tile || s->rhs_in_jac));
     XB_PHASE_END(zm, PH_BKSUB);
+#endif
     {
       const double *aa = net.aa;
       const double ymin = ctl.ymin;
       double *yt = zm.yt;
       const double *rhs = zm.rhs;
       block_sum2<STRICT>(ny, [&](int k, double &ta, double &tb) {
+#ifdef XB_SLU
+        const double dy = rhs[spos[k]];
+#else
         const double dy = rhs[k];
+#endif
         const double ytmp = A::add(yt[k], dy);
         double rel, ynew;
         if (ytmp < ymin) { ynew = 0.0; rel = 0.0; }
@@ -926,7 +1052,7 @@ __device__ __noinline__ void step_be_cta() {
       const double toln = (ctl.iconvc != 0) ? ctl.tolc : ctl.tolm;
       s->relt9 = 0.0;
       if (ctl.iheat > 0) {   // temperature update and its convergence measure (xnet_integrate_be.F90:402-416)
-        s->dt9 = zm.rhs[ny];
+        s->dt9 = zm.rhs[ny];   // T9 is equation ny in both orderings (the structured LU keeps it last)
         s->t9t = A::add(s->t9t, s->dt9);
         s->relt9 = (fabs(s->t9t) > 2.2250738585072014e-308) ? fabs(A::div(s->dt9, s->t9t)) : 0.0;
       }
@@ -1208,7 +1334,11 @@ __device__ __forceinline__ void full_net_cta(const DevZones &zn, const DevOut &o
     }
   }
   for (int k = tid; k <= net.nffn; k += nt) zm.qkffn[k] = 0.0;
+#ifndef XB_SLU
   for (int k = tid; k < net.msize; k += nt) { zm.orig[k] = k; zm.pos[k] = k; }   // no pivot history yet
+#else
+  if (tid == 0) { s->lu_dense = 0; s->nlu_zone = 0; s->slu_fail = 0; }
+#endif
   __syncthreads();
   if (tid == 0) {
     if (restart) { double t9x, rhox; t9rhofind<STRICT>(s, s->t, &s->nt, &t9x, &rhox); }
@@ -1221,6 +1351,9 @@ __device__ __forceinline__ void full_net_cta(const DevZones &zn, const DevOut &o
   benuc_cta<STRICT>(zm, zm.y, &s->enm);
   if (tid == 0) s->enold = restart ? s->enm : 0.0;
   __syncthreads();
+  // constant conditions without self-heating: the rates are evaluated once, in the first timestep call (tdel = 0),
+  // and never by step_be; a restarted zone has tdel != 0, so the rates of its state are evaluated here
+  if (restart && s->nh == 1 && ctl.iheat == 0) cross_sect_cta<STRICT>();
   if (!restart) hist_put<STRICT>(out, iz, ny, 0, zm);
   int mykstep = 0;
   bool lzsolve = true;

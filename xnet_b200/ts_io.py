@@ -57,6 +57,9 @@ def write_ev(path, net, hist, zone=0, names=()):
     the mass fractions of the species in `names` (the control file's output nuclei; 5-character names as in sunet,
     matched after stripping blanks)."""
     n = int(hist['hist_n'][zone])
+    cap = hist['hist_kstep'].shape[1]
+    if n > cap:
+        raise ValueError('history overflow: %d records, capacity %d' % (n, cap))
     aa = net.dtable('aa')
     known = [s.strip().lower() for s in net.names()] if hasattr(net, 'names') else None
     idx = []
