@@ -493,7 +493,7 @@ def main():
             'bound_note': 'FP64 compute (the LU): neither HBM nor the bf16 tensor peak bounds this path; the FP64 tensor '
                           'pipe (DMMA.8x8x4) has the same 64 FMA/clk/SM peak as DFMA on B200 (profiles/r02_dmma_probe.txt)',
             'peak_source': 'FP64 FMA peak measured live on this GPU (DFMA microbenchmark); MEASURED_PEAKS.json has only bf16/HBM entries',
-            'phase_share': {k: round(ph[k] / phase_tot, 4) for k in ('rates', 'yderiv', 'jac', 'lu', 'bksub', 'other')},
+            'phase_share': {k: round(ph[k] / phase_tot, 4) for k in ('rates', 'yderiv', 'jac', 'lu', 'bksub', 'other', 'lu_panel', 'lu_swap_trsm', 'lu_gemm')},
             'cycles_per_newton_iter': phase_tot / max(newton, 1.0),
             'traffic_note': 'dram__bytes of one launch from ncu: profiles/r02_evolve_ncu.txt (the Jacobian, csect and the zone state '
                             'never touch HBM; HBM sees the restart state in, the results out and the cold misses of the tables)',
@@ -505,6 +505,11 @@ def main():
         roof['actual_lu_tflops'] = slu['flops'] * nlu / (ms_launch * 1e-3) / 1e12
         roof['structured'] = slu
         roof['dense_fallbacks_per_lu'] = ph['spare'] / max(nlu, 1.0)
+        nfb = max(ph['spare'], 1.0)
+        roof['fallback_stats'] = {'count': ph['spare'], 'mean_first_violated_column': ph['dbg0'] / nfb,
+                                  'mean_lu_number_in_zone': ph['dbg1'] / nfb, 'mean_newton_iteration': ph['dbg2'] / nfb,
+                                  'cycles_per_fallback': ph['lu_swap_trsm'] / nfb,
+                                  'phase_note': 'lu_panel = failed structured attempts, lu_swap_trsm = attempts + dense fallback'}
     else:
         roof['pivot_steps_per_lu'] = ph['spare'] / max(nlu, 1.0)
     line = {

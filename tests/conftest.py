@@ -41,6 +41,9 @@ PROBLEMS = {
     'sn160_heat': ('test_settings_heat', 'setup_heat_sn160'),
     # logft weak rates + self-heating + screening on SN231 (test/test_xnet.sh test 53; BASELINE configs[3])
     'sn231_logft': ('test_settings_logft', 'setup_logft_sn231'),
+    # 16 zones with their own trajectory / abundance files, self-heating + screening, zone batching
+    # (test/test_xnet.sh tests 61/62: test_settings_batch + setup_batch_torch47; BASELINE configs[1] batch variant)
+    'torch47_batch': ('test_settings_batch', 'setup_batch_torch47'),
 }
 
 
@@ -75,6 +78,23 @@ def gpu_problem(built):
             net = X.Network(os.path.join(DATA, ctl['data_dir']), ctl['iweak0'])
             fx = [X.load_fixture(net, os.path.join(DATA, a), os.path.join(DATA, t))
                   for a, t in list(zip(ctl['inab_file'], ctl['thermo_file']))[:1]]
+            cache[name] = (ctl, net, fx)
+        return cache[name]
+    return get
+
+
+@pytest.fixture(scope='session')
+def gpu_problem_all(built):
+    """As gpu_problem, with EVERY fixture of the control file (multi-zone set-ups)."""
+    import xnet_b200 as X
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            ctl = X.read_controls(control_text(*PROBLEMS[name]))
+            net = X.Network(os.path.join(DATA, ctl['data_dir']), ctl['iweak0'])
+            fx = [X.load_fixture(net, os.path.join(DATA, a), os.path.join(DATA, t))
+                  for a, t in zip(ctl['inab_file'], ctl['thermo_file'])]
             cache[name] = (ctl, net, fx)
         return cache[name]
     return get

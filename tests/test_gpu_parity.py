@@ -137,6 +137,131 @@ def test_fast_end_state(gpu_problem, oracle_problem, name):
     ctx.close()
 
 
+# ---------------------------------------------------------------- whole trajectories (round-1 verdict item 1)
+def _sha(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).astype(a.dtype.newbyteorder('<')).tobytes()).hexdigest()
+
+
+def test_strict_xrb304_complete_trajectory_golden(gpu_problem):
+    """BASELINE configs[4]: XRB304 over the complete th_fisker_aboveign_b1 trajectory in strict arithmetic against the
+    committed full-length golden of the portable-math oracle (tests/golden/make_golden_full.py): every 50th record
+    explicitly, every record through SHA-256 digests of the complete tdel / T9 / y / kmon histories."""
+    g = np.load(os.path.join(GOLD, 'ts_xrb304_full_pm.npz'))
+    n = int(g['n'])
+    X, ctl, net, fx, ctx = _ctx(gpu_problem, 'xrb304', 1, arith=1)
+    r = ctx.full_net(X.build_zone_set(fx, nzone=1), hist_cap=n + 8)
+    ctx.close()
+    assert int(r['hist_n'][0]) == n and r['status'][0] == -1
+    idx = g['idx']
+    assert np.array_equal(r['hist_kstep'][0, idx], g['kstep']) and np.array_equal(r['hist_t'][0, idx], g['t'])
+    assert np.array_equal(r['hist_tdel'][0, idx], g['tdel']) and np.array_equal(r['hist_y'][0, idx], g['y'])
+    assert np.array_equal(r['ktot'][0], g['ktot']) and np.array_equal(r['y'][0], g['y_final'])
+    assert _sha(r['hist_tdel'][0, :n]) == str(g['sha_tdel']) and _sha(r['hist_t9'][0, :n]) == str(g['sha_t9'])
+    assert _sha(r['hist_y'][0, :n]) == str(g['sha_y']) and _sha(r['hist_kmon'][0, :n]) == str(g['sha_kmon'])
+
+
+@pytest.mark.parametrize('name', ['torch47_batch', 'sn160_heat', 'sn231_logft'])
+def test_multi_fixture_strict_bit_exact(gpu_problem_all, oracle_problem, name):
+    """Jobs with K > 1 input fixtures (test/test_xnet.sh tests 61/62: 16 th_batch/ab_batch pairs with self-heating and
+    screening; the six C/O-burn trajectories of setup_heat_sn160; three of setup_logft_sn231): global zone z evolves
+    fixture z mod K.  2K zones, strict arithmetic, every zone bit-identical to the oracle's run of its fixture."""
+    import xnet_b200 as X
+    ctl, net, fx = gpu_problem_all(name)
+    K = len(fx)
+    assert K > 1
+    ctx = X.Context(net, ctl, nzevolve=1, arith=1)
+    cap = 2200
+    r = ctx.full_net(X.build_zone_set(fx, nzone=2 * K), hist_cap=cap)
+    ctx.close()
+    o = oracle_problem(name).run(nzone=K, hist_cap=cap, fast='pm', nthreads=0)
+    for z in range(2 * K):
+        f = z % K
+        n = int(o['hist_n'][f])
+        assert n <= cap and int(r['hist_n'][z]) == n, (z, n)
+        assert np.array_equal(r['hist_tdel'][z, :n], o['hist_tdel'][f, :n])
+        assert np.array_equal(r['hist_t9'][z, :n], o['hist_t9'][f, :n])
+        assert np.array_equal(r['hist_y'][z, :n], o['hist_y'][f, :n])
+        assert np.array_equal(r['ktot'][z], o['ktot'][f]) and r['status'][z] == -1
+
+
+_HIST = {}
+
+
+def _oracle_history(oracle_problem, name, build):
+    """complete run of one zone by one build of the oracle: False = strict IEEE + libm (the reference-faithful build),
+    True = -O3 -march=native (FMA contraction)"""
+    key = (name, build)
+    if key not in _HIST:
+        _HIST[key] = oracle_problem(name).run(nzone=1, hist_cap=6000, fast=build)
+    return _HIST[key]
+
+
+def _dev(a, b, n, floor):
+    """per-record deviation: max over Y > floor of |a - b| / b"""
+    ya, yb = a['hist_y'][0, :n], b['hist_y'][0, :n]
+    m = yb > floor
+    return np.where(m, np.abs(ya - yb) / np.where(m, yb, 1.0), 0.0).max(axis=1)
+
+
+@pytest.mark.parametrize('solver', [0, 1])
+@pytest.mark.parametrize('name,floor', [('sn160_scrn', 1e-20), ('sn160_heat', 1e-10), ('sn231_logft', 1e-10), ('xrb304', 1e-20)])
+def test_fast_complete_trajectory_vs_cpu_build_noise(gpu_problem, oracle_problem, name, floor, solver):
+    """The benched mode over the COMPLETE trajectory.  A fast-arithmetic run is one rounding of the reference's
+    algorithm; the reference's own CPU algorithm compiled with FMA contraction (-O3 -march=native) is another.  Per
+    accepted step, the deviation of the GPU run from the libm oracle is compared with the running maximum of the deviation
+    of that second CPU build from the same oracle: it must stay within C = 100 times that envelope (floored at 1e-11, the
+    level at which the two CPU builds start) -- i.e. the GPU is not a worse reproduction of the reference than the
+    reference recompiled.  Both solvers (dense threshold-pivoting LU, structured LU).  Also: the run finishes, its
+    accepted-step count is within 1 % of the oracle's, mass is conserved."""
+    ref = _oracle_history(oracle_problem, name, False)
+    alt = _oracle_history(oracle_problem, name, True)
+    import xnet_b200 as X
+    ctl, net, fx = gpu_problem(name)
+    ctx = X.Context(net, ctl, nzevolve=1, arith=0, solver=solver)
+    r = ctx.full_net(X.build_zone_set(fx, nzone=1), hist_cap=6000)
+    ctx.close()
+    nr, na, ng = int(ref['hist_n'][0]), int(alt['hist_n'][0]), int(r['hist_n'][0])
+    assert r['status'][0] == -1 and abs(ng - nr) <= max(2, 0.01 * nr)
+    n = min(nr, na, ng)
+    dg, da = _dev(r, ref, n, floor), _dev(alt, ref, n, floor)
+    env = np.maximum(np.maximum.accumulate(da), 1e-11)
+    ratio = float((dg / env).max())
+    k = int(np.argmax(dg / env))
+    print('\n%s solver %d: records ref/alt/gpu %d/%d/%d  max dev gpu %.3g  cpu-fma %.3g  worst ratio %.3g at record %d' % (
+        name, solver, nr, na, ng, dg.max(), da.max(), ratio, k))
+    assert ratio <= 100.0, (ratio, k, dg[k], env[k])
+    aa = net.dtable('aa')
+    assert abs((r['y'][0] * aa).sum() - 1.0) < 1e-8
+
+
+@pytest.mark.parametrize('name,stride', [('sn160_scrn', 9), ('sn160_heat', 5), ('sn231_logft', 7), ('xrb304', 23)])
+def test_fast_single_step_restart_all_configs(gpu_problem, oracle_problem, name, stride):
+    """test_fast_single_step_restart on the remaining configurations, sampling the whole trajectory (dense solver; the
+    structured solver has the same test in test_gpu_slu.py).  Reports the measured bounds."""
+    h = _oracle_history(oracle_problem, name, False)
+    n = int(h['hist_n'][0])
+    idx = np.arange(1, n - 1, stride)
+    rs = dict(t=h['hist_t'][0, idx], tdel=h['hist_tdel'][0, idx], t9=h['hist_t9'][0, idx], rho=h['hist_rho'][0, idx],
+              t9o=h['hist_t9'][0, idx - 1], y=h['hist_y'][0, idx], yo=h['hist_y'][0, idx - 1], kstep0=h['hist_kstep'][0, idx])
+    X, ctl, net, fx, ctx = _ctx(gpu_problem, name, 1, arith=0, kstmx=1)
+    zs = X.build_zone_set(fx, nzone=len(idx), zfix=np.zeros(len(idx), int), restart=rs)
+    r = ctx.full_net(zs, check=False)
+    ctx.close()
+    ref = h['hist_y'][0, idx + 1]
+    e = np.abs(r['y'] - ref).max(axis=1) / ref.max(axis=1)
+    e12 = _rel(r['y'], ref, 1e-12).max(); e20 = _rel(r['y'], ref, 1e-20).max()
+    print('\n%s: %d restarts  |dY|/max(Y) 90%% %.3g max %.3g  rel(Y>1e-12) %.3g  rel(Y>1e-20) %.3g' % (
+        name, len(idx), np.percentile(e, 90), e.max(), e12, e20))
+    assert np.abs(r['tdel'] / h['hist_tdel'][0, idx + 1] - 1).max() < 1e-10
+    if ctl['iheat'] == 0:
+        assert e.max() < 1e-9 and e12 < 1e-6
+    else:
+        # the C/O burns end in NSE: the last Newton matrices are ill-conditioned (LAPACK's own solutions are good to 1e-8
+        # of max|dy| there), so two roundings of one step differ by up to 5.4e-8 (measured); 90 % are within 3e-10
+        assert np.percentile(e, 90) < 1e-9 and e.max() < 1e-6 and e12 < 1e-4
+
+
 # ---------------------------------------------------------------- module-level drop-ins
 def _states(op, name, k=6):
     h = op.run(nzone=1, hist_cap=3200)

@@ -11,7 +11,7 @@ import pytest
 
 from conftest import DATA, PROBLEMS, control_text
 
-TAU = 0.1
+TAU = 1.0e-3     # kSluTauDefault (xb_slu.cuh)
 
 
 class Slu:

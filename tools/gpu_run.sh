@@ -28,7 +28,7 @@ try:
     print('value %.4g  e2e %.4g  ms/step %.1f  cycles/iter %.0f  frac %.4f  launch %s' % (d['value'], d['e2e']['value'], d['ms_per_step'], r['cycles_per_newton_iter'], r['frac'], d['config']['launch']))
     print(' shares', r['phase_share'])
     print(' also', {k: (v if not isinstance(v, dict) else {a: b for a, b in v.items() if a in ('value', 'seconds', 'ms_per_step')}) for k, v in d['also'].items()})
-    for k in ('lu_isolated', 'cublas_batched', 'xb_over_cublas_speedup', 'structured', 'dense_fallbacks_per_lu'):
+    for k in ('lu_isolated', 'cublas_batched', 'xb_over_cublas_speedup', 'structured', 'dense_fallbacks_per_lu', 'fallback_stats'):
         if k in r: print(' ', k, r[k])
     print(' cpu', d.get('cpu_baseline', {}).get('value'), 'clocks', d['clocks'])
 except Exception as e:

@@ -95,6 +95,7 @@ struct xb_ctx {
   SluTables slu_tab;
   PlanBufs pby_slu, pbj_slu;
   DevBuf<unsigned short> slu_tab16;
+  DevBuf<uint2> slu_sched;
   DevBuf<int> slu_pos;
   DevScratch scr_slu{};
   DevBuf<double> scratch_slu;

@@ -85,7 +85,7 @@ slu_test_kernel(const double *__restrict__ a, const double *__restrict__ b, doub
   const double *A = a + (size_t)iz * n * n;
   double *S = zm.jac;
   const int *__restrict__ spos = D.pos;
-  if (tid == 0) { s->slu_fail = 0; s->info = 0; s->flag = 0; }
+  if (tid == 0) { s->slu_fail = 0; s->slu_fail_k = 0x7fffffff; s->info = 0; s->flag = 0; }
   for (int e = tid; e < D.nstore; e += nt) S[e] = 0.0;
   __syncthreads();
   for (int e = tid; e < n * n; e += nt) {
@@ -142,7 +142,7 @@ static SmemOff slu_layout(int ny, int n, int nstore, int npart, int nzs, int *of
   L.rdiag = (int)o; o += (size_t)n * 8; al();
   L.part = (int)o; o += (size_t)npart * 8; al();
   L.fhs = (int)o; o += (size_t)2 * nzs * 8; al();
-  *off_tab = (int)o; o += (size_t)6 * n * 2; al();
+  *off_tab = (int)o; o += ((size_t)7 * n + 2) * 2; al();   // rf, cf, lo, uo, rhi, chi [n] each, pbk [n+1]
   L.prow = L.indx = L.orig = L.pos = L.scal;    // not used by the structured path
   L.lds2 = 0; L.lu_s = L.lu_u = (int)o;
   L.cs = (int)o;
@@ -188,7 +188,7 @@ int xb_slu_configure(xb_ctx *c) {
     int off_tab = 0;
     SmemOff L = slu_layout(ny, n, T.nstore, c->slu_npart, d.nzs, &off_tab);
     if ((size_t)L.total + 64 > max_smem) return fail(XB_ERR_UNSUPPORTED, "structured LU: the zone does not fit in shared memory");
-    const int per_sm_smem = (int)(sm_smem / ((size_t)L.total + 1024));
+    const int per_sm_smem = (int)(sm_smem / ((size_t)L.total + 1024 + 64));
     const int want = env_int("XB_SLU_THREADS", 0);
     const int t2 = want > 0 ? want : (per_sm_smem >= 4 ? 128 : 256);
     d.lay = L; d.slu.off_tab = off_tab;
@@ -206,17 +206,58 @@ int xb_slu_configure(xb_ctx *c) {
   c->slu_threads = threads;
   d.tile = 1; d.ld = n;
   d.slu.ntest = n - heat;
+  { const char *v = std::getenv("XB_SLU_TAU"); d.slu.tau = (v && *v) ? std::atof(v) : kSluTauDefault; }
   d.slu.on = 1; d.slu.n = n; d.slu.nstore = T.nstore; d.slu.nbord = T.nbord;
   d.slu.nwl = std::max(1, std::min(env_int("XB_SLU_NWL", threads / 32), threads / 32));
   d.slu.force_fb = env_int("XB_SLU_FORCE_FALLBACK", 0);
   d.slu.tab16 = c->slu_tab16.p; d.slu.pos = c->slu_pos.p;
+  {
+    // elimination schedule of the heavy part (see slu_factor): per pivot the cross product of its rows and columns,
+    // column by column (consecutive lanes -> consecutive rows), then the right-hand-side entries; padded to whole blocks
+    // of ntl = 32*nwl entries, first block of every pivot flagged
+    const int ntl = 32 * d.slu.nwl;
+    const int rhs_off = (d.lay.rhs - d.lay.jac) / 8;
+    if (rhs_off < T.nstore || rhs_off + n >= 0xffff) return fail(XB_ERR_UNSUPPORTED, "structured LU: store too large for 16-bit addresses");
+    d.slu.rhs_off = rhs_off;
+    std::vector<uint2> sch;
+    std::vector<unsigned short> pbk(nh + 1, 0);
+    for (int k = 0; k < nh; ++k) {
+      const size_t first = sch.size();
+      const int r0 = T.rstart[k], r1 = T.rstart[k + 1], c0 = T.cstart[k], c1 = T.cstart[k + 1];
+      auto entry = [&](unsigned a, unsigned b, unsigned cc, unsigned fl) { sch.push_back(make_uint2(a | (b << 16), cc | (fl << 16))); };
+      for (int cI = c0; cI < c1; ++cI) {
+        const int j = T.clist[2 * cI], uoj = T.clist[2 * cI + 1];
+        for (int rI = r0; rI < r1; ++rI) {
+          const int i = T.rlist[2 * rI], loi = T.rlist[2 * rI + 1];
+          const unsigned a = (unsigned)((i <= j) ? uoj + i : loi + j);
+          entry(a, (unsigned)(loi + k), (unsigned)(uoj + k), (i >= d.slu.ntest) ? 1u : 0u);
+        }
+      }
+      for (int rI = r0; rI < r1; ++rI) {
+        const int i = T.rlist[2 * rI], loi = T.rlist[2 * rI + 1];
+        entry((unsigned)(rhs_off + i), (unsigned)(loi + k), (unsigned)(rhs_off + k), 4u | ((i >= d.slu.ntest) ? 1u : 0u));
+      }
+      if (sch.size() == first) entry(0xffffu, 0u, 0u, 0u);                       // a pivot without work still needs its block
+      while ((sch.size() - first) % ntl) entry(0xffffu, 0u, 0u, 0u);
+      pbk[k] = (unsigned short)(first / ntl);
+    }
+    if (sch.size() / ntl >= (size_t)0xffff) return fail(XB_ERR_UNSUPPORTED, "structured LU: schedule too long");
+    pbk[nh] = (unsigned short)(sch.size() / ntl);
+    d.slu.nblk = (int)(sch.size() / ntl);
+    CUDA_TRY(c->slu_sched.put(sch));
+    d.slu.sched = c->slu_sched.p;
+    tab.resize((size_t)7 * n + 2, 0);
+    for (int k = 0; k <= nh; ++k) tab[(size_t)6 * n + k] = pbk[k];
+    CUDA_TRY(c->slu_tab16.put(tab));
+    d.slu.tab16 = c->slu_tab16.p;
+  }
   // zones per SM by shared memory, then whatever is left on the SM caches csect (tail of the reaction list first)
   SmemOff &L = d.lay;
-  int per_sm = std::max(1, (int)(sm_smem / ((size_t)L.total + 1024)));
+  int per_sm = std::max(1, (int)(sm_smem / ((size_t)L.total + 1024 + 64)));
   per_sm = std::min(per_sm, std::max(1, 512 / threads));            // 128 registers per thread: 512 threads per SM
   per_sm = std::min(per_sm, std::max(1, env_int("XB_SLU_PER_SM", per_sm)));
   {
-    const size_t budget = std::min(max_smem - 64, sm_smem / per_sm - 1024);
+    const size_t budget = std::min(max_smem - 64, sm_smem / per_sm - 1024 - 64);   // 1 KB per CTA reserved by the system, 16 B static
     const size_t room = budget > (size_t)L.total ? (budget - (size_t)L.total) / 8 : 0;
     const int ncache = (int)std::min<size_t>(room, (size_t)d.nrtot);
     d.cs_lo = d.nrtot - ncache;
@@ -252,7 +293,7 @@ int xb_slu_configure(xb_ctx *c) {
 }
 
 void xb_slu_release(xb_ctx *c) {
-  c->slu_tab16.release(); c->slu_pos.release(); c->scratch_slu.release();
+  c->slu_tab16.release(); c->slu_pos.release(); c->scratch_slu.release(); c->slu_sched.release();
   xb_ctx::PlanBufs *pb[] = {&c->pby_slu, &c->pbj_slu};
   for (auto *b : pb) {
     b->a.release(); b->nn.release(); b->mc.release(); b->seg_start.release(); b->seg_dest.release();

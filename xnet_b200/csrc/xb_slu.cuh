@@ -11,7 +11,7 @@
 // one SM where the dense tile allows one.
 //
 // Numerical safety: every heavy column is verified, tau*|a(i,k)| <= |a(k,k)| for all rows below (the test the dense
-// fast path applies to its predicted pivot, with tau = 0.1: multipliers bounded by 10); the border block at the end
+// fast path applies to its predicted pivot; tau = 1e-3, see kSluTauDefault below); the border block at the end
 // is factored with ordinary partial pivoting (its rows are full, so interchanges stay inside the envelope).  A
 // factorisation with a violated column is discarded and redone by a dense partial-pivoting LU in the CTA's global
 // scratch (slu_dense_*), so the result is always that of a bounded-growth LU.
@@ -21,10 +21,13 @@
 
 namespace xb {
 
-#ifndef XB_SLU_TAU
-#define XB_SLU_TAU 0.1
-#endif
-constexpr double kSluTau = XB_SLU_TAU;
+// Default threshold of the column test (DevSlu.tau; XB_SLU_TAU in the environment overrides it at context creation).
+// 1e-3 bounds the multipliers by 1000.  Measured on every step of the SN160 flame trajectory
+// (tools/structured_lu_stability.py, profiles/r02_structured_lu_stability.txt): 2 % of the factorisations have a
+// multiplier above 10 (always the proton row against ga64 / ge63, whose diagonal has cancelled by the time it is the
+// pivot), the largest is 222, and the solutions of those systems are as close to an extended-precision solve as
+// LAPACK's partial-pivoting ones (error ratio 0.7 - 5.5): the growth that a large multiplier could cause does not occur.
+constexpr double kSluTauDefault = 1.0e-3;
 constexpr int kSluBord = 8;     // border rows/columns handled in registers (light particles + T9 <= 7)
 
 // per-zone views of the index tables (shared memory, 16-bit)
@@ -44,7 +47,7 @@ __device__ __forceinline__ SluIdx slu_idx() {
 __device__ __forceinline__ void slu_stage_tables() {
   const DevSlu &D = c_net.slu;
   unsigned short *t = reinterpret_cast<unsigned short *>(xb_smem + D.off_tab);
-  for (int k = threadIdx.x; k < 6 * D.n; k += blockDim.x) t[k] = D.tab16[k];
+  for (int k = threadIdx.x; k < 7 * D.n + 2; k += blockDim.x) t[k] = D.tab16[k];
 }
 __device__ __forceinline__ int slu_addr(const SluIdx &I, const int i, const int j) {
   return (i <= j) ? (int)I.uo[j] + i : (int)I.lo[i] + j;
@@ -68,10 +71,24 @@ __device__ __forceinline__ void slu_sync(const int nwl) {
 }
 
 // ---- factorisation -----------------------------------------------------------------------------------------------
+// The elimination of the heavy part is a FIXED sequence of element updates (the structure is the network's, the same
+// for every zone and every step), so it is executed from a precomputed schedule instead of being re-derived from the
+// index tables by every lane of every warp: entry = (a, b, c) meaning S[a] -= (S[b] * rinv_k) * S[c], with b in the
+// pivot column, c in the pivot row.  Entries of one pivot are independent; they are stored in blocks of ntl = 32*nwl
+// (one entry per participating thread, coalesced 8-byte loads, padded with no-ops), the first block of a pivot is
+// flagged: barrier, new pivot.  Every lane does useful work (the row x column tables above left a third of the lanes
+// idle and cost 22 instructions per column and warp).  All blocks of a pivot are processed together -- every load
+// issued before the first FMA, every store after the last -- so the latency chain per pivot is barrier, one round of
+// shared-memory loads, reciprocal, multiply-add, store.  The schedule streams from L2 (SN160: 0.5 MB per
+// factorisation, shared by all zones); the entries of the next two pivots are in flight in registers.
+//   x = a | b << 16,  y = c | flags << 16;  flags: 1 = row exempt from the threshold test (T9 row), 4 = right-hand-side
+//   entry (skipped when the right-hand side is not carried);  a = 0xffff: no-op.  pbk[k] (16-bit table, shared memory):
+//   first block of pivot k.
 // Executed by the first nwl warps of the CTA (the others return at once; the caller's __syncthreads joins them).
-// with_rhs: rhs[n] (position order) is carried along as an extra column: it leaves as L^-1 P b.
-// *fail is set when a heavy column violates the threshold test or a pivot is zero/NaN.  ipb[kSluBord]: interchanges of
-// the border block (row of the block, 0-based).
+// with_rhs: the right-hand side (rhs = S + rhs_off, position order) is carried along as an extra column: it leaves as
+// L^-1 P b.  fail[0] is set when a heavy column violates the threshold test or a pivot is zero/NaN, fail[1] receives
+// the first such column (caller initialises it to a large value).  ipb[kSluBord]: interchanges of the border block.
+constexpr int kSluChunk = 6;     // blocks of one pivot processed together (all loads, then all FMAs, then all stores)
 __device__ __noinline__ void slu_factor(double *__restrict__ S, double *__restrict__ rhs, double *__restrict__ rinv,
                                         int *ipb, int *fail, const bool with_rhs, const int nwl) {
   XB_ASSUME_SHARED(S); XB_ASSUME_SHARED(rhs); XB_ASSUME_SHARED(rinv); XB_ASSUME_SHARED(fail); XB_ASSUME_SHARED(ipb);
@@ -82,46 +99,60 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S, double *__restri
   // The temperature equation (self-heating: the last row) is exempt from the test: it is the linear functional
   // -sum_i mex_i (row i) / cv of the abundance rows, i.e. a row in different units whose multipliers measure mex/cv and
   // not element growth (elimination without interchanges is invariant under row scaling); it is pivoted in the border.
-  const int ntest = c_net.slu.ntest;
+  const double tau = c_net.slu.tau;
   bool viol = false;
-  for (int k = 0; k < nh; ++k) {
-    if (k > 0) slu_sync(nwl);
-    const int nrb = (int)I.rhi[k] - k, nrc = nrb + nb;       // band candidates, all candidates (rows)
-    const int ncb = (int)I.chi[k] - k, ncc = ncb + nb;       // columns
-    const double piv = S[(int)I.uo[k] + k];
-    const double apiv = fabs(piv);
-    const double rk = pivot_rcp<false>(piv);
-    if (!(apiv > 0.0)) viol = true;                          // zero or NaN pivot
-    if (tid == 0) rinv[k] = rk;
-    for (int rb = 0; rb < nrc; rb += 32) {
-      const int i = slu_row_cand(I, k, nrb, rb + lane, nrc);
-      const bool act = i >= 0;
-      const int loi = act ? (int)I.lo[i] : 0;
-      const double a = act ? S[loi + k] : 0.0;
-      if (i < ntest && kSluTau * fabs(a) > apiv) viol = true;
-      const double l = a * rk;
-      // columns in chunks of four per warp: index loads, then value loads, then FMAs, then stores
-      for (int q = w; 4 * q < ncc; q += nwl) {
-        int j[4], uoj[4], ad[4];
-        double u[4], s[4];
+  {
+    const DevSlu &D = c_net.slu;
+    const int ntl = nwl * 32;
+    const uint2 *__restrict__ sch = D.sched + tid;
+    const unsigned short *pbk = I.rf + 6 * I.n;          // [nh+1] first schedule block of every pivot
+    const uint2 kNop = make_uint2(0xffffu, 0u);
+    // entries of the next two pivots are in flight (registers) while the current one is eliminated: the schedule comes
+    // from L2 (~250 cycles), a pivot takes ~150
+    uint2 q1[kSluChunk], q2[kSluChunk];
+    auto fetch = [&](uint2 (&q)[kSluChunk], const int kk) {
+      if (kk < nh) {
+        const int g0 = (int)pbk[kk], cnt = (int)pbk[kk + 1] - g0;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          j[t] = slu_col_cand(I, k, ncb, 4 * q + t, ncc);
-          uoj[t] = (j[t] >= 0) ? (int)I.uo[j[t]] : 0;
-        }
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const bool on = act && j[t] >= 0;
-          ad[t] = on ? ((i <= j[t]) ? uoj[t] + i : loi + j[t]) : -1;
-          u[t] = (j[t] >= 0) ? S[uoj[t] + k] : 0.0;
-          s[t] = on ? S[ad[t]] : 0.0;
-        }
-#pragma unroll
-        for (int t = 0; t < 4; ++t) s[t] = fma(-l, u[t], s[t]);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) if (ad[t] >= 0) S[ad[t]] = s[t];
+        for (int m = 0; m < kSluChunk; ++m) q[m] = (m < cnt) ? __ldg(sch + (size_t)(g0 + m) * ntl) : kNop;
       }
-      if (with_rhs && w == nwl - 1 && act) rhs[i] = fma(-l, rhs[k], rhs[i]);
+    };
+    fetch(q1, 0); fetch(q2, 1);
+    for (int k = 0; k < nh; ++k) {
+      uint2 e[kSluChunk];
+#pragma unroll
+      for (int m = 0; m < kSluChunk; ++m) { e[m] = q1[m]; q1[m] = q2[m]; }
+      fetch(q2, k + 2);
+      const int g0 = (int)pbk[k], cnt = (int)pbk[k + 1] - g0;
+      if (k > 0) slu_sync(nwl);
+      const double piv = S[(int)I.uo[k] + k];
+      const double apiv = fabs(piv);
+      const double rk = pivot_rcp<false>(piv);
+      if (!(apiv > 0.0)) { viol = true; atomicMin(fail + 1, k); }   // zero or NaN pivot
+      if (tid == 0) rinv[k] = rk;
+      for (int base = 0; base < cnt; base += kSluChunk) {
+        if (base > 0) {                                  // wide pivots (the dense head of the band): fetched on demand
+#pragma unroll
+          for (int m = 0; m < kSluChunk; ++m) e[m] = (base + m < cnt) ? __ldg(sch + (size_t)(g0 + base + m) * ntl) : kNop;
+        }
+        double sb[kSluChunk], sc[kSluChunk], sa[kSluChunk];
+        bool on[kSluChunk];
+#pragma unroll
+        for (int m = 0; m < kSluChunk; ++m) {
+          const unsigned a = e[m].x & 0xffffu, fl = e[m].y >> 16;
+          on[m] = a != 0xffffu && (with_rhs || !(fl & 4u));
+          sb[m] = on[m] ? S[e[m].x >> 16] : 0.0;
+          sc[m] = on[m] ? S[e[m].y & 0xffffu] : 0.0;
+          sa[m] = on[m] ? S[a] : 0.0;
+        }
+#pragma unroll
+        for (int m = 0; m < kSluChunk; ++m) {
+          if (!((e[m].y >> 16) & 1u) && tau * fabs(sb[m]) > apiv) { viol = true; atomicMin(fail + 1, k); }   // fail[1]: first violated column
+          sa[m] = fma(-(sb[m] * rk), sc[m], sa[m]);
+        }
+#pragma unroll
+        for (int m = 0; m < kSluChunk; ++m) if (on[m]) S[e[m].x & 0xffffu] = sa[m];
+      }
     }
   }
   slu_sync(nwl);
@@ -200,16 +231,16 @@ __device__ __noinline__ void slu_solve(const double *__restrict__ S, double *__r
   const SluIdx I = slu_idx();
   const int n = I.n, nh = I.nh, nb = I.nb;
   if (!fwd_done) {
-    for (int k = 0; k < n; ++k) {
-      if (k == nh) {   // interchanges of the border block, in order
-        if (lane == 0) {
-          for (int jj = 0; jj < nb; ++jj) {
-            const int p = ipb[jj];
-            if (p != jj) { const double t = b[nh + jj]; b[nh + jj] = b[nh + p]; b[nh + p] = t; }
-          }
-        }
-        __syncwarp();
+    // interchanges of the border block first (DLASWP precedes the forward substitution: the heavy pivots' updates of
+    // the border entries use the multipliers of the rows in their final slots)
+    if (lane == 0) {
+      for (int jj = 0; jj < nb; ++jj) {
+        const int p = ipb[jj];
+        if (p != jj) { const double t = b[nh + jj]; b[nh + jj] = b[nh + p]; b[nh + p] = t; }
       }
+    }
+    __syncwarp();
+    for (int k = 0; k < n; ++k) {
       const double f = b[k] * rinv[k];
       if (k < nh) {
         const int nrb = (int)I.rhi[k] - k, nrc = nrb + nb;
@@ -279,10 +310,22 @@ __device__ __noinline__ void slu_dense_factor(const double *__restrict__ S, cons
     __syncthreads();
     for (int i = k + 1 + tid; i < n; i += nt) A[(size_t)k * n + i] *= rk;
     __syncthreads();
-    for (int j = k + 1 + wq; j <= n; j += nw) {
-      double *col = A + (size_t)j * n;
-      const double u = col[k];
-      for (int i = k + 1 + lane; i < n; i += 32) col[i] = fma(-A[(size_t)k * n + i], u, col[i]);
+    // four columns per warp pass, two row chunks per iteration: up to 10 loads in flight per lane (L2 latency)
+    for (int j0 = k + 1 + 4 * wq; j0 <= n; j0 += 4 * nw) {
+      double *cp[4]; double u[4]; bool on[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { on[t] = j0 + t <= n; cp[t] = A + (size_t)(on[t] ? j0 + t : j0) * n; u[t] = cp[t][k]; }
+      for (int i = k + 1 + lane; i < n; i += 64) {
+        const int i2 = i + 32; const bool two = i2 < n;
+        const double l0 = A[(size_t)k * n + i], l1 = two ? A[(size_t)k * n + i2] : 0.0;
+        double c0[4], c1[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { c0[t] = cp[t][i]; c1[t] = two ? cp[t][i2] : 0.0; }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { c0[t] = fma(-l0, u[t], c0[t]); c1[t] = fma(-l1, u[t], c1[t]); }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) if (on[t]) { cp[t][i] = c0[t]; if (two) cp[t][i2] = c1[t]; }
+      }
     }
     __syncthreads();
   }

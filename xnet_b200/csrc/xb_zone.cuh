@@ -31,7 +31,7 @@ struct ZoneScalars {
   int kmon[5], ktot[5];
   int inr, its, flag, piv, info, tile_ctr;
   int rhs_in_jac;            // global-memory Jacobian: the right-hand side rides as column N of the per-CTA scratch (fused path)
-  int slu_fail, lu_dense, nlu_zone;   // structured LU: threshold test failed / factors are the dense fallback's / factorisations so far
+  int slu_fail, slu_fail_k, lu_dense, nlu_zone;   // structured LU: threshold test failed (+ first violated column) / factors are the dense fallback's / factorisations so far
   int slu_ipb[8];            // interchanges of the border block
   long long ph[PH_COUNT];    // see enum Phase
   long long tmark, dmark;
@@ -988,7 +988,7 @@ __device__ __noinline__ void step_be_cta() {
       }
     };
     fill_rhs();
-    if (tid == 0 && rebuild) { s->slu_fail = 0; s->nlu_zone += 1; }
+    if (tid == 0 && rebuild) { s->slu_fail = 0; s->slu_fail_k = 0x7fffffff; s->nlu_zone += 1; }
     __syncthreads();
     if (rebuild) {
       slu_factor(zm.jac, zm.rhs, zm.rdiag, s->slu_ipb, &s->slu_fail, true, net.slu.nwl);
@@ -998,9 +998,16 @@ __device__ __noinline__ void step_be_cta() {
         // a column failed the threshold test: this factorisation is redone by the dense partial-pivoting LU
         jacobian_build_cta<STRICT>();
         fill_rhs();
-        if (tid == 0) { s->ktot[2] -= 1; s->lu_dense = 1; s->ph[PH_SPARE] += 1; }
+        if (tid == 0) {
+          s->ktot[2] -= 1; s->lu_dense = 1; s->ph[PH_SPARE] += 1;
+          // where the fallbacks come from: sums of the first violated column, the zone's factorisation count and the
+          // Newton iteration (divide by the fallback count)
+          s->ph[PH_DBG0] += (s->slu_fail_k < N) ? s->slu_fail_k : N; s->ph[PH_DBG0 + 1] += s->nlu_zone; s->ph[PH_DBG0 + 2] += kit;
+          const long long now_ = clock64(); s->ph[PH_LU_PANEL] += now_ - s->tmark;   // the failed structured attempt
+        }
         __syncthreads();
         slu_dense_factor(zm.jac, zm.rhs, s->g_jac, reinterpret_cast<int *>(s->g_jac + (size_t)(N + 1) * N), zm.part, &s->info);
+        if (tid == 0) { const long long now_ = clock64(); s->ph[PH_LU_SWAP] += now_ - s->tmark; }   // fallback cycles (incl. the failed attempt)
       } else if (tid == 0) s->lu_dense = 0;
       __syncthreads();
       XB_PHASE_END(zm, PH_LU);
