@@ -256,8 +256,9 @@ int xb_last_kernel_ms(xb_ctx *ctx, float *ms);
  * factorisation (2 per multiply-add), zones resident per SM, rows/columns of the pivoted border, warps that
  * factor, reaction rates cached in shared memory */
 int xb_solver_info(xb_ctx *ctx, double *info8);
-/* structured-LU index tables of a network (heat = 1: with the T9 equation); what = "perm","pos","rf","cf","lo","uo",
- * "rstart","cstart","rlist","clist","sizes" -- see SluTables in xnet_b200/csrc/xb_host.h */
+/* structured-LU index tables of a network (heat = 1: with the T9 equation); what = "perm","pos","rf","cf","cb","cbot",
+ * "nrb","ncb","sizes" (n, nstore, nbord, flops, bo, bs, flops of the stored envelope) -- see SluTables in
+ * xnet_b200/csrc/xb_host.h */
 int xb_slu_table(const xb_net *net, int32_t heat, const char *what, int32_t *out, int64_t cap, int64_t *n);
 /* nz dense systems a[nz][n*n] (column-major, equation order, zero outside the structural envelope) solved with the
  * structured LU of a solver = 1 context: mode 0 = right-hand side carried through the factorisation, 1 = factor, then

@@ -231,8 +231,11 @@ def test_fast_complete_trajectory_vs_cpu_build_noise(gpu_problem, oracle_problem
     print('\n%s solver %d: records ref/alt/gpu %d/%d/%d  max dev gpu %.3g  cpu-fma %.3g  worst ratio %.3g at record %d' % (
         name, solver, nr, na, ng, dg.max(), da.max(), ratio, k))
     assert ratio <= 100.0, (ratio, k, dg[k], env[k])
+    # mass conservation no worse than the oracle's own (self-heating runs end at |sum X - 1| ~ 1e-8 on the CPU too)
     aa = net.dtable('aa')
-    assert abs((r['y'][0] * aa).sum() - 1.0) < 1e-8
+    mg, mr = abs((r['y'][0] * aa).sum() - 1.0), abs((ref['y'][0] * aa).sum() - 1.0)
+    print('   |sum X - 1|: gpu %.3g  oracle %.3g' % (mg, mr))
+    assert mg <= 3.0 * max(mr, 1e-8)
 
 
 @pytest.mark.parametrize('name,stride', [('sn160_scrn', 9), ('sn160_heat', 5), ('sn231_logft', 7), ('xrb304', 23)])

@@ -15,39 +15,37 @@ TAU = 1.0e-3     # kSluTauDefault (xb_slu.cuh)
 
 
 class Slu:
-    """numpy mirror of slu_factor / slu_solve"""
+    """numpy mirror of slu_factor / slu_solve: same storage, same elimination order, same pivot rule in the border"""
     def __init__(self, net, heat):
         self.heat = heat
-        t = {k: net.slu_table(k, heat) for k in ('perm', 'pos', 'rf', 'cf', 'lo', 'uo', 'sizes')}
+        t = {k: net.slu_table(k, heat) for k in ('perm', 'pos', 'rf', 'cf', 'cb', 'cbot', 'nrb', 'ncb', 'sizes')}
         self.n, self.nstore, self.nb = int(t['sizes'][0]), int(t['sizes'][1]), int(t['sizes'][2])
-        self.perm, self.pos, self.rf, self.cf, self.lo, self.uo = (t[k].astype(int) for k in ('perm', 'pos', 'rf', 'cf', 'lo', 'uo'))
-        n, nh = self.n, self.n - self.nb
-        self.nh = nh
-        # rhi / chi exactly as xb_slu_configure forms them
-        self.rhi = np.arange(n); self.chi = np.arange(n)
-        for p in range(n):
-            for i in range(p + 1, nh):
-                if self.rf[i] <= p:
-                    self.rhi[p] = i
-                if self.cf[i] <= p:
-                    self.chi[p] = i
+        self.bo, self.bs = int(t['sizes'][4]), int(t['sizes'][5])
+        self.perm, self.pos, self.rf, self.cf, self.cb, self.cbot, self.nrb, self.ncb = (
+            t[k].astype(int) for k in ('perm', 'pos', 'rf', 'cf', 'cb', 'cbot', 'nrb', 'ncb'))
+        self.nh = self.n - self.nb
 
     def addr(self, i, j):
-        return self.uo[j] + i if i <= j else self.lo[i] + j
+        return self.bo + j * self.bs + (i - self.nh) if i >= self.nh else self.cb[j] + i
 
     def inside(self, i, j):
+        return i >= self.nh or self.cf[j] <= i <= self.cbot[j]
+
+    def structural(self, i, j):
+        """the row/column skyline of structured_lu_plan (a subset of the stored envelope)"""
         return self.cf[j] <= i if i <= j else self.rf[i] <= j
 
     def rows(self, k):
-        c = list(range(k + 1, self.rhi[k] + 1)) + list(range(self.nh, self.n))
-        return [i for i in c if self.rf[i] <= k]
+        """rows that take part in pivot k: the band span, then the border"""
+        return list(range(k + 1, k + 1 + self.nrb[k])) + list(range(self.nh, self.n))
 
     def cols(self, k):
-        c = list(range(k + 1, self.chi[k] + 1)) + list(range(self.nh, self.n))
+        c = list(range(k + 1, k + 1 + self.ncb[k])) + list(range(self.nh, self.n))
         return [j for j in c if self.cf[j] <= k]
 
     def scatter(self, a):
-        """a[row, col] in equation order -> store; asserts nothing non-zero falls outside the envelope"""
+        """a[row, col] in equation order -> store; asserts nothing non-zero falls outside the structural pattern, that
+        the pattern lies inside the stored envelope and that no two elements share an address"""
         S = np.zeros(self.nstore)
         used = np.zeros(self.nstore, bool)
         for r in range(self.n):
@@ -57,33 +55,43 @@ class Slu:
                     ad = self.addr(pi, pj)
                     assert 0 <= ad < self.nstore and not used[ad]
                     used[ad] = True; S[ad] = a[r, c]
+                if not self.structural(pi, pj):
+                    assert a[r, c] == 0.0, 'non-zero outside the structural pattern at (%d,%d)' % (r, c)
                 else:
-                    assert a[r, c] == 0.0, 'non-zero outside the envelope at (%d,%d)' % (r, c)
-        assert used.all(), 'store has unaddressed slots'
+                    assert self.inside(pi, pj), 'structural element (%d,%d) outside the stored envelope' % (pi, pj)
         return S
 
     def factor(self, S, b=None):
         n, nh, nb = self.n, self.nh, self.nb
         rinv = np.zeros(n); fail = False
         b = None if b is None else b.copy()
+        ntest = n - self.heat
         for k in range(nh):
-            piv = S[self.uo[k] + k]
+            piv = S[self.cb[k] + k]
             rinv[k] = 1.0 / piv
-            for i in self.rows(k):
-                a = S[self.lo[i] + k]
-                if i < n - self.heat and TAU * abs(a) > abs(piv):   # the T9 row is exempt (xb_slu.cuh)
-                    fail = True
-                l = a * rinv[k]
-                for j in self.cols(k):
-                    S[self.addr(i, j)] -= l * S[self.uo[j] + k]
-                if b is not None:
-                    b[i] -= l * b[k]
-        # border block with partial pivoting (registers on the device)
+            rows = self.rows(k)
+            l = np.array([S[self.addr(i, k)] for i in rows])
+            if any(TAU * abs(v) > abs(piv) for v, i in zip(l, rows) if i < ntest):   # the T9 row is exempt (xb_slu.cuh)
+                fail = True
+            for j in self.cols(k):
+                u = S[self.cb[j] + k] * rinv[k]
+                for v, i in zip(l, rows):
+                    S[self.addr(i, j)] -= v * u
+            if b is not None:
+                u = b[k] * rinv[k]
+                for v, i in zip(l, rows):
+                    b[i] -= v * u
+        # border block: the diagonal is kept while it passes the threshold test against the tested rows below it
         v = np.array([[S[self.addr(nh + r, nh + c)] for c in range(nb)] for r in range(nb)])
         vb = None if b is None else b[nh:].copy()
         ipb = list(range(nb))
+        nbt = ntest - nh
         for j in range(nb):
-            p = j + int(np.argmax(np.abs(v[j:, j])))
+            col = np.abs(v[j:, j])
+            p = j + int(np.argmax(col))
+            bestt = col[:max(nbt - j, 0)].max() if nbt > j else -1.0
+            if col[0] > 0.0 and not TAU * bestt > col[0]:
+                p = j
             ipb[j] = p
             if p != j:
                 v[[j, p]] = v[[p, j]]
@@ -102,8 +110,8 @@ class Slu:
             b[nh:] = vb
         for j in range(nb):
             if ipb[j] != j:
-                la, lb = self.lo[nh + j], self.lo[nh + ipb[j]]
-                tmp = S[la:la + nh].copy(); S[la:la + nh] = S[lb:lb + nh]; S[lb:lb + nh] = tmp
+                ia = [self.addr(nh + j, c) for c in range(nh)]; ib = [self.addr(nh + ipb[j], c) for c in range(nh)]
+                tmp = S[ia].copy(); S[ia] = S[ib]; S[ib] = tmp
         return rinv, ipb, fail, b
 
     def solve(self, S, rinv, ipb, b, fwd_done):
@@ -118,12 +126,12 @@ class Slu:
                 f = b[k] * rinv[k]
                 rows = self.rows(k) if k < nh else range(k + 1, n)
                 for i in rows:
-                    b[i] -= S[self.lo[i] + k] * f
+                    b[i] -= S[self.addr(i, k)] * f
         for k in range(n - 1, -1, -1):
             x = b[k] * rinv[k]
             b[k] = x
             for i in range(self.cf[k], k):
-                b[i] -= S[self.uo[k] + i] * x
+                b[i] -= S[self.addr(i, k)] * x
         return b
 
 

@@ -11,7 +11,8 @@ import json
 try:
     d=json.load(open('gpurun_out/v.json')); r=d['roofline']
     print('value %.4g cycles/iter %.0f launch %s' % (d['value'], r['cycles_per_newton_iter'], d['config']['launch']))
-    print(' shares', {k: v for k, v in r['phase_share'].items() if v}, 'fb', r.get('dense_fallbacks_per_lu'), r.get('structured'))
+    cyc = r['cycles_per_newton_iter']
+    print(' cycles', {k: int(v * cyc) for k, v in r['phase_share'].items() if v}, 'fb', r.get('dense_fallbacks_per_lu'), r.get('structured'))
 except Exception as e: print('no result', e)
 PY
 done

@@ -1181,8 +1181,8 @@ int xb_solver_info(xb_ctx *c, double *info8) {
   return XB_OK;
 }
 
-// Structured-LU tables of a network (tests): heat = 1 adds the T9 equation.  what = "perm","pos","rf","cf","lo","uo",
-// "rstart","cstart","rlist","clist" (pairs), "sizes" (n, nstore, nbord)
+// Structured-LU tables of a network (tests): heat = 1 adds the T9 equation.  what = "perm","pos","rf","cf","cb","cbot",
+// "nrb","ncb" (SluTables, xb_host.h), "sizes" (n, nstore, nbord, flops, bo, bs, flops_envelope)
 int xb_slu_table(const xb_net *net, int32_t heat, const char *what, int32_t *out, int64_t cap, int64_t *n) {
   if (!net || !what) return fail(XB_ERR_ARG, "xb_slu_table: null argument");
   SluTables t;
@@ -1192,13 +1192,11 @@ int xb_slu_table(const xb_net *net, int32_t heat, const char *what, int32_t *out
   if (w == "pos") return copy_out(t.pos, out, cap, n);
   if (w == "rf") return copy_out(t.rf, out, cap, n);
   if (w == "cf") return copy_out(t.cf, out, cap, n);
-  if (w == "lo") return copy_out(t.lo, out, cap, n);
-  if (w == "uo") return copy_out(t.uo, out, cap, n);
-  if (w == "rstart") return copy_out(t.rstart, out, cap, n);
-  if (w == "cstart") return copy_out(t.cstart, out, cap, n);
-  if (w == "rlist") return copy_out(t.rlist, out, cap, n);
-  if (w == "clist") return copy_out(t.clist, out, cap, n);
-  if (w == "sizes") { std::vector<int32_t> v{t.n, t.nstore, t.nbord, (int32_t)t.flops}; return copy_out(v, out, cap, n); }
+  if (w == "cb") return copy_out(t.cb, out, cap, n);
+  if (w == "cbot") return copy_out(t.cbot, out, cap, n);
+  if (w == "nrb") return copy_out(t.nrb, out, cap, n);
+  if (w == "ncb") return copy_out(t.ncb, out, cap, n);
+  if (w == "sizes") { std::vector<int32_t> v{t.n, t.nstore, t.nbord, (int32_t)t.flops, t.bo, t.bs, (int32_t)t.flops_envelope}; return copy_out(v, out, cap, n); }
   return fail(XB_ERR_ARG, "xb_slu_table: unknown key " + w);
 }
 

@@ -94,8 +94,7 @@ struct xb_ctx {
   DevNet dn_slu{};
   SluTables slu_tab;
   PlanBufs pby_slu, pbj_slu;
-  DevBuf<unsigned short> slu_tab16;
-  DevBuf<uint2> slu_sched;
+  DevBuf<uint2> slu_tabd;
   DevBuf<int> slu_pos;
   DevScratch scr_slu{};
   DevBuf<double> scratch_slu;
@@ -218,7 +217,7 @@ static inline int build_plans(xb_ctx *c, DevNet &dn_out, xb_ctx::PlanBufs &pby, 
       ++id; prev = key;
       const int i0 = key / N, col = key % N;
       int dest = (col << 10) | i0;   // device: column*ld + slot(row)
-      if (slu) { const int pi = slu->pos[i0], pj = slu->pos[col]; dest = (pi <= pj) ? slu->uo[pj] + pi : slu->lo[pi] + pj; }
+      if (slu) dest = slu->addr(slu->pos[i0], slu->pos[col]);
       js_start.push_back((int)r); js_dest.push_back((dest << 1) | (i0 == col ? 1 : 0));
     }
     rj[r].fseg = id; rj[r].sseg = id; rj[r].fdest = js_dest.back();

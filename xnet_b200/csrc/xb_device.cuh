@@ -32,16 +32,16 @@ struct DevPlan {
 // byte offsets of the zone working set inside the CTA's dynamic shared memory
 struct SmemOff { int scal, jac, y, yt, ydot, rhs, rdiag, part, prow, indx, orig, pos, fhs, lu_s, lu_u, lds2, cs, total; };
 
-// structured LU (xb_slu.cuh): sizes, the 16-bit index tables staged into every CTA's shared memory, species -> position
+// structured LU (xb_slu.cuh): sizes, the index tables staged into every CTA's shared memory, species -> position
 struct DevSlu {
-  double tau;                                // threshold of the column test: tau*|a(i,k)| <= |a(k,k)| (multipliers <= 1/tau)
+  double tau, itau;                          // threshold of the column test: tau*|a(i,k)| <= |a(k,k)| (multipliers <= 1/tau); 1/tau
   int ntest;                                 // rows 0..ntest-1 are subject to the threshold test (all but the T9 row)
   int on, n, nstore, nbord, nwl, force_fb;   // nwl: warps that factor; force_fb > 0: every force_fb-th LU takes the dense fallback (tests)
-  int off_tab;                               // byte offset of the staged tables in shared memory
-  const unsigned short *tab16;               // [6][n]: rf, cf, lo, uo, rhi, chi; then pbk [n+1]: first schedule block of each pivot
+  int off_tab, tab_rel;                      // staged table: byte offset in shared memory; 64-bit entries relative to the store S
+  int bo, bs, rhs_off, rinv_off;             // border rows: base and column stride (doubles); rhs = S + rhs_off, rdiag = S + rinv_off
+  int fail_rel;                              // ZoneScalars::slu_fail as a 32-bit word offset from S (negative: the scalars precede the store)
+  const uint2 *tab;                          // [n+1] x = cb | cf << 16 (entry n: the right-hand side), y = ncb | nrb << 8
   const int *pos;                            // [n] equation (species, then T9) -> position in the reordered system
-  const uint2 *sched;                        // [nblk][32*nwl] elimination schedule of the heavy part (xb_slu.cuh)
-  int nblk, rhs_off;                         // blocks of the schedule; rhs = S + rhs_off (doubles)
 };
 
 struct DevNet {

@@ -62,17 +62,33 @@ void flux_init(Network &net);
 // fills slu_perm, slu_rowfirst, slu_colfirst, slu_doubles from the species <-> reaction maps
 void structured_lu_plan(Network &net);
 // Tables of the structured LU for a system of N = ny (+1 with self-heating: the T9 equation is the last row and
-// column, both full) equations in the light-particles-last order.  Storage ("skyline"): for every column j the part
-// of U in rows cf[j]..j, for every row i the part of L in columns rf[i]..i-1; element (i,j) of the permuted matrix
-// lives at  i <= j ? uo[j] + i : lo[i] + j.  Elimination without interchanges never leaves this envelope.
+// column, both full) equations in the light-particles-last order: nh = n - nbord "heavy" equations with a variable-band
+// pattern, then the border (light particles, T9).  Storage, S[nstore] doubles:
+//   rows i < nh  : COLUMN-major, column j holds rows ct[j] = cf[j] .. cbot[j] contiguously, element (i,j) at cb[j] + i.
+//                  Heavy columns: cbot[j] = last heavy row whose stored part reaches column j (>= j); border columns: all
+//                  heavy rows.  Column starts are padded so that cb[j] = j (mod 16): lanes working on consecutive columns
+//                  at one row hit distinct shared-memory banks.
+//   rows i >= nh : also by column, element (i,j) at bo + j * bs + (i - nh) with an odd stride bs >= nbord; n + 1 columns, the
+//                  last one carries the border rows' right-hand side entries through the factorisation.
+// Elimination without interchanges over the heavy part never leaves this envelope (it contains the row/column skyline
+// rf/cf of structured_lu_plan; the zero entries it adds stay zero).
 struct SluTables {
   int n = 0, nstore = 0, nbord = 0;           // order, doubles of the store, trailing rows/columns factored with pivoting
+  int bo = 0, bs = 0;                         // border rows: base and column stride
   std::vector<int32_t> perm, pos;             // [n] position -> equation, equation -> position (0-based; equation ny = T9)
-  std::vector<int32_t> rf, cf;                // [n] first stored column of row i / first stored row of column j
-  std::vector<int32_t> lo, uo;                // [n] address bases (see above)
-  std::vector<int32_t> rstart, cstart;        // [n+1] per pivot k: rows i > k with rf[i] <= k / columns j > k with cf[j] <= k
-  std::vector<int32_t> rlist, clist;          // [2 * count] pairs (i, lo[i]) / (j, uo[j]), ascending
-  double flops = 0;                           // of one factorisation (2 per multiply-add, 1 per scaled multiplier)
+  std::vector<int32_t> rf, cf;                // [n] first structural column of row i / first structural row of column j
+  std::vector<int32_t> cb, cbot;              // [n] column base (address of a virtual row 0), last stored heavy row
+  std::vector<int32_t> nrb, ncb;              // [nh] per pivot k: rows k+1..k+nrb and columns k+1..k+ncb of the heavy part take part
+  double flops = 0;                           // of one factorisation over the structural pattern (2 per multiply-add, 1 per multiplier)
+  double flops_envelope = 0;                  // what the kernel executes (spans instead of patterns)
+  bool inside(int i, int j) const {
+    const int nh = n - nbord;
+    return i >= nh ? true : (cf[j] <= i && i <= cbot[j]);
+  }
+  int addr(int i, int j) const {
+    const int nh = n - nbord;
+    return i >= nh ? bo + j * bs + (i - nh) : cb[j] + i;
+  }
 };
 void structured_lu_tables(const Network &net, int heat, SluTables &t);
 int index_from_name(const Network &net, const std::string &name);

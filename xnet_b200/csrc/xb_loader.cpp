@@ -430,22 +430,43 @@ void structured_lu_tables(const Network &net, int heat, SluTables &t) {
   if (heat) { t.rf[ny] = 0; t.cf[ny] = 0; }
   // the border rows and columns are stored in full: the pivoting inside the border exchanges whole rows
   for (int p = n - t.nbord; p < n; ++p) { t.rf[p] = 0; t.cf[p] = 0; }
-  t.lo.resize(n); t.uo.resize(n);
+  const int nh = n - t.nbord;
+  // spans of the heavy part per pivot, last stored heavy row per column
+  t.nrb.assign(nh, 0); t.ncb.assign(nh, 0); t.cbot.assign(n, nh - 1);
+  for (int k = 0; k < nh; ++k) {
+    int rhi = k, chi = k;
+    for (int i = k + 1; i < nh; ++i) { if (t.rf[i] <= k) rhi = i; if (t.cf[i] <= k) chi = i; }
+    t.nrb[k] = rhi - k; t.ncb[k] = chi - k; t.cbot[k] = rhi;
+  }
+  t.cb.resize(n);
+  int padw = 8;                                      // XB_SLU_PADW = 1 (no padding) .. 16 (conflict-free half-warps)
+  if (const char *v = std::getenv("XB_SLU_PADW")) if (*v) padw = std::min(16, std::max(1, std::atoi(v)));
   int o = 0;
-  for (int p = 0; p < n; ++p) {
-    t.uo[p] = o - t.cf[p]; o += p - t.cf[p] + 1;     // rows cf..p of column p
-    t.lo[p] = o - t.rf[p]; o += p - t.rf[p];         // columns rf..p-1 of row p
+  for (int j = 0; j < n; ++j) {
+    // start address a of row cf[j] such that cb[j] = a - cf[j] differs (mod 16: the 64-bit shared-memory bank pair) from
+    // the bases of the padw - 1 columns before it
+    int a = o;
+    auto res = [&](int base) { return ((base % 16) + 16) % 16; };
+    for (;; ++a) {
+      bool clash = false;
+      for (int q = std::max(0, j - (padw - 1)); q < j && !clash; ++q) clash = res(t.cb[q]) == res(a - t.cf[j]);
+      if (!clash) break;
+    }
+    t.cb[j] = a - t.cf[j];
+    o = a + (t.cbot[j] - t.cf[j] + 1);
   }
+  // border rows, column by column with an odd stride (consecutive columns -> distinct banks); column n carries the
+  // right-hand side entries of the border rows through the factorisation
+  t.bo = o; t.bs = t.nbord | 1;
+  o += (n + 1) * t.bs;
   t.nstore = o;
-  t.rstart.assign(n + 1, 0); t.cstart.assign(n + 1, 0);
   for (int k = 0; k < n; ++k) {
-    t.rstart[k] = (int)t.rlist.size() / 2; t.cstart[k] = (int)t.clist.size() / 2;
-    for (int i = k + 1; i < n; ++i) if (t.rf[i] <= k) { t.rlist.push_back(i); t.rlist.push_back(t.lo[i]); }
-    for (int j = k + 1; j < n; ++j) if (t.cf[j] <= k) { t.clist.push_back(j); t.clist.push_back(t.uo[j]); }
-    const double nr = (double)(t.rlist.size() / 2 - t.rstart[k]), nc = (double)(t.clist.size() / 2 - t.cstart[k]);
+    double nr = 0, nc = 0;
+    for (int i = k + 1; i < n; ++i) { if (t.rf[i] <= k) nr += 1; if (t.cf[i] <= k) nc += 1; }
     t.flops += nr + 2.0 * nr * nc;
+    if (k < nh) { const double er = t.nrb[k] + t.nbord, ec = t.ncb[k] + t.nbord; t.flops_envelope += er + 2.0 * er * ec; }
+    else { const double e = n - 1 - k; t.flops_envelope += e + 2.0 * e * e; }
   }
-  t.rstart[n] = (int)t.rlist.size() / 2; t.cstart[n] = (int)t.clist.size() / 2;
 }
 
 namespace {

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -91,7 +92,7 @@ slu_test_kernel(const double *__restrict__ a, const double *__restrict__ b, doub
   for (int e = tid; e < n * n; e += nt) {
     const int col = e / n, row = e - col * n;
     const int pi = spos[row], pj = spos[col];
-    const bool inside = (pi <= pj) ? ((int)I.cf[pj] <= pi) : ((int)I.rf[pi] <= pj);
+    const bool inside = pi >= I.nh || (slu_cf(I, pj) <= pi && pi <= slu_cbot(I, pj));
     const double v = A[e];
     if (inside) S[slu_addr(I, pi, pj)] = v;
     else if (v != 0.0) s->flag = 2;
@@ -101,11 +102,11 @@ slu_test_kernel(const double *__restrict__ a, const double *__restrict__ b, doub
   int *ipiv = reinterpret_cast<int *>(s->g_jac + (size_t)(n + 1) * n);
   if (mode < 2) {
     if (mode == 0) {
-      slu_factor(S, zm.rhs, zm.rdiag, s->slu_ipb, &s->slu_fail, true, D.nwl);
+      slu_factor(S, true);
       __syncthreads();
       slu_solve(S, zm.rhs, zm.rdiag, s->slu_ipb, true);
     } else {
-      slu_factor(S, zm.part, zm.rdiag, s->slu_ipb, &s->slu_fail, false, D.nwl);
+      slu_factor(S, false);
       __syncthreads();
       slu_solve(S, zm.rhs, zm.rdiag, s->slu_ipb, false);
     }
@@ -142,9 +143,11 @@ static SmemOff slu_layout(int ny, int n, int nstore, int npart, int nzs, int *of
   L.rdiag = (int)o; o += (size_t)n * 8; al();
   L.part = (int)o; o += (size_t)npart * 8; al();
   L.fhs = (int)o; o += (size_t)2 * nzs * 8; al();
-  *off_tab = (int)o; o += ((size_t)7 * n + 2) * 2; al();   // rf, cf, lo, uo, rhi, chi [n] each, pbk [n+1]
+  *off_tab = (int)o; o += ((size_t)n + 1) * 8; al();   // column table [n+1]
   L.prow = L.indx = L.orig = L.pos = L.scal;    // not used by the structured path
   L.lds2 = 0; L.lu_s = L.lu_u = (int)o;
+  // slu_factor's row loops read (and drop) up to 8 rows past a column / past the border block: keep that inside the CTA's memory
+  o = std::max(o, (size_t)L.jac + ((size_t)nstore + 16) * 8); al();
   L.cs = (int)o;
   L.total = (int)o;
   return L;
@@ -163,23 +166,11 @@ int xb_slu_configure(xb_ctx *c) {
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, c->device));
   const size_t max_smem = prop.sharedMemPerBlockOptin, sm_smem = prop.sharedMemPerMultiprocessor;
-  // 16-bit tables: rf, cf, lo, uo, rhi, chi (last band row / column with an entry in column / row k)
-  std::vector<unsigned short> tab((size_t)6 * n, 0);
   const int nh = n - T.nbord;
-  for (int p = 0; p < n; ++p) {
-    tab[p] = (unsigned short)T.rf[p]; tab[n + p] = (unsigned short)T.cf[p];
-    if (T.lo[p] < 0 || T.uo[p] < 0) {
-      // lo/uo are bases minus the first index: non-negative because rows/columns are stored in position order
-      return fail(XB_ERR_UNSUPPORTED, "structured LU: negative address base");
-    }
-    tab[2 * n + p] = (unsigned short)T.lo[p]; tab[3 * n + p] = (unsigned short)T.uo[p];
-    int rhi = p, chi = p;
-    for (int i = p + 1; i < nh; ++i) { if (T.rf[i] <= p) rhi = i; if (T.cf[i] <= p) chi = i; }
-    tab[4 * n + p] = (unsigned short)rhi; tab[5 * n + p] = (unsigned short)chi;
-  }
-  CUDA_TRY(c->slu_tab16.put(tab));
+  for (int k = 0; k < nh; ++k)
+    if (T.nrb[k] > 255 || T.ncb[k] > 255) return fail(XB_ERR_UNSUPPORTED, "structured LU: band wider than 255");
   CUDA_TRY(c->slu_pos.put(T.pos));
-  // threads per zone: 128 when four or more zones fit on an SM, else 256 (XB_SLU_THREADS overrides)
+  // threads per zone: 128 when three or more zones fit on an SM, else 256 (XB_SLU_THREADS overrides)
   DevNet &d = c->dn_slu;
   d = c->dn;
   int threads = 128;
@@ -190,7 +181,7 @@ int xb_slu_configure(xb_ctx *c) {
     if ((size_t)L.total + 64 > max_smem) return fail(XB_ERR_UNSUPPORTED, "structured LU: the zone does not fit in shared memory");
     const int per_sm_smem = (int)(sm_smem / ((size_t)L.total + 1024 + 64));
     const int want = env_int("XB_SLU_THREADS", 0);
-    const int t2 = want > 0 ? want : (per_sm_smem >= 4 ? 128 : 256);
+    const int t2 = want > 0 ? want : (per_sm_smem >= 3 ? 128 : 256);
     d.lay = L; d.slu.off_tab = off_tab;
     if (t2 == threads) break;
     if (t2 != 64 && t2 != 128 && t2 != 256) return fail(XB_ERR_ARG, "XB_SLU_THREADS must be 64, 128 or 256");
@@ -210,46 +201,26 @@ int xb_slu_configure(xb_ctx *c) {
   d.slu.on = 1; d.slu.n = n; d.slu.nstore = T.nstore; d.slu.nbord = T.nbord;
   d.slu.nwl = std::max(1, std::min(env_int("XB_SLU_NWL", threads / 32), threads / 32));
   d.slu.force_fb = env_int("XB_SLU_FORCE_FALLBACK", 0);
-  d.slu.tab16 = c->slu_tab16.p; d.slu.pos = c->slu_pos.p;
+  d.slu.pos = c->slu_pos.p;
+  d.slu.itau = 1.0 / d.slu.tau;
+  d.slu.bo = T.bo; d.slu.bs = T.bs;
   {
-    // elimination schedule of the heavy part (see slu_factor): per pivot the cross product of its rows and columns,
-    // column by column (consecutive lanes -> consecutive rows), then the right-hand-side entries; padded to whole blocks
-    // of ntl = 32*nwl entries, first block of every pivot flagged
-    const int ntl = 32 * d.slu.nwl;
+    // staged tables: per column cb | cf << 16 (entry n = the right-hand side as a pseudo-column), per pivot ncb | nrb << 8
     const int rhs_off = (d.lay.rhs - d.lay.jac) / 8;
     if (rhs_off < T.nstore || rhs_off + n >= 0xffff) return fail(XB_ERR_UNSUPPORTED, "structured LU: store too large for 16-bit addresses");
     d.slu.rhs_off = rhs_off;
-    std::vector<uint2> sch;
-    std::vector<unsigned short> pbk(nh + 1, 0);
-    for (int k = 0; k < nh; ++k) {
-      const size_t first = sch.size();
-      const int r0 = T.rstart[k], r1 = T.rstart[k + 1], c0 = T.cstart[k], c1 = T.cstart[k + 1];
-      auto entry = [&](unsigned a, unsigned b, unsigned cc, unsigned fl) { sch.push_back(make_uint2(a | (b << 16), cc | (fl << 16))); };
-      for (int cI = c0; cI < c1; ++cI) {
-        const int j = T.clist[2 * cI], uoj = T.clist[2 * cI + 1];
-        for (int rI = r0; rI < r1; ++rI) {
-          const int i = T.rlist[2 * rI], loi = T.rlist[2 * rI + 1];
-          const unsigned a = (unsigned)((i <= j) ? uoj + i : loi + j);
-          entry(a, (unsigned)(loi + k), (unsigned)(uoj + k), (i >= d.slu.ntest) ? 1u : 0u);
-        }
-      }
-      for (int rI = r0; rI < r1; ++rI) {
-        const int i = T.rlist[2 * rI], loi = T.rlist[2 * rI + 1];
-        entry((unsigned)(rhs_off + i), (unsigned)(loi + k), (unsigned)(rhs_off + k), 4u | ((i >= d.slu.ntest) ? 1u : 0u));
-      }
-      if (sch.size() == first) entry(0xffffu, 0u, 0u, 0u);                       // a pivot without work still needs its block
-      while ((sch.size() - first) % ntl) entry(0xffffu, 0u, 0u, 0u);
-      pbk[k] = (unsigned short)(first / ntl);
+    d.slu.tab_rel = (d.slu.off_tab - d.lay.jac) / 8;
+    d.slu.rinv_off = (d.lay.rdiag - d.lay.jac) / 8;
+    d.slu.fail_rel = (d.lay.scal + (int)offsetof(ZoneScalars, slu_fail) - d.lay.jac) / 4;
+    std::vector<uint2> tab((size_t)n + 1, make_uint2(0u, 0u));
+    for (int j = 0; j < n; ++j) {
+      if (T.cb[j] < 0) return fail(XB_ERR_UNSUPPORTED, "structured LU: negative column base");
+      tab[j].x = (unsigned)T.cb[j] | ((unsigned)T.cf[j] << 16);
+      if (j < nh) tab[j].y = (unsigned)T.ncb[j] | ((unsigned)T.nrb[j] << 8);
     }
-    if (sch.size() / ntl >= (size_t)0xffff) return fail(XB_ERR_UNSUPPORTED, "structured LU: schedule too long");
-    pbk[nh] = (unsigned short)(sch.size() / ntl);
-    d.slu.nblk = (int)(sch.size() / ntl);
-    CUDA_TRY(c->slu_sched.put(sch));
-    d.slu.sched = c->slu_sched.p;
-    tab.resize((size_t)7 * n + 2, 0);
-    for (int k = 0; k <= nh; ++k) tab[(size_t)6 * n + k] = pbk[k];
-    CUDA_TRY(c->slu_tab16.put(tab));
-    d.slu.tab16 = c->slu_tab16.p;
+    tab[n].x = (unsigned)rhs_off;
+    CUDA_TRY(c->slu_tabd.put(tab));
+    d.slu.tab = c->slu_tabd.p;
   }
   // zones per SM by shared memory, then whatever is left on the SM caches csect (tail of the reaction list first)
   SmemOff &L = d.lay;
@@ -293,7 +264,7 @@ int xb_slu_configure(xb_ctx *c) {
 }
 
 void xb_slu_release(xb_ctx *c) {
-  c->slu_tab16.release(); c->slu_pos.release(); c->scratch_slu.release(); c->slu_sched.release();
+  c->slu_tabd.release(); c->slu_pos.release(); c->scratch_slu.release();
   xb_ctx::PlanBufs *pb[] = {&c->pby_slu, &c->pbj_slu};
   for (auto *b : pb) {
     b->a.release(); b->nn.release(); b->mc.release(); b->seg_start.release(); b->seg_dest.release();

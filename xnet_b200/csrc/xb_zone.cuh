@@ -31,8 +31,9 @@ struct ZoneScalars {
   int kmon[5], ktot[5];
   int inr, its, flag, piv, info, tile_ctr;
   int rhs_in_jac;            // global-memory Jacobian: the right-hand side rides as column N of the per-CTA scratch (fused path)
-  int slu_fail, slu_fail_k, lu_dense, nlu_zone;   // structured LU: threshold test failed (+ first violated column) / factors are the dense fallback's / factorisations so far
+  int slu_fail, slu_fail_k;  // structured LU: threshold test failed, first violated column.  slu_fail, slu_fail_k, slu_ipb stay adjacent (slu_factor)
   int slu_ipb[8];            // interchanges of the border block
+  int lu_dense, nlu_zone;   // factors are the dense fallback's / factorisations so far
   long long ph[PH_COUNT];    // see enum Phase
   long long tmark, dmark;
 };
@@ -868,16 +869,17 @@ __device__ __noinline__ void jacobian_build_cta() {
     const SluIdx I = slu_idx();
     const int n = I.n, ny = net.ny, nh = I.nh;
     const DevPlan &Py = net.py;
-    const int uoT = (int)I.uo[n - 1];       // column n-1: d ydot_i / d T9 (xnet_jacobian_dense.F90:343-399)
+    const int cbT = slu_cb(I, n - 1);       // column n-1 (a border column: every heavy row stored): d ydot_i / d T9 (xnet_jacobian_dense.F90:343-399)
     const int *__restrict__ spos = D.pos;
+    auto t9col = [&](const int eq) { const int pi = spos[eq]; return (pi >= nh) ? I.bo + (n - 1) * I.bs + (pi - nh) : cbT + pi; };
     plan_run_fast(Py, zm.dcsect, zm.cs_sm, net.nrtot, zm.yt, [&](unsigned ctl_, double acc) {
-      if ((ctl_ & 3u) == 1u) S[uoT + spos[ctl_ >> 3]] = acc; else part[ctl_ >> 3] = acc;
+      if ((ctl_ & 3u) == 1u) S[t9col(ctl_ >> 3)] = acc; else part[ctl_ >> 3] = acc;
     });
     __syncthreads();
     for (int m = tid; m < Py.nmulti; m += nt) {
       double sm = 0.0;
       for (int q = Py.multi_start[m]; q < Py.multi_start[m + 1]; ++q) sm += part[q];
-      S[uoT + spos[Py.multi_dest[m] >> 1]] = sm;
+      S[t9col(Py.multi_dest[m] >> 1)] = sm;
     }
     __syncthreads();
     // row n-1: d t9dot / d(y_j, T9) = - sum_i mex_i dydotdy(i, j) / cv over the stored rows of column j
@@ -887,25 +889,21 @@ __device__ __noinline__ void jacobian_build_cta() {
     for (int i = tid; i < ny; i += nt) mexp[spos[i]] = net.mex[i];
     __syncthreads();
     const double cv = zm.s->cv;
+    const int nbq = I.nb;
     for (int pj = tid; pj < n; pj += nt) {
       double s0 = 0.0;
-      const int uoj = (int)I.uo[pj];
-      for (int r = (int)I.cf[pj]; r <= pj; ++r) s0 = fma(mexp[r], S[uoj + r], s0);
-      if (pj < nh) {
-        for (int i = pj + 1; i <= (int)I.rhi[pj]; ++i) if ((int)I.rf[i] <= pj) s0 = fma(mexp[i], S[(int)I.lo[i] + pj], s0);
-        for (int i = nh; i < n; ++i) s0 = fma(mexp[i], S[(int)I.lo[i] + pj], s0);
-      } else {
-        for (int i = pj + 1; i < n; ++i) s0 = fma(mexp[i], S[(int)I.lo[i] + pj], s0);
-      }
-      const double v = -s0 / cv;
-      if (pj < n - 1) S[(int)I.lo[n - 1] + pj] = v; else S[uoj + pj] = v;
+      const int cbj = slu_cb(I, pj);
+      const int r1 = slu_cbot(I, pj);
+      for (int r = slu_cf(I, pj); r <= r1; ++r) s0 = fma(mexp[r], S[cbj + r], s0);
+      for (int r = 0; r < nbq - 1; ++r) s0 = fma(mexp[nh + r], S[I.bo + pj * I.bs + r], s0);
+      S[I.bo + pj * I.bs + nbq - 1] = -s0 / cv;
     }
     __syncthreads();
     // jacobian_scale: jac = mult * dydotdy^T + diag on the diagonal
     const double rdt = zm.s->rdt, m = zm.s->mult;
     for (int e = tid; e < D.nstore; e += nt) S[e] *= m;
     __syncthreads();
-    for (int p = tid; p < n; p += nt) S[(int)I.uo[p] + p] += rdt;
+    for (int p = tid; p < n; p += nt) S[slu_addr(I, p, p)] += rdt;
     __syncthreads();
   }
 }
@@ -991,7 +989,7 @@ __device__ __noinline__ void step_be_cta() {
     if (tid == 0 && rebuild) { s->slu_fail = 0; s->slu_fail_k = 0x7fffffff; s->nlu_zone += 1; }
     __syncthreads();
     if (rebuild) {
-      slu_factor(zm.jac, zm.rhs, zm.rdiag, s->slu_ipb, &s->slu_fail, true, net.slu.nwl);
+      slu_factor(zm.jac, true);
       __syncthreads();
       const bool forced = net.slu.force_fb > 0 && (s->nlu_zone % net.slu.force_fb) == 0;
       if (s->slu_fail != 0 || forced) {
