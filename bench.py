@@ -480,6 +480,8 @@ def main():
     ms_launch = sum(kern_ms) / len(kern_ms)
     achieved = lu_flops / (ms_launch * 1e-3) / 1e12
     phase_tot = max(ph['total'], 1.0)
+    if os.environ.get('XB_DUMP_PHASES'):
+        sys.stderr.write('phases per Newton iteration: %s\n' % {k: round(v / max(newton, 1.0), 1) for k, v in ph.items()})
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))

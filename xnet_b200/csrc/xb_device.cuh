@@ -38,7 +38,8 @@ struct DevSlu {
   int ntest;                                 // rows 0..ntest-1 are subject to the threshold test (all but the T9 row)
   int on, n, nstore, nbord, nwl, force_fb;   // nwl: warps that factor; force_fb > 0: every force_fb-th LU takes the dense fallback (tests)
   int off_tab, tab_rel;                      // staged table: byte offset in shared memory; 64-bit entries relative to the store S
-  int bo, bs, rhs_off, rinv_off;             // border rows: base and column stride (doubles); rhs = S + rhs_off, rdiag = S + rinv_off
+  int bo, bs, rhs_off;                       // border rows: base and column stride (doubles); rhs = S + rhs_off
+  int ph_rel;                                // ZoneScalars::ph as a 64-bit word offset from S (profiling build)
   int fail_rel;                              // ZoneScalars::slu_fail as a 32-bit word offset from S (negative: the scalars precede the store)
   const uint2 *tab;                          // [n+1] x = cb | cf << 16 (entry n: the right-hand side), y = ncb | nrb << 8
   const int *pos;                            // [n] equation (species, then T9) -> position in the reordered system

@@ -439,7 +439,7 @@ void structured_lu_tables(const Network &net, int heat, SluTables &t) {
     t.nrb[k] = rhi - k; t.ncb[k] = chi - k; t.cbot[k] = rhi;
   }
   t.cb.resize(n);
-  int padw = 8;                                      // XB_SLU_PADW = 1 (no padding) .. 16 (conflict-free half-warps)
+  int padw = 16;                                     // XB_SLU_PADW = 1 (no padding) .. 16 (any 16 consecutive columns: 16 distinct bank pairs)
   if (const char *v = std::getenv("XB_SLU_PADW")) if (*v) padw = std::min(16, std::max(1, std::atoi(v)));
   int o = 0;
   for (int j = 0; j < n; ++j) {

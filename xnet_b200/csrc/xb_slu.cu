@@ -104,11 +104,11 @@ slu_test_kernel(const double *__restrict__ a, const double *__restrict__ b, doub
     if (mode == 0) {
       slu_factor(S, true);
       __syncthreads();
-      slu_solve(S, zm.rhs, zm.rdiag, s->slu_ipb, true);
+      slu_solve(S, zm.rhs, s->slu_ipb, true);
     } else {
       slu_factor(S, false);
       __syncthreads();
-      slu_solve(S, zm.rhs, zm.rdiag, s->slu_ipb, false);
+      slu_solve(S, zm.rhs, s->slu_ipb, false);
     }
   } else {
     slu_dense_factor(S, zm.rhs, s->g_jac, ipiv, zm.part, &s->info);
@@ -130,21 +130,24 @@ int env_int(const char *name, int dflt) {
 }  // namespace
 
 // Shared-memory carve-up of one zone of the structured kernel
-static SmemOff slu_layout(int ny, int n, int nstore, int npart, int nzs, int *off_tab) {
+static SmemOff slu_layout(int ny, int n, int nstore, int npart, int nzs, int *off_tab, unsigned rhs_avoid) {
   SmemOff L{};
   size_t o = 0;
   auto al = [&]() { o = (o + 15) / 16 * 16; };
   L.scal = (int)o; o += sizeof(ZoneScalars); al();
   L.jac = (int)o; o += (size_t)nstore * 8; al();
+  // the right-hand side is one more column of the elimination: its base (in doubles from S) avoids the bank pairs of the
+  // border columns it shares a half-warp with
+  while ((rhs_avoid >> (((o - L.jac) / 8) % 16)) & 1u) o += 8;
   L.rhs = (int)o; o += (size_t)n * 8;
   L.y = (int)o; o += (size_t)ny * 8;
   L.yt = (int)o; o += (size_t)(ny + 1) * 8;
   L.ydot = (int)o; o += (size_t)ny * 8;
-  L.rdiag = (int)o; o += (size_t)n * 8; al();
+  al();
   L.part = (int)o; o += (size_t)npart * 8; al();
   L.fhs = (int)o; o += (size_t)2 * nzs * 8; al();
   *off_tab = (int)o; o += ((size_t)n + 1) * 8; al();   // column table [n+1]
-  L.prow = L.indx = L.orig = L.pos = L.scal;    // not used by the structured path
+  L.rdiag = L.prow = L.indx = L.orig = L.pos = L.scal;    // not used by the structured path (the reciprocals of the pivots replace U's diagonal)
   L.lds2 = 0; L.lu_s = L.lu_u = (int)o;
   // slu_factor's row loops read (and drop) up to 8 rows past a column / past the border block: keep that inside the CTA's memory
   o = std::max(o, (size_t)L.jac + ((size_t)nstore + 16) * 8); al();
@@ -170,6 +173,8 @@ int xb_slu_configure(xb_ctx *c) {
   for (int k = 0; k < nh; ++k)
     if (T.nrb[k] > 255 || T.ncb[k] > 255) return fail(XB_ERR_UNSUPPORTED, "structured LU: band wider than 255");
   CUDA_TRY(c->slu_pos.put(T.pos));
+  unsigned rhs_avoid = 0;
+  for (int j = nh; j < n; ++j) rhs_avoid |= 1u << (((T.cb[j] % 16) + 16) % 16);
   // threads per zone: 128 when three or more zones fit on an SM, else 256 (XB_SLU_THREADS overrides)
   DevNet &d = c->dn_slu;
   d = c->dn;
@@ -177,7 +182,7 @@ int xb_slu_configure(xb_ctx *c) {
   for (int pass = 0; pass < 2; ++pass) {
     int rc = build_plans(c, d, c->pby_slu, c->pbj_slu, threads, n, &c->slu_npart, &T); if (rc) return rc;
     int off_tab = 0;
-    SmemOff L = slu_layout(ny, n, T.nstore, c->slu_npart, d.nzs, &off_tab);
+    SmemOff L = slu_layout(ny, n, T.nstore, c->slu_npart, d.nzs, &off_tab, rhs_avoid);
     if ((size_t)L.total + 64 > max_smem) return fail(XB_ERR_UNSUPPORTED, "structured LU: the zone does not fit in shared memory");
     const int per_sm_smem = (int)(sm_smem / ((size_t)L.total + 1024 + 64));
     const int want = env_int("XB_SLU_THREADS", 0);
@@ -191,7 +196,7 @@ int xb_slu_configure(xb_ctx *c) {
   {
     int off_tab = 0;
     int rc = build_plans(c, d, c->pby_slu, c->pbj_slu, threads, n, &c->slu_npart, &T); if (rc) return rc;
-    SmemOff L = slu_layout(ny, n, T.nstore, c->slu_npart, d.nzs, &off_tab);
+    SmemOff L = slu_layout(ny, n, T.nstore, c->slu_npart, d.nzs, &off_tab, rhs_avoid);
     d.lay = L; d.slu.off_tab = off_tab;
   }
   c->slu_threads = threads;
@@ -210,7 +215,7 @@ int xb_slu_configure(xb_ctx *c) {
     if (rhs_off < T.nstore || rhs_off + n >= 0xffff) return fail(XB_ERR_UNSUPPORTED, "structured LU: store too large for 16-bit addresses");
     d.slu.rhs_off = rhs_off;
     d.slu.tab_rel = (d.slu.off_tab - d.lay.jac) / 8;
-    d.slu.rinv_off = (d.lay.rdiag - d.lay.jac) / 8;
+    d.slu.ph_rel = (d.lay.scal + (int)offsetof(ZoneScalars, ph) - d.lay.jac) / 8;
     d.slu.fail_rel = (d.lay.scal + (int)offsetof(ZoneScalars, slu_fail) - d.lay.jac) / 4;
     std::vector<uint2> tab((size_t)n + 1, make_uint2(0u, 0u));
     for (int j = 0; j < n; ++j) {

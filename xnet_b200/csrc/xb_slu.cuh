@@ -39,7 +39,6 @@ namespace xb {
 // factorisations have a multiplier above 10 (always the proton row against ga64 / ge63, whose diagonal has cancelled
 // by the time it is the pivot), the largest is 222, and the solutions of those systems are as close to an
 // extended-precision solve as LAPACK's partial-pivoting ones: the growth that a large multiplier could cause does not occur.
-// (The heavy-column test compares the upper 32 bits of the doubles: a relative slack of 2^-20 on the threshold.)
 constexpr double kSluTauDefault = 1.0e-3;
 constexpr int kSluBord = 8;     // border rows/columns handled in registers (light particles + T9 <= 7)
 
@@ -71,35 +70,38 @@ __device__ __forceinline__ int slu_addr(const SluIdx &I, const int i, const int 
   return (i >= I.nh) ? I.bo + j * I.bs + (i - I.nh) : slu_cb(I, j) + i;
 }
 
-// Shared-memory accesses of the elimination's row loops as VOLATILE PTX with compile-time offsets: volatile accesses keep
-// their program order through ptxas, which otherwise sinks each load to its use (load - multiply-add - store, one
-// element after the other: eight exposed shared-memory latencies per chunk instead of one).
-template <int OFF>
-__device__ __forceinline__ double slu_lds(const unsigned addr) {
-  double v;
-  asm volatile("ld.volatile.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
-  return v;
+// One chunk of a pivot's update, eight rows of this lane's column:  a[t] -= l[t] * u,  stored for t < nleft, as ONE block
+// of PTX in exactly the order the hardware should see: the 16 loads, a warp-level ordering point that keeps ptxas from
+// sinking the loads to their uses (load - multiply-add - store chains, eight exposed latencies), the multiply-adds, the
+// predicated stores.  Every load is unconditional (a conditionally written register would have to be kept alive around
+// the pivot loop: ptxas spills it): rows past the span read what follows in the store, idle lanes are handed the
+// multipliers' address (a broadcast the warp performs anyway); nothing of that is stored.
+// lp / ap: shared addresses of the multipliers (the same for every lane) and of the column segment; un = -u.
+// Returns a[0] (the next pivot, for the lane that owns it).
+__device__ __forceinline__ double slu_chunk8(const unsigned lp, const unsigned ap, const int nleft, const double un) {
+  double a0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p0, p1, p2, p3, p4, p5, p6, p7;\n\t"
+      ".reg .f64 l0, l1, l2, l3, l4, l5, l6, l7, a0, a1, a2, a3, a4, a5, a6, a7;\n\t"
+      "ld.shared.f64 l0, [%1];\n\tld.shared.f64 l1, [%1+8];\n\tld.shared.f64 l2, [%1+16];\n\tld.shared.f64 l3, [%1+24];\n\t"
+      "ld.shared.f64 l4, [%1+32];\n\tld.shared.f64 l5, [%1+40];\n\tld.shared.f64 l6, [%1+48];\n\tld.shared.f64 l7, [%1+56];\n\t"
+      "ld.shared.f64 a0, [%2];\n\tld.shared.f64 a1, [%2+8];\n\tld.shared.f64 a2, [%2+16];\n\tld.shared.f64 a3, [%2+24];\n\t"
+      "ld.shared.f64 a4, [%2+32];\n\tld.shared.f64 a5, [%2+40];\n\tld.shared.f64 a6, [%2+48];\n\tld.shared.f64 a7, [%2+56];\n\t"
+      "setp.gt.s32 p0, %3, 0;\n\tsetp.gt.s32 p1, %3, 1;\n\tsetp.gt.s32 p2, %3, 2;\n\tsetp.gt.s32 p3, %3, 3;\n\t"
+      "setp.gt.s32 p4, %3, 4;\n\tsetp.gt.s32 p5, %3, 5;\n\tsetp.gt.s32 p6, %3, 6;\n\tsetp.gt.s32 p7, %3, 7;\n\t"
+      "bar.warp.sync 0xffffffff;\n\t"
+      "fma.rn.f64 a0, l0, %4, a0;\n\tfma.rn.f64 a1, l1, %4, a1;\n\tfma.rn.f64 a2, l2, %4, a2;\n\tfma.rn.f64 a3, l3, %4, a3;\n\t"
+      "fma.rn.f64 a4, l4, %4, a4;\n\tfma.rn.f64 a5, l5, %4, a5;\n\tfma.rn.f64 a6, l6, %4, a6;\n\tfma.rn.f64 a7, l7, %4, a7;\n\t"
+      "@p0 st.shared.f64 [%2], a0;\n\t@p1 st.shared.f64 [%2+8], a1;\n\t@p2 st.shared.f64 [%2+16], a2;\n\t@p3 st.shared.f64 [%2+24], a3;\n\t"
+      "@p4 st.shared.f64 [%2+32], a4;\n\t@p5 st.shared.f64 [%2+40], a5;\n\t@p6 st.shared.f64 [%2+48], a6;\n\t@p7 st.shared.f64 [%2+56], a7;\n\t"
+      "mov.f64 %0, a0;\n\t"
+      "}"
+      : "=d"(a0)
+      : "r"(lp), "r"(ap), "r"(nleft), "d"(un)
+      : "memory");
+  return a0;
 }
-template <int OFF>
-__device__ __forceinline__ void slu_sts(const unsigned addr, const double v, const int on) {     // predicated store: no branch
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.volatile.shared.f64 [%0+%1], %2;\n\t}" ::"r"(addr), "n"(OFF), "d"(v), "r"(on));
-}
-template <int T, int N>
-struct SluRow {     // rows T..N-1 of a chunk: all loads, then all multiply-adds, then the stores of the first nleft rows
-  static __device__ __forceinline__ void load(double (&l)[N], double (&a)[N], const unsigned lp, const unsigned ap) {
-    l[T] = slu_lds<8 * T>(lp); a[T] = slu_lds<8 * T>(ap);
-    SluRow<T + 1, N>::load(l, a, lp, ap);
-  }
-  static __device__ __forceinline__ void store(const double (&a)[N], const unsigned ap, const int nleft) {
-    slu_sts<8 * T>(ap, a[T], T < nleft);
-    SluRow<T + 1, N>::store(a, ap, nleft);
-  }
-};
-template <int N>
-struct SluRow<N, N> {
-  static __device__ __forceinline__ void load(double (&)[N], double (&)[N], const unsigned, const unsigned) {}
-  static __device__ __forceinline__ void store(const double (&)[N], const unsigned, const int) {}
-};
 
 __device__ __forceinline__ void slu_sync(const int nwl) {
   if (nwl == 1) __syncwarp(); else bar_named(1, nwl * 32);
@@ -110,7 +112,20 @@ __device__ __forceinline__ void slu_sync(const int nwl) {
 // with_rhs: the right-hand side (S + rhs_off, position order) is carried along as an extra column: it leaves as
 // L^-1 P b.  ZoneScalars::slu_fail is set when a heavy column violates the threshold test or a pivot is zero/NaN,
 // slu_fail_k receives the first such column (caller initialises it to a large value), slu_ipb the interchanges of the
-// border block; the reciprocals of the pivots go to rdiag.
+// border block.  On return the diagonal of U holds the RECIPROCALS of the pivots.
+//
+// The pivot loop is latency bound (a zone has four warps; an SM three or four zones): what counts is the number of
+// instructions and above all of branches on a warp's path through one pivot.  Hence: the lane -> column map is a
+// chain of selects, every warp owns exactly one chunk of rows per pivot (a warp without rows runs the chunk with a zero
+// store count), the rare wide pivots (more chunks than warps, more columns than lanes) take a separate loop.
+__device__ __forceinline__ int slu_slot_col(const int k, const int ncb, const int ncx, const int nh, const int c) {
+  // lane slots of a pivot: 0..15 the first 16 band columns (consecutive columns: 16 distinct banks per row), 16.. the
+  // border columns and the right-hand side, then the band columns past the 16th.  Returns the column (n = rhs) or -1.
+  const int e = c - 16, cc = e - ncx + 16;
+  const int lo = (c < ncb) ? k + 1 + c : -1;
+  const int hi = (e < ncx) ? nh + e : ((cc < ncb) ? k + 1 + cc : -1);
+  return (c < 16) ? lo : hi;
+}
 __device__ __noinline__ void slu_factor(double *__restrict__ S, const bool with_rhs) {
   XB_ASSUME_SHARED(S);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -118,10 +133,9 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S, const bool with_
   const int nwl = D.nwl;
   if (w >= nwl) return;
   const int n = D.n, nb = D.nbord, nh = n - nb, bo = D.bo, bs = D.bs;
-  // everything the loop touches is addressed relative to S (one shared-memory base): the index table, the reciprocals
-  // of the pivots (rdiag), the right-hand side
+  // everything the loop touches is addressed relative to S (one shared-memory base): the index table, the right-hand side
   const uint2 *__restrict__ tcol = reinterpret_cast<const uint2 *>(S) + D.tab_rel;
-  double *rhs = S + D.rhs_off, *rinv = S + D.rinv_off;
+  double *rhs = S + D.rhs_off;
   int *fail = reinterpret_cast<int *>(S) + D.fail_rel, *ipb = fail + 2;      // ZoneScalars::slu_fail, slu_fail_k, slu_ipb[8]
   const unsigned sS = (unsigned)__cvta_generic_to_shared(S);
   // The temperature equation (self-heating: the last row) is exempt from the test: it is the linear functional
@@ -133,57 +147,92 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S, const bool with_
   bool viol = false;
   // the border entries of the right-hand side ride in column n of the border block (same address rule as the matrix columns)
   if (with_rhs && w == 0 && lane < nb) S[bo + n * bs + lane] = rhs[nh + lane];
+  uint2 tk = tcol[0];
+  double rprev = 0.0; int dprev = -1;                // reciprocal of the previous pivot, stored over it one barrier later
+#ifdef XB_SLU_PROF
+  long long pt[5] = {0, 0, 0, 0, 0}, pc0 = clock64();
+#define SLU_PT(i) { const long long now_ = clock64(); pt[i] += now_ - pc0; pc0 = now_; }
+#else
+#define SLU_PT(i)
+#endif
   for (int k = 0; k < nh; ++k) {
+    SLU_PT(4)
     slu_sync(nwl);
-    const uint2 tk = tcol[k];
+    SLU_PT(0)
+    const uint2 tk1 = tcol[min(k + 1, nh - 1)];      // next pivot's entry, in flight during this one
     const int ncb = (int)(tk.y & 0xffu), nrb = (int)((tk.y >> 8) & 0xffu);
     const int cbk = (int)(tk.x & 0xffffu);
     const int lband = cbk + k + 1, lbord = bo + k * bs;   // multipliers (unscaled): band rows, border rows
     const double piv = S[lband - 1];
+    if (tid == 0 && dprev >= 0) S[dprev] = rprev;
+    const int j = slu_slot_col(k, ncb, ncx, nh, lane);
+    const unsigned tj = tcol[max(j, 0)].x;
     const double rk = pivot_rcp<false>(piv);
-    // |a(i,k)| > thr  <=>  tau |a(i,k)| > |a(k,k)|, compared on the upper words; a zero or NaN pivot fails every row
-    const double thr = fabs(piv) * itau;
-    const int thr_hi = (fabs(piv) > 0.0) ? __double2hiint(thr) : -1;
-    int lmax = 0;                                    // largest upper word of |multiplier| this thread has seen
-    if (tid == 0) rinv[k] = rk;
-    const int ncols = ncb + ncx;
+    const bool act = j >= 0 && (int)(tj >> 16) <= k;
+    const int cbj = (int)(tj & 0xffffu);
+    // idle lanes are handed the multipliers' addresses (broadcasts the warp performs anyway) and store nothing
+    const double un = -(S[act ? cbj + k : lband - 1] * rk);
+#ifdef XB_SLU_PROF
+    if (__double2hiint(un) == 0x7ff12345) viol = true;   // consume u: the time stamp below waits for the operand loads
+    SLU_PT(1)
+#endif
     const int nchunk = (nrb + 7) >> 3;               // chunks of band rows; chunk number nchunk = the border rows
+    {
+      const int q = w, r0 = q << 3;
+      const bool band = q < nchunk;
+      const int lpi = band ? lband + r0 : lbord;
+      const int api = act ? (band ? cbj + k + 1 + r0 : bo + j * bs) : lpi;
+      const int nrow = band ? nrb - r0 : ((q == nchunk) ? nb : 0);
+      slu_chunk8(sS + 8u * (unsigned)lpi, sS + 8u * (unsigned)api, act ? nrow : 0, un);
+    }
+    if (nchunk >= nwl || ncb + ncx > 32) {
+      // wide pivot: the chunks beyond one per warp, then the lane slots from 32 on with all their chunks
+      const int nslot = (ncb <= 16) ? 16 + ncx : ncb + ncx;
 #pragma unroll 1
-    for (int c0 = 0; c0 < ncols; c0 += 32) {
-      const int c = c0 + lane;
-      const bool valid = c < ncols;
-      const int j = valid ? ((c < ncb) ? k + 1 + c : nh + (c - ncb)) : k;
-      const unsigned tj = tcol[j].x;
-      const bool act = valid && (int)(tj >> 16) <= k;
-      // idle lanes read the pivot column (valid addresses, results dropped): no predicated loads in the row loops
-      const int cbj = act ? (int)(tj & 0xffffu) : cbk;
-      const double u = S[cbj + k] * rk;
+      for (int c0 = 0; c0 < nslot; c0 += 32) {
+        const int j2 = slu_slot_col(k, ncb, ncx, nh, c0 + lane);
+        const unsigned t2 = tcol[max(j2, 0)].x;
+        const bool act2 = j2 >= 0 && (int)(t2 >> 16) <= k;
+        const int cb2 = (int)(t2 & 0xffffu);
+        const double un2 = -(S[act2 ? cb2 + k : lband - 1] * rk);
 #pragma unroll 1
-      for (int q = w; q <= nchunk; q += nwl) {
-        // rows past the span / past the border read (and drop) what follows in the store
-        double l[8], a[8];
-        const bool band = q < nchunk;
-        const int r0 = q << 3;
-        const unsigned lp = sS + 8u * (unsigned)(band ? lband + r0 : lbord);
-        const unsigned ap = sS + 8u * (unsigned)(band ? cbj + k + 1 + r0 : bo + (act ? j : k) * bs);
-        const int nrow = band ? nrb - r0 : nb, ntst = band ? nrb - r0 : nbt;
-        SluRow<0, 8>::load(l, a, lp, ap);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          if (t < ntst) lmax = max(lmax, __double2hiint(l[t]) & 0x7fffffff);
-          a[t] = fma(-l[t], u, a[t]);
+        for (int q = (c0 == 0) ? w + nwl : w; q <= nchunk; q += nwl) {
+          const bool band = q < nchunk;
+          const int r0 = q << 3;
+          const int lpi = band ? lband + r0 : lbord;
+          const int api = act2 ? (band ? cb2 + k + 1 + r0 : bo + j2 * bs) : lpi;
+          slu_chunk8(sS + 8u * (unsigned)lpi, sS + 8u * (unsigned)api, act2 ? (band ? nrb - r0 : nb) : 0, un2);
         }
-        SluRow<0, 8>::store(a, ap, act ? nrow : 0);
       }
     }
-    if (lmax > thr_hi) { viol = true; atomicMin(fail + 1, k); }
+    SLU_PT(2)
+    // column test by the last warp that factors, lanes = rows: |a(i,k)| > thr  <=>  tau |a(i,k)| > |a(k,k)|
+    if (w == nwl - 1) {
+      const double apiv = fabs(piv), thr = apiv * itau;
+      const int nt_ = nrb + nbt;
+      double v = 0.0;
+      if (lane < nt_) v = fabs(S[(lane < nrb) ? lband + lane : lbord + (lane - nrb)]);
+      bool vk = !(apiv > 0.0) || v > thr;            // zero or NaN pivot fails
+#pragma unroll 1
+      for (int r = lane + 32; r < nt_; r += 32) vk |= fabs(S[(r < nrb) ? lband + r : lbord + (r - nrb)]) > thr;
+      if (vk) { viol = true; atomicMin(fail + 1, k); }
+    }
+    rprev = rk; dprev = lband - 1; tk = tk1;
+    SLU_PT(3)
   }
+#ifdef XB_SLU_PROF
+  if (lane == 0 && w == 0) {
+    long long *ph = reinterpret_cast<long long *>(S) + D.ph_rel;
+    for (int i = 0; i < 5; ++i) ph[PH_DBG0 + 4 + i] += pt[i];
+  }
+#endif
   slu_sync(nwl);
+  if (tid == 0 && dprev >= 0) S[dprev] = rprev;
   // ---- border block, one warp, lane c holds column c of the block (lane nb: the right-hand side).  The diagonal is
   // the pivot while it passes the threshold test against the tested rows below it; otherwise the largest entry of the
   // column (any row) is brought up.
   if (w == 0) {
-    double v[kSluBord];
+    double v[kSluBord], rb[kSluBord];
     const int c = lane;
     const bool mine = c < nb || (c == nb && with_rhs);
 #pragma unroll
@@ -191,7 +240,7 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S, const bool with_
     int sw[kSluBord];
 #pragma unroll
     for (int jj = 0; jj < kSluBord; ++jj) {
-      sw[jj] = jj;
+      sw[jj] = jj; rb[jj] = 0.0;
       if (jj < nb) {
         // lane jj: largest entry of column jj from the diagonal down (first maximum), and the largest among the tested rows
         double best = -1.0, bestt = -1.0; int p = jj;
@@ -214,7 +263,7 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S, const bool with_
         const double pv = __shfl_sync(kFull, v[jj], jj);
         if (!(fabs(pv) > 0.0)) viol = true;
         const double rk = pivot_rcp<false>(pv);
-        if (lane == 0) rinv[nh + jj] = rk;
+        rb[jj] = rk;
 #pragma unroll
         for (int r = 0; r < kSluBord; ++r) {
           if (r > jj && r < nb) {
@@ -227,7 +276,7 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S, const bool with_
 #pragma unroll
     for (int r = 0; r < kSluBord; ++r) {
       if (r < nb) {
-        if (c < nb) S[bo + (nh + c) * bs + r] = v[r];
+        if (c < nb) S[bo + (nh + c) * bs + r] = (r == c) ? rb[r] : v[r];       // reciprocal over the pivot
         else if (c == nb && with_rhs) rhs[nh + r] = v[r];
       }
     }
@@ -248,16 +297,18 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S, const bool with_
 
 // ---- triangular solves (all threads of the CTA enter) ------------------------------------------------------------------
 // fwd_done: b already holds L^-1 P b (it rode through slu_factor).  Otherwise: forward substitution with the unscaled
-// multipliers (warp 0), border interchanges first.  Then U x = y:
+// multipliers (warp 0), border interchanges first.  Then U x = y (the diagonal of U holds the reciprocals of the pivots):
 //   A  the border unknowns (warp 0, nb dependent steps);
 //   B  their columns are full: every heavy row takes its nb updates at once (all threads);
 //   C  the band, last column first (warp 0).  The 32 unknowns below the current one live in REGISTERS (lane = row mod
 //      32), x(k) travels by shuffle, U's entries and the reciprocal are loaded one step ahead: the dependent chain of a
 //      step is shuffle - multiply - multiply-add, no shared-memory round trip.  Rows further than 31 above the diagonal
 //      (a few outlier columns) are updated in shared memory before they enter the window.
-__device__ __noinline__ void slu_solve(const double *__restrict__ S, double *__restrict__ b, const double *__restrict__ rinv,
-                                       const int *ipb, const bool fwd_done) {
-  XB_ASSUME_SHARED(S); XB_ASSUME_SHARED(b); XB_ASSUME_SHARED(rinv); XB_ASSUME_SHARED(ipb);
+__device__ __forceinline__ int slu_diag(const SluIdx &I, const int k) {
+  return (k < I.nh) ? slu_cb(I, k) + k : I.bo + k * I.bs + (k - I.nh);
+}
+__device__ __noinline__ void slu_solve(const double *__restrict__ S, double *__restrict__ b, const int *ipb, const bool fwd_done) {
+  XB_ASSUME_SHARED(S); XB_ASSUME_SHARED(b); XB_ASSUME_SHARED(ipb);
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
   const bool w0 = tid < 32;
   const SluIdx I = slu_idx();
@@ -274,7 +325,7 @@ __device__ __noinline__ void slu_solve(const double *__restrict__ S, double *__r
       }
       __syncwarp();
       for (int k = 0; k < n; ++k) {
-        const double f = b[k] * rinv[k];
+        const double f = b[k] * S[slu_diag(I, k)];
         if (k < nh) {
           const int nrb = slu_nrb(I, k), cbk = slu_cb(I, k);
           for (int r = lane; r < nrb; r += 32) b[k + 1 + r] = fma(-S[cbk + k + 1 + r], f, b[k + 1 + r]);
@@ -288,7 +339,7 @@ __device__ __noinline__ void slu_solve(const double *__restrict__ S, double *__r
     }
     // A: border unknowns
     for (int k = n - 1; k >= nh; --k) {
-      const double x = b[k] * rinv[k];
+      const double x = b[k] * S[bo + k * bs + (k - nh)];
       __syncwarp();
       if (lane == 0) b[k] = x;
       const int i = nh + lane;
@@ -309,29 +360,31 @@ __device__ __noinline__ void slu_solve(const double *__restrict__ S, double *__r
   // C: the band
   if (w0 && nh > 0) {
     int k = nh - 1;
-    auto row_of = [&](const int kk) { return kk - ((kk - lane) & 31); };   // the window row this lane holds at step kk (kk itself for lane kk & 31)
-    auto load_u = [&](const unsigned t, const int kk) {
-      const int i = row_of(kk);
-      return (i != kk && i >= (int)(t >> 16)) ? S[(int)(t & 0xffffu) + i] : 0.0;     // i >= cf >= 0
+    const int lk = (k - lane) & 31;                // this lane's window row at step kk is kk - ((kk - lane) & 31): the offset drops by one per step
+    auto load_u = [&](const unsigned t, const int kk, const int off) {      // off = (kk - lane) & 31; row kk - off, off = 0: the unknown itself
+      const int i = kk - off;
+      return (off != 0 && i >= (int)(t >> 16)) ? S[(int)(t & 0xffffu) + i] : 0.0;     // i >= cf >= 0
     };
     double bv, be = 0.0;
-    { const int i = row_of(k); bv = (i >= 0) ? b[i] : 0.0; }
+    { const int i = k - lk; bv = (i >= 0) ? b[i] : 0.0; }
     unsigned t_cur = I.col[k].x, t_next = (k >= 1) ? I.col[k - 1].x : 0u;
-    double u_cur = load_u(t_cur, k), r_cur = rinv[k];
+    double u_cur = load_u(t_cur, k, lk), r_cur = S[(int)(t_cur & 0xffffu) + k];
+    int off = lk;
     for (; k >= 0; --k) {
-      const unsigned t_n2 = (k >= 2) ? I.col[k - 2].x : 0u;
-      const double u_next = (k >= 1) ? load_u(t_next, k - 1) : 0.0;
-      const double r_next = (k >= 1) ? rinv[k - 1] : 0.0;
+      const int offn = (off - 1) & 31;             // offset at step k-1
+      const unsigned t_n2 = I.col[max(k - 2, 0)].x;
+      const double u_next = load_u(t_next, k - 1, offn);                  // k = 0: t_next = 0 -> row -1 - offn < 0 is never >= cf... guarded below
+      const double r_next = S[(int)(t_next & 0xffffu) + max(k - 1, 0)];
       const double x = __shfl_sync(kFull, bv, k & 31) * r_cur;
-      if (k + 1 < nh && lane == ((k + 1) & 31)) bv = be;      // row k-31 enters the window (loaded a step ago)
+      if (off == 31 && k + 1 < nh) bv = be;       // row k-31 enters the window (loaded a step ago); off == 31 <=> lane == (k+1) & 31
       const int cfk = (int)(t_cur >> 16), cbk = (int)(t_cur & 0xffffu);
       if (cfk <= k - 32) {                                     // outlier column: rows above the window, in shared memory
         for (int i = cfk + lane; i <= k - 32; i += 32) b[i] = fma(-S[cbk + i], x, b[i]);
         __syncwarp();
       }
       bv = fma(-u_cur, x, bv);
-      if (lane == (k & 31)) { b[k] = x; be = (k >= 32) ? b[k - 32] : 0.0; }
-      t_cur = t_next; t_next = t_n2; u_cur = u_next; r_cur = r_next;
+      if (off == 0) { b[k] = x; be = (k >= 32) ? b[k - 32] : 0.0; }
+      t_cur = t_next; t_next = t_n2; u_cur = u_next; r_cur = r_next; off = offn;
     }
   }
 }

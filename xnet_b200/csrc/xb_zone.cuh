@@ -1011,7 +1011,7 @@ __device__ __noinline__ void step_be_cta() {
       XB_PHASE_END(zm, PH_LU);
     }
     if (s->lu_dense) slu_dense_solve(s->g_jac, reinterpret_cast<const int *>(s->g_jac + (size_t)(N + 1) * N), zm.rhs, rebuild);
-    else slu_solve(zm.jac, zm.rhs, zm.rdiag, s->slu_ipb, rebuild);
+    else slu_solve(zm.jac, zm.rhs, s->slu_ipb, rebuild);
     __syncthreads();
     XB_PHASE_END(zm, PH_BKSUB);
 #else
