@@ -196,6 +196,28 @@ def cpu_sample_zones(points, nfix, threads, target_iters, window):
     return per_pass * passes
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything any library writes to stdout from here on (NCCL prints its version there) goes to stderr; the one
+    JSON line of the contract is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def run_reference(args):
     # no process group: the reference arm has nothing to exchange; under torchrun rank 0 alone works and prints
     rank = int(os.environ.get('RANK', '0'))
@@ -219,7 +241,7 @@ def run_reference(args):
                        'window_steps': args.window, 'restart_points': args.points},
             'cpu_baseline': {'value': value, 'unit': 'zone-Newton-iterations/s', 'cores': arm.threads, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': 'zone-Newton-iterations/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_name(args, nz):
@@ -350,6 +372,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='only the headline measurement (value, e2e, roofline)')
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == 'reference':
         return run_reference(args)
 
@@ -550,7 +573,7 @@ def main():
                                 'sample': '%d zones, the same windows (up to %d accepted steps from %d restart points), OpenMP over zones with '
                                           'OMP_PROC_BIND=true on %d threads, C oracle -O3 -march=native (Fortran reference not buildable: '
                                           'no Fortran compiler); %.1f s' % (cz, args.window, args.points, cpu.threads, dt_cpu)}
-    print(json.dumps(line))
+    emit(line)
     arm.close()
     dist_teardown(world)
 

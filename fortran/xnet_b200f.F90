@@ -38,6 +38,9 @@ Module xnet_b200f
     Integer(C_INT) Function xb_net_from_arrays(arr,net) Bind(C,name="xb_net_from_arrays")
       Import ; Type(C_PTR), Value :: arr ; Type(C_PTR) :: net
     End Function
+    Integer(C_INT) Function xb_net_load_helm(net,path) Bind(C,name="xb_net_load_helm")
+      Import ; Type(C_PTR), Value :: net ; Character(kind=C_CHAR), Intent(in) :: path(*)
+    End Function
     Subroutine xb_net_free(net) Bind(C,name="xb_net_free")
       Import ; Type(C_PTR), Value :: net
     End Subroutine
@@ -55,6 +58,12 @@ Module xnet_b200f
     End Function
     Integer(C_INT) Function xb_jacobian_build(ctx,zlo,zhi,mask,diag,mult) Bind(C,name="xb_jacobian_build")
       Import ; Type(C_PTR), Value :: ctx, mask, diag, mult ; Integer(C_INT32_T), Value :: zlo, zhi
+    End Function
+    Integer(C_INT) Function xb_jacobian_scale(ctx,zlo,zhi,mask,diag,mult) Bind(C,name="xb_jacobian_scale")
+      Import ; Type(C_PTR), Value :: ctx, mask, diag, mult ; Integer(C_INT32_T), Value :: zlo, zhi
+    End Function
+    Integer(C_INT) Function xb_get_csect(ctx,zlo,zhi,csect) Bind(C,name="xb_get_csect")
+      Import ; Type(C_PTR), Value :: ctx, csect ; Integer(C_INT32_T), Value :: zlo, zhi
     End Function
     Integer(C_INT) Function xb_get_jac(ctx,zlo,zhi,jac) Bind(C,name="xb_get_jac")
       Import ; Type(C_PTR), Value :: ctx, jac ; Integer(C_INT32_T), Value :: zlo, zhi

@@ -8,9 +8,17 @@
 ! library call ends the run through xnet_terminate, the reference's one fatal path.
 !
 ! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Fortran compiler.  To use it,
-!   cp fortran/xnet_jacobian_b200.F90 fortran/xnet_b200f.F90 $XNET/source/
+!   cp fortran/xnet_jacobian_b200.F90 fortran/xnet_b200f.F90 fortran/xnet_integrate_b200.F90 $XNET/source/
 !   add `xnet_b200f.o` to BASE and `MATRIX_SOLVER = b200` to Makefile.opt, link with
 !   -L$REPO/xnet_b200 -lxnet_b200 -lcudart      (see INTEGRATION.md)
+!
+! Run-time switches (environment, read once in read_jacobian_data):
+!   XNET_B200_ARITH  = strict | fast (default strict: IEEE operation order and DGETRF's pivots, the mode that
+!                      reproduces the CPU build; fast = FMA, CUDA libm, threshold pivoting)
+!   XNET_B200_HELM   = path of the Helmholtz table (default helm_table.dat in the run directory, where
+!                      actual_eos_init reads it)
+! Threads: every call serialises on one launch mutex and one stream inside the library (the contexts of different
+! OpenMP threads may share a device); calls on disjoint zone slices are correct from any thread, they do not overlap.
 !***************************************************************************************************
 
 Module xnet_jacobian
@@ -39,13 +47,15 @@ Contains
     ! read_reaction_data / read_ffn_data built to the library (it copies; Fortran keeps ownership).
     Use nuclear_data, Only: ny, aa, zz, mex, be, mex_n, mex_p, g, t9i
     Use reaction_data
-    Use xnet_ffn, Only: ffnsum, ffnenu
+    Use xnet_ffn, Only: ffnsum, ffnenu, ffn_ec, ffn_beta, ffn_qval, has_logft
     Use xnet_match, Only: mflx, nflx, iwflx, qflx, ifl1, ifl2, ifl3, ifl4
     Use xnet_controls
     Implicit None
     Character(*), Intent(in) :: data_dir
     Type(xb_net_arrays), Target :: arr
     Type(xb_ctl_t), Target :: ctl
+    Character(len=512) :: env
+    Integer :: envlen, envstat
 
     msize = ny
     If ( iheat > 0 ) msize = ny + 1
@@ -67,17 +77,34 @@ Contains
     arr%mex_n = mex_n ; arr%mex_p = mex_p
     arr%g = c_loc(g) ; arr%t9i = c_loc(t9i)
     arr%ffnsum = c_loc(ffnsum) ; arr%ffnenu = c_loc(ffnenu)
+    ! logft weak rates (read_ffn_data_logft, xnet_ffn.F90:96-137): log(ft) and beta-decay tables, Q values, capture type
+    If ( abs(iweak0) == 2 ) Then
+      arr%ffn_ec = c_loc(ffn_ec) ; arr%ffn_beta = c_loc(ffn_beta)
+      arr%ffn_qval = c_loc(ffn_qval) ; arr%has_logft = c_loc(has_logft)
+    EndIf
     ! reaction pairs (read_match_data, xnet_match.F90:230-257, runs before read_jacobian_data in net.F90)
     arr%mflx = mflx
     arr%ifl = [ c_loc(ifl1), c_loc(ifl2), c_loc(ifl3), c_loc(ifl4) ]
     arr%nflx = c_loc(nflx) ; arr%iwflx = c_loc(iwflx) ; arr%qflx = c_loc(qflx)
     Call xb_check(xb_net_from_arrays(c_loc(arr),xb_net),'xb_net_from_arrays')
 
+    ! Screening and self-heating need the electron EoS: the library reads the same Helmholtz table that eos_initialize
+    ! (net.F90:138 -> actual_eos_init) reads on the host
+    If ( iscrn > 0 .or. iheat > 0 ) Then
+      Call get_environment_variable('XNET_B200_HELM',env,envlen,envstat)
+      If ( envstat /= 0 .or. envlen == 0 ) env = 'helm_table.dat'
+      Call xb_check(xb_net_load_helm(xb_net,trim(env)//C_NULL_CHAR),'xb_net_load_helm')
+    EndIf
+
     ctl%iweak0 = iweak0 ; ctl%iscrn = iscrn ; ctl%iheat = iheat ; ctl%isolv = isolv
     ctl%kstmx = kstmx ; ctl%kitmx = kitmx ; ctl%ijac = ijac ; ctl%iconvc = iconvc
     ctl%changemx = changemx ; ctl%changemxt = changemxt ; ctl%yacc = yacc ; ctl%tolm = tolm
     ctl%tolc = tolc ; ctl%tolt9 = tolt9 ; ctl%ymin = ymin ; ctl%tdel_maxmult = tdel_maxmult
-    ctl%arith = 0 ; ctl%solver = 0
+    ctl%arith = 1 ; ctl%solver = 0
+    Call get_environment_variable('XNET_B200_ARITH',env,envlen,envstat)
+    If ( envstat == 0 .and. envlen > 0 ) Then
+      If ( env(1:4) == 'fast' ) ctl%arith = 0
+    EndIf
     Call xb_check(xb_ctx_create(xb_net,c_loc(ctl),int(nzevolve,C_INT),int(mod(myid,max(1,ngpu)),C_INT),xb_ctx), &
       & 'xb_ctx_create')
     Return
@@ -105,8 +132,9 @@ Contains
   End Function mask_ptr
 
   Subroutine jacobian_build(diag_in,mult_in,mask_in)
-    ! Replaces jacobian_build + jacobian_scale (xnet_jacobian_dense.F90:136-434); yt, csect and b
-    ! stay device resident from the preceding cross_sect / yderiv calls of the b200 xnet_integrate.
+    ! Replaces jacobian_build (xnet_jacobian_dense.F90:257-434): dydotdy from the device-resident yt, csect (and, with
+    ! iheat > 0, dcsect/cv) of the preceding cross_sect / yderiv calls of the b200 xnet_integrate, kept on the device, then
+    ! jacobian_scale with the factors given here.
     Use xnet_controls, Only: zb_lo, zb_hi, idiag
     Real(dp), Optional, Target, Intent(in) :: diag_in(zb_lo:zb_hi), mult_in(zb_lo:zb_hi)
     Logical, Optional, Target, Intent(in) :: mask_in(zb_lo:zb_hi)
@@ -121,12 +149,20 @@ Contains
   End Subroutine jacobian_build
 
   Subroutine jacobian_scale(diag_in,mult_in,mask_in)
-    ! BDF calls jacobian_scale directly (xnet_integrate_bdf.F90:925-927): same device operation with
-    ! the dydotdy part reused; the library re-derives jac = mult*dydotdy^T + diag from its plan.
-    Use xnet_controls, Only: zb_lo, zb_hi
+    ! Replaces jacobian_scale (xnet_jacobian_dense.F90:136-255): jac = mult*dydotdy^T + diag from the dydotdy of the last
+    ! build, WITHOUT re-assembly -- BDF refactors with new (diag,mult) while yt and the rates have moved on
+    ! (xnet_integrate_bdf.F90:925-927: jacobian_build under `rebuild`, jacobian_scale under `refactor`).
+    Use xnet_controls, Only: zb_lo, zb_hi, idiag
     Real(dp), Optional, Target, Intent(in) :: diag_in(zb_lo:zb_hi), mult_in(zb_lo:zb_hi)
     Logical, Optional, Target, Intent(in) :: mask_in(zb_lo:zb_hi)
-    Call jacobian_build(diag_in,mult_in,mask_in)
+    Integer(C_INT), Target :: m(zb_lo:zb_hi)
+    Type(C_PTR) :: pd, pm
+    pd = C_NULL_PTR ; pm = C_NULL_PTR
+    If ( present(diag_in) ) pd = c_loc(diag_in)
+    If ( present(mult_in) ) pm = c_loc(mult_in)
+    Call xb_check(xb_jacobian_scale(xb_ctx,int(zb_lo,C_INT),int(zb_hi,C_INT),mask_ptr(mask_in,m),pd,pm), &
+      & 'xb_jacobian_scale')
+    If ( idiag >= 5 ) Call xb_check(xb_get_jac(xb_ctx,int(zb_lo,C_INT),int(zb_hi,C_INT),c_loc(jac(1,1,zb_lo))),'xb_get_jac')
   End Subroutine jacobian_scale
 
   Subroutine jacobian_decomp(kstep,mask_in)

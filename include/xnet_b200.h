@@ -21,7 +21,8 @@
  *   xb_ctx_destroy        <- jacobian_finalize (source/xnet_jacobian_dense.F90:121-134)
  *   xb_cross_sect         <- cross_sect (source/xnet_integrate.F90:569-984)
  *   xb_yderiv             <- yderiv (source/xnet_integrate.F90:364-567)
- *   xb_jacobian_build     <- jacobian_build + jacobian_scale (source/xnet_jacobian_dense.F90:136-434)
+ *   xb_jacobian_build     <- jacobian_build (source/xnet_jacobian_dense.F90:257-434)
+ *   xb_jacobian_scale     <- jacobian_scale (source/xnet_jacobian_dense.F90:136-255)
  *   xb_jacobian_decomp    <- jacobian_decomp -> LUDecompBatched_GPU/cublasDgetrfBatched
  *                            (source/xnet_jacobian_dense.F90:549-616, source/xnet_linalg.F90:1814-1870)
  *   xb_jacobian_bksub     <- jacobian_bksub -> cublasDgetrsBatched
@@ -141,7 +142,13 @@ int xb_cross_sect(xb_ctx *ctx, int32_t zlo, int32_t zhi, const int32_t *mask, co
 /* copies the device-resident csect back: csect[(nr1+nr2+nr3+nr4), nz] */
 int xb_get_csect(xb_ctx *ctx, int32_t zlo, int32_t zhi, double *csect);
 int xb_yderiv(xb_ctx *ctx, int32_t zlo, int32_t zhi, const int32_t *mask, const double *yt, double *ydot);
+/* jacobian_build (xnet_jacobian_dense.F90:257-434): dydotdy from the device-resident yt / csect (kept on the device,
+ * as the reference keeps its module array), then jacobian_scale.  diag / mult NULL = diag0 (0) / mult1 (1). */
 int xb_jacobian_build(xb_ctx *ctx, int32_t zlo, int32_t zhi, const int32_t *mask, const double *diag,
+                      const double *mult);
+/* jacobian_scale (xnet_jacobian_dense.F90:136-255): jac = mult * dydotdy^T + diag on the diagonal from the dydotdy of
+ * the last xb_jacobian_build, without re-assembly (BDF refactors this way, xnet_integrate_bdf.F90:925-927). */
+int xb_jacobian_scale(xb_ctx *ctx, int32_t zlo, int32_t zhi, const int32_t *mask, const double *diag,
                       const double *mult);
 /* copies jac(msize,msize,nz) back (idiag>=5 style inspection) */
 int xb_get_jac(xb_ctx *ctx, int32_t zlo, int32_t zhi, double *jac);

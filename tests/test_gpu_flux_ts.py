@@ -91,7 +91,7 @@ def test_fast_ts_file_against_oracle_prefix(gpu_problem, oracle_problem, tmp_pat
     ctx.close()
 
 
-@pytest.mark.parametrize('name', ['torch47', 'sn160_heat'])
+@pytest.mark.parametrize('name', ['torch47', 'sn160_heat', 'sn231_logft'])
 def test_network_from_fortran_arrays_runs_identically(gpu_problem, name):
     """The Fortran shim's route: a network handed over as module arrays (xb_net_from_arrays) gives bit-identical
     trajectories and fluxes to the network the library loads from the files itself."""

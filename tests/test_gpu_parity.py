@@ -436,3 +436,57 @@ def test_screened_rates_module_level(gpu_problem, oracle_problem, name, arith):
     cs0 = ctx0.csect(len(t9))
     assert (cs >= cs0).all() and (cs > cs0 * (1 + 1e-6)).any()
     ctx.close(); ctx0.close()
+
+
+# ---------------------------------------------------------------- the reference-side binding's call sequence
+@pytest.mark.parametrize('arith', [1, 0])
+@pytest.mark.parametrize('name', ['sn160_scrn', 'sn160_heat', 'sn231_logft'])
+def test_fortran_shim_call_sequence(gpu_problem, oracle_problem, name, arith):
+    """Exactly what fortran/xnet_jacobian_b200.F90 + xnet_integrate_b200.F90 do for test_settings (screening),
+    test_settings_heat and test_settings_logft: the network handed over as module arrays (xb_net_from_arrays, with the
+    logft tables), the Helmholtz table loaded because iscrn / iheat > 0 (xb_net_load_helm), then cross_sect(mask) ->
+    yderiv(mask) -> jacobian_build(diag, mult, mask) -> jacobian_scale(diag', mult') (BDF's refactor without rebuild,
+    xnet_integrate_bdf.F90:925-927) -> jacobian_decomp -> jacobian_bksub.  Checked against the library's own file-loaded
+    network driven the plain way (build with the final factors): strict arithmetic bit for bit, fast arithmetic to
+    round-off; masked-out zones keep their state."""
+    import xnet_b200 as X
+    from conftest import fortran_tables
+    ctl, net, fx = gpu_problem(name)
+    heat = ctl['iheat'] > 0
+    y, t9, rho, rdt = _states(oracle_problem(name), name, 4)
+    nz = len(t9)
+    mask = np.array([1, 1, 0, 1], np.int32)[:nz]
+    net2 = X.Network.from_fortran_arrays(fortran_tables(net), ctl['iweak0'])
+    net2.data_dir = net.data_dir
+    net2.load_helm()                                   # the shim's explicit xb_net_load_helm call
+    out = []
+    for n_, shim in ((net, False), (net2, True)):
+        ctx = X.Context(n_, ctl, nzevolve=nz, arith=arith)
+        mult = -np.ones(nz)
+        if shim:
+            ctx.cross_sect(y, t9, rho, mask=mask)
+            ydot = ctx.yderiv(y, mask=mask)
+            ctx.jacobian_build(nz, diag=0.37 * rdt, mult=-0.5 * np.ones(nz), mask=mask)      # some earlier (diag, mult)
+            ctx.jacobian_scale(nz, diag=rdt, mult=mult, mask=mask)                             # refactor only
+        else:
+            ctx.cross_sect(y, t9, rho)
+            ydot = ctx.yderiv(y)
+            ctx.jacobian_build(nz, diag=rdt, mult=mult)
+        jac = ctx.jac(nz)
+        info = ctx.jacobian_decomp(nz, mask=mask if shim else None)
+        rhs_t9 = np.linspace(1e-3, 2e-3, nz) if heat else None
+        dy = ctx.jacobian_bksub(ydot, t9rhs=rhs_t9, mask=mask if shim else None)
+        out.append((ydot, jac, info, dy))
+        ctx.close()
+    (yd0, j0, i0, d0), (yd1, j1, i1, d1) = out
+    on = mask.astype(bool)
+    dy0, dy1 = (d0[0], d1[0]) if isinstance(d0, tuple) else (d0, d1)
+    if arith:
+        assert np.array_equal(yd0[on], yd1[on]) and np.array_equal(j0[on], j1[on]) and np.array_equal(i0[on], i1[on])
+        assert np.array_equal(dy0[on], dy1[on])
+        if isinstance(d0, tuple):
+            assert np.array_equal(d0[1][on], d1[1][on])
+    else:
+        assert np.allclose(j0[on], j1[on], rtol=1e-13, atol=0) and np.allclose(dy0[on], dy1[on], rtol=1e-9, atol=1e-300)
+    # zones outside the mask were never evaluated through the shim path: the caller's ydot is untouched
+    assert not np.any(yd1[~on])

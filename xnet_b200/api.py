@@ -69,7 +69,7 @@ _lib = None
 # every symbol include/xnet_b200.h declares (tests check the library exports all of them)
 EXPORTS = ['xb_last_error', 'xb_version', 'xb_launch_count', 'xb_net_load', 'xb_net_load_helm', 'xb_net_from_arrays', 'xb_net_free',
            'xb_net_int', 'xb_net_itable', 'xb_net_dtable', 'xb_read_thermo', 'xb_read_inab', 'xb_zone_start',
-           'xb_ctx_create', 'xb_ctx_destroy', 'xb_cross_sect', 'xb_get_csect', 'xb_yderiv', 'xb_jacobian_build',
+           'xb_ctx_create', 'xb_ctx_destroy', 'xb_cross_sect', 'xb_get_csect', 'xb_yderiv', 'xb_jacobian_build', 'xb_jacobian_scale',
            'xb_get_jac', 'xb_set_jac', 'xb_jacobian_decomp', 'xb_get_indx', 'xb_jacobian_bksub',
            'xb_jacobian_solve', 'xb_get_dcsect', 'xb_get_eos', 'xb_flux', 'xb_set_flux_output', 'xb_step_be', 'xb_ts_write', 'xb_ev_write', 'xb_evolve', 'xb_zones_upload', 'xb_evolve_resident', 'xb_results_download',
            'xb_phase_cycles', 'xb_last_copy_bytes', 'xb_launch_config', 'xb_measure_fp64_peak', 'xb_last_kernel_ms', 'xb_solver_info', 'xb_slu_table', 'xb_slu_solve']
@@ -102,6 +102,7 @@ def lib():
         l.xb_get_csect.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_dp]
         l.xb_yderiv.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_ip, c_dp, c_dp]
         l.xb_jacobian_build.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_ip, c_dp, c_dp]
+        l.xb_jacobian_scale.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_ip, c_dp, c_dp]
         l.xb_get_jac.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_dp]
         l.xb_set_jac.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_dp]
         l.xb_jacobian_decomp.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_ip, c_ip]
@@ -486,6 +487,12 @@ class Context:
         d = None if diag is None else _d(diag); mu = None if mult is None else _d(mult)
         m = None if mask is None else _i(mask)
         _chk(lib().xb_jacobian_build(self.h, 1, nz, _pi(m), _pd(d), _pd(mu)))
+
+    def jacobian_scale(self, nz, diag=None, mult=None, mask=None):
+        """jacobian_scale: rescales the dydotdy of the last jacobian_build (no re-assembly)"""
+        d = None if diag is None else _d(diag); mu = None if mult is None else _d(mult)
+        m = None if mask is None else _i(mask)
+        _chk(lib().xb_jacobian_scale(self.h, 1, nz, _pi(m), _pd(d), _pd(mu)))
 
     def jac(self, nz):
         """jac[z, col, row] as it lies in memory (column-major per zone)."""

@@ -722,7 +722,7 @@ void xb_ctx_destroy(xb_ctx *c) {
   for (int k = 0; k < 4; ++k) { c->a[k].release(); c->mu[k].release(); for (int r = 0; r < 4; ++r) c->nn[k][r].release(); }
   c->scratch.release(); c->phase.release(); c->counter.release();
   xb_slu_release(c);
-  DevBuf<double> *db[] = {&c->m_yt, &c->m_t9t, &c->m_rhot, &c->m_ext, &c->m_yet, &c->m_csect, &c->m_qk, &c->m_ydot, &c->m_jac,
+  DevBuf<double> *db[] = {&c->m_yt, &c->m_t9t, &c->m_rhot, &c->m_ext, &c->m_yet, &c->m_csect, &c->m_qk, &c->m_ydot, &c->m_jac, &c->m_dyd,
                           &c->m_rhs, &c->m_diag, &c->m_mult, &c->m_dcsect, &c->m_eos, &c->m_t9dot, &c->m_y, &c->m_t9,
                           &c->m_tdel, &c->z_th, &c->z_t9h, &c->z_rhoh, &c->z_tstart, &c->z_tstop,
                           &c->z_tdelstart, &c->z_t9start, &c->z_rhostart, &c->z_yestart, &c->z_ystart, &c->z_xext, &c->z_aext,
@@ -788,6 +788,26 @@ static int check_slice(xb_ctx *c, int zlo, int zhi) {
 }
 
 }  // extern "C"
+// jacobian_scale (xnet_jacobian_dense.F90:136-255): jac = mult * dydotdy^T + diag on the diagonal, from the stored
+// dydotdy^T of the last build.  One thread per element; strict arithmetic rounds the product and the sum separately
+// as the reference's two statements do, fast arithmetic fuses them (as the fused build does).
+template <bool STRICT>
+__global__ void jac_scale_kernel(const double *__restrict__ dyd, double *__restrict__ jac, const double *__restrict__ diag,
+                                 const double *__restrict__ mult, const int *__restrict__ mask, const int z0, const int N) {
+  const int iz = z0 + blockIdx.y;
+  if (mask && mask[iz] == 0) return;
+  const size_t nn = (size_t)N * N;
+  const double m = mult[iz], d = diag[iz];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < (int)nn; e += gridDim.x * blockDim.x) {
+    const int j = e / N, i = e - j * N;
+    const double v = dyd[(size_t)iz * nn + e];
+    double r;
+    if (STRICT) { r = __dmul_rn(m, v); if (i == j) r = __dadd_rn(r, d); }
+    else r = (i == j) ? fma(m, v, d) : m * v;
+    jac[(size_t)iz * nn + e] = r;
+  }
+}
+
 template <int OP>
 static int launch_module(xb_ctx *c, int zlo, int zhi, const int32_t *mask) {
   const int nz = zhi - zlo + 1;
@@ -850,20 +870,65 @@ int xb_yderiv(xb_ctx *c, int32_t zlo, int32_t zhi, const int32_t *mask, const do
   const int nz = zhi - zlo + 1, ny = c->dn.ny, z0 = zlo - 1;
   if (yt) CUDA_TRY(cudaMemcpy(c->m_yt.p + (size_t)z0 * ny, yt, (size_t)nz * ny * 8, cudaMemcpyHostToDevice));
   rc = launch_module<OP_YDERIV>(c, zlo, zhi, mask); if (rc) return rc;
-  if (ydot) CUDA_TRY(cudaMemcpy(ydot, c->m_ydot.p + (size_t)z0 * ny, (size_t)nz * ny * 8, cudaMemcpyDeviceToHost));
-  else CUDA_TRY(cudaDeviceSynchronize());
+  if (ydot && !mask) CUDA_TRY(cudaMemcpy(ydot, c->m_ydot.p + (size_t)z0 * ny, (size_t)nz * ny * 8, cudaMemcpyDeviceToHost));
+  else if (ydot) {     // masked-out zones keep the caller's ydot (xnet_integrate.F90:409: the loop body runs under mask(izb))
+    for (int i = 0; i < nz; ++i)
+      if (mask[i]) CUDA_TRY(cudaMemcpy(ydot + (size_t)i * ny, c->m_ydot.p + (size_t)(z0 + i) * ny, (size_t)ny * 8, cudaMemcpyDeviceToHost));
+  } else CUDA_TRY(cudaDeviceSynchronize());
   return XB_OK;
 }
 
-int xb_jacobian_build(xb_ctx *c, int32_t zlo, int32_t zhi, const int32_t *mask, const double *diag, const double *mult) {
-  int rc = check_slice(c, zlo, zhi); if (rc) return rc;
-  const int nz = zhi - zlo + 1, z0 = zlo - 1;
+static int jac_scale(xb_ctx *c, int zlo, int zhi, const int32_t *mask, const double *diag, const double *mult) {
+  const int nz = zhi - zlo + 1, z0 = zlo - 1, N = c->dn.msize;
   std::vector<double> one(nz, 1.0), zero(nz, 0.0);
   CUDA_TRY(cudaMemcpy(c->m_diag.p + z0, diag ? diag : zero.data(), nz * 8, cudaMemcpyHostToDevice));  // diag0 = 0
   CUDA_TRY(cudaMemcpy(c->m_mult.p + z0, mult ? mult : one.data(), nz * 8, cudaMemcpyHostToDevice));   // mult1 = 1
-  rc = launch_module<OP_JBUILD>(c, zlo, zhi, mask); if (rc) return rc;
+  const int *dmask = nullptr;
+  if (mask) {
+    CUDA_TRY(cudaMemcpy(c->m_mask.p + z0, mask, nz * sizeof(int), cudaMemcpyHostToDevice));
+    dmask = c->m_mask.p;
+  }
+  const dim3 grid((unsigned)std::min((N * N + 255) / 256, 64), (unsigned)nz);
+  CUDA_TRY(cudaEventRecord(c->ev0));
+  if (c->ctl.arith) jac_scale_kernel<true><<<grid, 256>>>(c->m_dyd.p, c->m_jac.p, c->m_diag.p, c->m_mult.p, dmask, z0, N);
+  else jac_scale_kernel<false><<<grid, 256>>>(c->m_dyd.p, c->m_jac.p, c->m_diag.p, c->m_mult.p, dmask, z0, N);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(c->ev1));
   CUDA_TRY(cudaDeviceSynchronize());
   return XB_OK;
+}
+
+// jacobian_build = dydotdy from the current yt / csect (kept, as the reference keeps its module array), then jacobian_scale
+int xb_jacobian_build(xb_ctx *c, int32_t zlo, int32_t zhi, const int32_t *mask, const double *diag, const double *mult) {
+  int rc = check_slice(c, zlo, zhi); if (rc) return rc;
+  const int nz = zhi - zlo + 1, z0 = zlo - 1, N = c->dn.msize;
+  const size_t nn = (size_t)N * N;
+  if (!c->m_dyd.p) {
+    CUDA_TRY(c->m_dyd.resize((size_t)c->nzevolve * nn));
+    CUDA_TRY(cudaMemset(c->m_dyd.p, 0, (size_t)c->nzevolve * nn * 8));
+  }
+  // the assembly kernel forms mult * sum + diag; with mult = 1, diag = 0 that is dydotdy^T itself (1 * x and x + 0 are exact)
+  std::vector<double> one(nz, 1.0), zero(nz, 0.0);
+  CUDA_TRY(cudaMemcpy(c->m_diag.p + z0, zero.data(), nz * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->m_mult.p + z0, one.data(), nz * 8, cudaMemcpyHostToDevice));
+  rc = launch_module<OP_JBUILD>(c, zlo, zhi, mask); if (rc) return rc;
+  // masked zones only: the others keep their dydotdy
+  if (!mask) {
+    CUDA_TRY(cudaMemcpy(c->m_dyd.p + (size_t)z0 * nn, c->m_jac.p + (size_t)z0 * nn, (size_t)nz * nn * 8, cudaMemcpyDeviceToDevice));
+  } else {
+    for (int i = 0; i < nz; ++i)
+      if (mask[i]) CUDA_TRY(cudaMemcpyAsync(c->m_dyd.p + (size_t)(z0 + i) * nn, c->m_jac.p + (size_t)(z0 + i) * nn, nn * 8, cudaMemcpyDeviceToDevice));
+  }
+  return jac_scale(c, zlo, zhi, mask, diag, mult);
+}
+
+// jacobian_scale alone (xnet_integrate_bdf.F90:925-927: refactor without rebuild): rescales the dydotdy of the last build
+int xb_jacobian_scale(xb_ctx *c, int32_t zlo, int32_t zhi, const int32_t *mask, const double *diag, const double *mult) {
+  int rc = check_slice(c, zlo, zhi); if (rc) return rc;
+  if (!c->m_dyd.p) return fail(XB_ERR_ARG, "xb_jacobian_scale: no Jacobian has been built yet (call xb_jacobian_build first)");
+  CUDA_TRY(cudaSetDevice(c->device));
+  return jac_scale(c, zlo, zhi, mask, diag, mult);
 }
 
 int xb_get_jac(xb_ctx *c, int32_t zlo, int32_t zhi, double *jac) {

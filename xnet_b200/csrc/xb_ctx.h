@@ -71,6 +71,7 @@ struct xb_ctx {
   DevBuf<int> counter;
   // module-level per-zone state (HBM)
   DevBuf<double> m_yt, m_t9t, m_rhot, m_ext, m_yet, m_csect, m_qk, m_ydot, m_jac, m_rhs, m_diag, m_mult;
+  DevBuf<double> m_dyd;                        // dydotdy^T of the last xb_jacobian_build (the reference's module array; allocated on first use)
   DevBuf<double> m_dcsect, m_eos, m_t9dot, m_y, m_t9, m_tdel;
   DevBuf<int> m_indx, m_info, m_mask, m_nh, m_inr, m_kcnt;
   // evolve: zones + outputs
