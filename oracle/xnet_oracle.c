@@ -71,6 +71,11 @@ typedef struct {
   int *n_n[4][4];                   /* expanded reactant indices n_cj [nan_c], 1-based */
   int kmon[5], ktot[5];
   double *rtau;
+  /* BDF integrator (xnet_integrate_bdf.F90): Nordsieck arrays [6][neq] and per-zone scalars */
+  int neq, bq, deltaq, q_age, j_age, p_age, nit_nrslv, nit_nr, nit_ts, nerr_ts, ncf_ts, ierr_nr, ierr_ts, retry_ts;
+  int bdf_started;
+  double *bz, *bz0, *bzt0, *ewt, *acor, *acorp, *acorhat, *dvec, *ydot0, *brtol, *batol;
+  double hvec[6], lvec[6], dt_scale, etaq[3], eta, eta_next, gam, gamhat, gamratio, t9dot0, acnrm, crate, tq[4], tq2save;
 } zone_t;
 
 /* -------------------------------------------------------------------------------------------- */
@@ -315,6 +320,17 @@ static void yderiv(zone_t *z) {
   z->ktot[3] += 1;
 }
 
+static void jacobian_scale(zone_t *z, double diag, double mult) {
+  /* xnet_jacobian_dense.F90:183-200: jac(i0,j1) = mult*dydotdy(j1,i0) (+diag); jac column-major */
+  int m = z->msize, i0, j1; const double *d = z->dydotdy;
+  for (j1 = 0; j1 < m; j1++)
+    for (i0 = 0; i0 < m; i0++) {
+      double v = mult * d[(size_t)i0 * m + j1];
+      if (i0 == j1) v = v + diag;
+      z->jac[(size_t)j1 * m + i0] = v;
+    }
+}
+
 static void jacobian_build(zone_t *z, double diag, double mult) {
   /* xnet_jacobian_dense.F90:303-399 then jacobian_scale :183-200 */
   const ox_net *net = z->net; int ny = z->ny, m = z->msize, i0, j1, c;
@@ -382,13 +398,7 @@ static void jacobian_build(zone_t *z, double diag, double mult) {
     }
   }
   z->ktot[2] += 1;
-  /* jacobian_scale: jac(i0,j1) = mult*dydotdy(j1,i0) (+diag) ; jac col-major */
-  for (j1 = 0; j1 < m; j1++)
-    for (i0 = 0; i0 < m; i0++) {
-      double v = mult * d[(size_t)i0 * m + j1];
-      if (i0 == j1) v = v + diag;
-      z->jac[(size_t)j1 * m + i0] = v;
-    }
+  jacobian_scale(z, diag, mult);
 }
 
 /* ------------------------------- LAPACK 3.8.0 restatement ----------------------------------- */
@@ -668,6 +678,346 @@ static int timestep(zone_t *z, int kstep) {
   return 0;
 }
 
+
+/* ------------------------------- BDF integrator (xnet_integrate_bdf.F90) ----------------------------------------
+ * Per-zone restatement of solve_bdf and its helpers (the zone masks of the reference become plain conditions).
+ * check_stability = .false. in the reference: bdf_stab / bdf_stab_detect are dead code and are not restated.
+ * Real powers go through M_POW (libm, or the portable exp/log pair of the -DOX_PMATH build), integer powers through
+ * the square-and-multiply loop of libgfortran's pow_r8_i4. */
+#define BDF_MAX_ORDER 5
+#define BDF_SKIP (-1)
+#define BDF_SUCCESS 0
+#define BDF_FAIL 1
+static const int bdf_max_it_ts = 20, bdf_max_it_nr = 3, bdf_max_p_age = -1, bdf_max_j_age = -1, bdf_max_nerr_ts = 10,
+                 bdf_max_ncf_ts = 10, bdf_nerr_ts_small = 2, bdf_nerr_ts_qreduce = 3, bdf_nstep_qwait = 10;
+static const double bdf_eta_min = 0.1, bdf_eta_small = 0.2, bdf_eta_reduce = 0.25, bdf_eta_max = 10.0, bdf_eta_thresh = 1.5,
+                    bdf_dgmaxp = 0.3, bdf_dgmaxj = 0.2, bdf_tol_nr = 0.1, bdf_cr_down = 0.3, bdf_cr_diverge = 2.0;
+#define BZ(a, j, i) (a)[(size_t)(j) * z->neq + (i)]
+
+static double bdf_powi(double a, int n) {
+  double pw = 1.0, x = a; unsigned u = (unsigned)(n < 0 ? -n : n);
+  if (n == 0) return 1.0;
+  for (;;) { if (u & 1u) pw = pw * x; u >>= 1; if (u) x = x * x; else break; }
+  return n < 0 ? 1.0 / pw : pw;
+}
+static double bdf_spacing(double x) { /* Fortran SPACING */
+  int e; if (x == 0.0) return DBL_MIN; (void)frexp(fabs(x), &e); return ldexp(1.0, e - 53);
+}
+static int bdf_pascal(int i, int j) { /* binomial(i, j), i >= j (pascal_build :2014-2046) */
+  static const int A[6][6] = {{1,0,0,0,0,0},{1,1,0,0,0,0},{1,2,1,0,0,0},{1,3,3,1,0,0},{1,4,6,4,1,0},{1,5,10,10,5,1}};
+  return A[i][j];
+}
+static void bdf_error_weights(const zone_t *z, const double *y, double *wt) { /* :2048-2085 */
+  const ox_ctl *ctl = z->ctl; int i, n = z->neq;
+  if (ctl->iconvc == 0 || ctl->iconvc == 1) {
+    for (i = 0; i < n; i++) {
+      if (y[i] < ctl->ymin) wt[i] = 0.0;
+      else if (y[i] < z->batol[i]) wt[i] = 1.0 / (z->brtol[i] * z->batol[i]);
+      else wt[i] = 1.0 / (z->brtol[i] * fabs(y[i]));
+    }
+  } else {
+    for (i = 0; i < n; i++) { double a = fabs(y[i]); if (a < ctl->ymin) a = ctl->ymin; wt[i] = 1.0 / (z->brtol[i] * a + z->batol[i]); }
+  }
+}
+static double bdf_normw(const zone_t *z, const double *x, const double *wt) { /* :2087-2140 */
+  int i, n = z->neq, ic = z->ctl->iconvc; double r = 0.0;
+  if (ic == 0) { for (i = 0; i < n; i++) { double v = fabs(x[i] * wt[i]); if (v > r) r = v; } }
+  else if (ic == 1) { for (i = 0; i < n; i++) r = r + fabs(x[i] * wt[i]); }
+  else if (ic == 2) { for (i = 0; i < n; i++) { double v = x[i] * wt[i]; r = r + v * v; } r = sqrt(r); }
+  else if (ic == 3) { for (i = 0; i < n; i++) { double v = x[i] * wt[i]; r = r + v * v; } r = sqrt(r / (double)n); }
+  return r;
+}
+static void bdf_reset(zone_t *z) { /* :490-593 (tolerances: bdf_init :333-340) */
+  const ox_ctl *ctl = z->ctl; int i, j, ny = z->ny, neq = z->neq;
+  for (i = 0; i < ny; i++) { z->brtol[i] = ctl->tolc; z->batol[i] = ctl->yacc; }
+  if (ctl->iheat > 0) { z->brtol[neq - 1] = ctl->tolt9; z->batol[neq - 1] = 1.0e-99; }
+  z->retry_ts = 0; z->nit_nrslv = 0; z->nit_nr = 0; z->nit_ts = 0; z->ierr_nr = 0; z->ierr_ts = 0; z->nerr_ts = 0; z->ncf_ts = 0;
+  z->bq = 1; z->deltaq = 0; z->j_age = bdf_max_j_age + 1; z->p_age = bdf_max_p_age + 1; z->q_age = 0;
+  for (j = 0; j <= BDF_MAX_ORDER; j++) for (i = 0; i < neq; i++) { BZ(z->bz, j, i) = 0.0; BZ(z->bz0, j, i) = 0.0; BZ(z->bzt0, j, i) = 0.0; }
+  for (i = 0; i < ny; i++) { BZ(z->bz, 0, i) = z->yt[i]; BZ(z->bz, 1, i) = z->ydot[i] * z->tdel; }
+  if (ctl->iheat > 0) { BZ(z->bz, 0, neq - 1) = z->t9t; BZ(z->bz, 1, neq - 1) = z->t9dot * z->tdel; }
+  for (i = 0; i <= BDF_MAX_ORDER; i++) { z->hvec[i] = z->tdel; z->lvec[i] = 0.0; }
+  z->dt_scale = z->tdel; z->etaq[0] = z->etaq[1] = z->etaq[2] = 0.0; z->eta = 0.0; z->eta_next = bdf_eta_max;
+  z->gam = z->tdel; z->gamhat = z->tdel; z->gamratio = 1.0;
+  for (i = 0; i < neq; i++) { z->ewt[i] = 0.0; z->acor[i] = 0.0; z->acorp[i] = 0.0; }
+  z->acnrm = 0.0; z->crate = 0.0; z->tq[0] = z->tq[1] = z->tq[2] = z->tq[3] = 0.0; z->tq2save = 0.0;
+  for (i = 0; i < ny; i++) z->ydot0[i] = z->ydot[i];
+  z->t9dot0 = z->t9dot;
+}
+static void bdf_adjust_order(zone_t *z) { /* :1844-1937 */
+  int i, j, neq = z->neq, q = z->bq; double hsum, xi;
+  if (z->deltaq == -1) {
+    for (i = 0; i <= BDF_MAX_ORDER; i++) z->lvec[i] = 0.0;
+    z->lvec[2] = 1.0; hsum = 0.0;
+    for (j = 1; j <= q - 2; j++) {
+      hsum = hsum + z->hvec[j]; xi = hsum / z->tdel;
+      for (i = j + 2; i >= 2; i--) z->lvec[i] = z->lvec[i] * xi + z->lvec[i - 1];
+    }
+    for (j = 2; j <= q - 1; j++) for (i = 0; i < neq; i++) BZ(z->bz, j, i) = BZ(z->bz, j, i) - BZ(z->bz, q, i) * z->lvec[j];
+    for (i = 0; i < neq; i++) BZ(z->bz, q, i) = 0.0;
+    z->bq = q - 1; z->q_age = 0;
+  } else if (z->deltaq == 1) {
+    double alpha0 = -1.0, alpha1 = 1.0, prod = 1.0, xiold = 1.0, a1;
+    for (i = 0; i <= BDF_MAX_ORDER; i++) z->lvec[i] = 0.0;
+    z->lvec[2] = 1.0; hsum = z->tdel;
+    for (j = 1; j <= q - 1; j++) {
+      hsum = hsum + z->hvec[j + 1]; xi = hsum / z->tdel; prod = prod * xi;
+      alpha0 = alpha0 - 1.0 / (double)(j + 1); alpha1 = alpha1 + 1.0 / xi;
+      for (i = j + 2; i >= 2; i--) z->lvec[i] = z->lvec[i] * xiold + z->lvec[i - 1];
+      xiold = xi;
+    }
+    a1 = -(alpha0 + alpha1) / prod;
+    for (j = 2; j <= q; j++) for (i = 0; i < neq; i++) BZ(z->bz, j, i) = BZ(z->bz, j, i) + a1 * z->acor[i] * z->lvec[j];
+    for (i = 0; i < neq; i++) BZ(z->bz, q + 1, i) = a1 * z->acor[i];
+    z->bq = q + 1; z->q_age = 0;
+  }
+  z->deltaq = 0;
+}
+static void bdf_rescale(zone_t *z) { /* :1939-1978 (mask true) */
+  int i, j, neq = z->neq;
+  z->tdel = z->eta * z->dt_scale; z->hvec[0] = z->tdel; z->tt = z->t + z->tdel;
+  for (j = 1; j <= z->bq; j++) { double f = bdf_powi(z->eta, j); for (i = 0; i < neq; i++) BZ(z->bz, j, i) = BZ(z->bz, j, i) * f; }
+  z->dt_scale = z->tdel;
+}
+static void bdf_adjust(zone_t *z) { /* :595-629 */
+  int rescale = 0;
+  if (z->ierr_ts == BDF_SUCCESS) {
+    if (fabs(z->tdel / z->tdel_old - 1.0) > DBL_EPSILON) { z->eta = z->tdel / z->tdel_old; rescale = 1; }
+  }
+  bdf_adjust_order(z);
+  if (rescale) bdf_rescale(z);
+}
+static void bdf_update(zone_t *z, int kstep) { /* :688-831 (zone active) */
+  int i, j, q = z->bq; double hsum, xi_inv = 1.0, xistar_inv = 1.0, alpha0 = -1.0, alpha0_hat = -1.0, a1, a2, a3, a4, a5, a6, c, cinv;
+  double *l = z->lvec;
+  l[0] = 1.0; l[1] = 1.0; for (i = 2; i <= BDF_MAX_ORDER; i++) l[i] = 0.0;
+  hsum = z->tdel;
+  if (q > 1) {
+    for (j = 2; j <= q - 1; j++) {
+      hsum = hsum + z->hvec[j - 1]; xi_inv = z->tdel / hsum; alpha0 = alpha0 - 1.0 / (double)j;
+      for (i = j; i >= 1; i--) l[i] = l[i] + l[i - 1] * xi_inv;
+    }
+    alpha0 = alpha0 - 1.0 / (double)q;
+    xistar_inv = -l[1] - alpha0;
+    hsum = hsum + z->hvec[q - 1]; xi_inv = z->tdel / hsum;
+    alpha0_hat = -l[1] - xi_inv;
+    for (i = q; i >= 1; i--) l[i] = l[i] + l[i - 1] * xistar_inv;
+  }
+  a1 = 1.0 - alpha0_hat + alpha0; a2 = 1.0 + q * a1;
+  z->tq[1] = fabs(a1 / (alpha0 * a2));                          /* tq(0) */
+  z->tq[3] = fabs(a2 * xistar_inv / (l[q] * xi_inv));           /* tq(2) */
+  if (q > 1) {
+    c = xistar_inv / l[q]; a3 = alpha0 + 1.0 / q; a4 = alpha0_hat + xi_inv;
+    z->tq[0] = fabs(c * (1.0 - a4 + a3) / a3);                  /* tq(-1) */
+  } else z->tq[0] = 1.0;
+  hsum = hsum + z->hvec[q]; xi_inv = z->tdel / hsum;
+  a5 = alpha0 - 1.0 / (double)(q + 1); a6 = alpha0_hat - xi_inv;
+  cinv = (1.0 - a6 + a5) / a2;
+  z->tq[2] = fabs(cinv / (xi_inv * (double)(q + 2) * a5));      /* tq(1) */
+  bdf_error_weights(z, &BZ(z->bz, 0, 0), z->ewt);
+  z->gam = z->tdel / l[1];
+  if (kstep > 1) z->gamratio = z->gam / z->gamhat; else { z->gamhat = z->gam; z->gamratio = 1.0; }
+}
+static void bdf_predict(zone_t *z) { /* :631-686 */
+  int i, j, k, neq = z->neq, q = z->bq;
+  for (j = 0; j <= BDF_MAX_ORDER; j++) for (i = 0; i < neq; i++) { BZ(z->bz0, j, i) = BZ(z->bz, j, i); BZ(z->bzt0, j, i) = BZ(z->bz, j, i); }
+  for (i = 0; i <= q; i++) for (j = i + 1; j <= q; j++) for (k = 0; k < neq; k++)
+    BZ(z->bzt0, i, k) = BZ(z->bzt0, i, k) + BZ(z->bz, j, k) * (double)bdf_pascal(j, i);
+}
+static int bdf_step(zone_t *z, int kstep, int active, int max_it_nrslv) { /* :833-1120 */
+  const ox_net *net = z->net; const ox_ctl *ctl = z->ctl;
+  int ny = z->ny, neq = z->neq, iheat = ctl->iheat, k, kit, refactor, rebuild, iterate, converged = 0, rc_;
+  double delp = 0.0, del = 0.0, dcon = 0.0, diag = 1.0, mult, cstar;
+  (void)kstep; (void)converged;
+  if (active) {
+    for (k = 0; k < ny; k++) { z->acor[k] = 0.0; z->yt[k] = BZ(z->bzt0, 0, k); }
+    if (iheat > 0) { z->acor[neq - 1] = 0.0; z->t9t = BZ(z->bzt0, 0, neq - 1); }
+    z->nit_nr = 0; z->nit_nrslv = 0;
+  }
+  refactor = active && (z->retry_ts || z->p_age > bdf_max_p_age || fabs(z->gamratio - 1.0) > bdf_dgmaxp);
+  rebuild = refactor && z->j_age > bdf_max_j_age;
+  iterate = active; z->crate = 1.0; mult = -z->gam;
+  if (iheat == 0 && z->retry_ts) t9rhofind(z, z->tt, &z->ntt, &z->t9t, &z->rhot);
+  for (kit = 1; kit <= max_it_nrslv; kit++) {
+    int eval_rates;
+    if (iterate) { z->nit_nr += 1; z->nit_nrslv += 1; }
+    if (iheat > 0) eval_rates = iterate; else if (kit == 1) eval_rates = iterate && z->nh > 1; else eval_rates = 0;
+    if (eval_rates) { rc_ = cross_sect(z); if (rc_) return rc_; }
+    if (iterate) yderiv(z);
+    if (rebuild) jacobian_build(z, diag, mult);           /* builds dydotdy and scales */
+    else if (refactor) jacobian_scale(z, diag, mult);     /* refactor without rebuild: dydotdy of the last build */
+    if (refactor) ox_dgetrf(z->msize, z->msize, z->jac, z->msize, z->indx, &z->info);
+    if (refactor) { z->gamhat = z->gam; z->gamratio = 1.0; z->crate = 1.0; z->p_age = 0; refactor = 0; }
+    if (rebuild) { z->j_age = 0; rebuild = 0; }
+    if (iterate) {
+      cstar = 2.0 / (1.0 + z->gamratio);
+      for (k = 0; k < ny; k++) z->yrhs[k] = cstar * (z->gam * z->ydot[k] - BZ(z->bzt0, 1, k) / z->lvec[1] - z->acor[k]);
+      if (iheat > 0) z->t9rhs = cstar * (z->gam * z->t9dot - BZ(z->bzt0, 1, neq - 1) / z->lvec[1] - z->acor[neq - 1]);
+      for (k = 0; k < ny; k++) z->rhs[k] = z->yrhs[k];
+      if (iheat > 0) z->rhs[ny] = z->t9rhs;
+      ox_dgetrs(z->msize, 1, z->jac, z->msize, z->indx, z->rhs, z->msize);
+      for (k = 0; k < ny; k++) z->dy[k] = z->rhs[k];
+      if (iheat > 0) z->dt9 = z->rhs[ny];
+      for (k = 0; k < ny; k++) {
+        z->yt[k] = BZ(z->bzt0, 0, k) + z->acor[k] + z->dy[k];
+        if (z->yt[k] < ctl->ymin) { z->yt[k] = 0.0; z->dy[k] = -BZ(z->bzt0, 0, k) - z->acor[k]; }
+        else if (z->yt[k] * net->aa[k] > 1.0) { z->yt[k] = 1.0 / net->aa[k]; z->dy[k] = 1.0 / net->aa[k] - BZ(z->bzt0, 0, k) - z->acor[k]; }
+        z->acor[k] = z->acor[k] + z->dy[k];
+        z->dvec[k] = z->dy[k];
+      }
+      if (iheat > 0) {
+        z->dvec[neq - 1] = z->dt9; z->acor[neq - 1] = z->acor[neq - 1] + z->dt9;
+        z->t9t = BZ(z->bzt0, 0, neq - 1) + z->acor[neq - 1];
+      }
+      del = bdf_normw(z, z->dvec, z->ewt);
+      if (z->nit_nr > 1) { double r = del / delp, c2 = bdf_cr_down * z->crate; z->crate = c2 > r ? c2 : r; }
+      dcon = del * (z->crate < 1.0 ? z->crate : 1.0) * z->tq[1];
+      converged = dcon < bdf_tol_nr;
+      if (converged) {
+        iterate = 0;
+        if (z->nit_nr > 1) z->acnrm = bdf_normw(z, z->acor, z->ewt); else z->acnrm = del;
+      } else if (z->nit_nrslv == max_it_nrslv) { iterate = 0; z->nit_nr = bdf_max_it_nr + 1; }
+      else if (z->nit_nr == bdf_max_it_nr || (z->nit_nr > 1 && del > delp * bdf_cr_diverge)) {
+        if (z->j_age > 0) {
+          for (k = 0; k < ny; k++) { z->yt[k] = BZ(z->bzt0, 0, k); z->acor[k] = 0.0; }
+          if (iheat > 0) { z->t9t = BZ(z->bzt0, 0, neq - 1); z->acor[neq - 1] = 0.0; }
+          refactor = 1; rebuild = fabs(z->gamratio - 1.0) < bdf_dgmaxj; z->nit_nr = 0;
+        } else { iterate = 0; z->nit_nr = bdf_max_it_nr + 1; }
+      }
+      delp = del;
+    }
+    if (!iterate) break;
+  }
+  return 0;
+}
+static void bdf_check(zone_t *z, int active) { /* :1122-1324 */
+  const ox_ctl *ctl = z->ctl; const double biasq = 6.0, addon = 1.0e-6;
+  int k, ny = z->ny, neq = z->neq, restore = 0, rescale = 0; double error;
+  z->retry_ts = 0;
+  if (active) {
+    if (z->nit_nr > bdf_max_it_nr) {
+      z->ncf_ts += 1; z->eta_next = 1.0;
+      if (z->nit_ts >= bdf_max_it_ts) { z->ierr_nr = BDF_SKIP; z->ierr_ts = BDF_FAIL; }
+      else if (z->tdel <= bdf_spacing(z->t)) { z->ierr_nr = BDF_SKIP; z->ierr_ts = BDF_FAIL; }
+      else if (z->ncf_ts == bdf_max_ncf_ts) { z->ierr_nr = BDF_SKIP; z->ierr_ts = BDF_FAIL; }
+      else {
+        double e2 = bdf_spacing(z->t) / z->tdel;
+        z->ierr_nr = BDF_FAIL; z->ierr_ts = BDF_SUCCESS; z->retry_ts = 1; restore = 1;
+        z->eta = bdf_eta_reduce > e2 ? bdf_eta_reduce : e2; rescale = 1;
+        z->kmon[1] = ctl->kitmx + 1;
+      }
+    } else {
+      error = z->tq[1] * z->acnrm;
+      if (error <= 1.0) { z->ierr_nr = BDF_SUCCESS; z->ierr_ts = BDF_SUCCESS; }
+      else {
+        z->nerr_ts += 1; z->eta_next = 1.0;
+        if (z->nerr_ts == bdf_max_nerr_ts) { z->ierr_nr = BDF_SKIP; z->ierr_ts = BDF_FAIL; }
+        else if (z->tdel <= bdf_spacing(z->t)) { z->ierr_nr = BDF_SKIP; z->ierr_ts = BDF_FAIL; }
+        else if (z->nerr_ts > bdf_nerr_ts_qreduce) {
+          double e2 = bdf_spacing(z->t) / z->tdel;
+          z->ierr_nr = BDF_FAIL; z->ierr_ts = BDF_SUCCESS; z->retry_ts = 1;
+          z->eta = bdf_eta_min > e2 ? bdf_eta_min : e2; rescale = 1;
+          if (z->bq == 1) {
+            z->q_age = z->bq - bdf_nstep_qwait;
+            for (k = 0; k < ny; k++) { BZ(z->bz, 0, k) = z->y[k]; BZ(z->bz, 1, k) = z->ydot0[k] * z->tdel; }
+            if (ctl->iheat > 0) { BZ(z->bz, 0, neq - 1) = z->t9; BZ(z->bz, 1, neq - 1) = z->t9dot0 * z->tdel; }
+            restore = 0;
+          } else { restore = 1; z->deltaq = -1; }
+        } else {
+          double e2 = bdf_spacing(z->t) / z->tdel, e;
+          z->ierr_nr = BDF_FAIL; z->ierr_ts = BDF_SUCCESS; z->retry_ts = 1; restore = 1;
+          e = 1.0 / (M_POW(biasq * error, 1.0 / (double)(z->bq + 1)) + addon);
+          if (e2 > e) e = e2;                       /* max( eta_min, spacing/tdel, eta ) */
+          if (bdf_eta_min > e) e = bdf_eta_min;
+          if (e > bdf_eta_max) e = bdf_eta_max;
+          if (z->nerr_ts >= bdf_nerr_ts_small && e > bdf_eta_small) e = bdf_eta_small;
+          z->eta = e; rescale = 1;
+        }
+      }
+    }
+    z->ktot[1] += z->nit_nrslv;
+    z->nit_ts += 1;
+  }
+  if (restore) { int i, j; for (j = 0; j <= BDF_MAX_ORDER; j++) for (i = 0; i < neq; i++) BZ(z->bz, j, i) = BZ(z->bz0, j, i); }
+  bdf_adjust_order(z);
+  if (rescale) bdf_rescale(z);
+}
+static void bdf_correct(zone_t *z) { /* :1326-1395 */
+  int i, j, k, ny = z->ny, neq = z->neq;
+  if (z->ierr_nr != BDF_SUCCESS) return;
+  for (k = 0; k < ny; k++) BZ(z->bz, 0, k) = z->yt[k];
+  if (z->ctl->iheat > 0) BZ(z->bz, 0, neq - 1) = z->t9t;
+  for (j = 1; j <= z->bq; j++) for (i = 0; i < neq; i++) BZ(z->bz, j, i) = BZ(z->bzt0, j, i) + z->acor[i] * z->lvec[j];
+  for (j = BDF_MAX_ORDER; j >= 1; j--) z->hvec[j] = z->hvec[j - 1];
+  z->q_age += 1; z->j_age += 1; z->p_age += 1;
+}
+static void bdf_eta(zone_t *z) { /* :1397-1522 */
+  const double biasqm1 = 6.0, biasq = 6.0, biasqp1 = 10.0, addon = 1.0e-6;
+  int i, neq = z->neq, q = z->bq; double errq, c;
+  if (z->ierr_nr != BDF_SUCCESS) return;
+  if (z->eta_next > 1.0) {
+    z->etaq[0] = z->etaq[1] = z->etaq[2] = 1.0;
+    errq = z->tq[1] * z->acnrm;
+    z->etaq[1] = 1.0 / (M_POW(biasq * errq, 1.0 / (double)(q + 1)) + addon);
+    if (z->q_age > q) {
+      if (q > 1) {
+        errq = z->tq[0] * bdf_normw(z, &BZ(z->bz, q, 0), z->ewt);
+        z->etaq[0] = 1.0 / (M_POW(biasqm1 * errq, 1.0 / (double)q) + addon);
+      }
+      if (q < BDF_MAX_ORDER) {
+        c = (z->tq[3] / z->tq2save) * bdf_powi(z->hvec[1] / z->hvec[2], q + 1);
+        for (i = 0; i < neq; i++) z->acorhat[i] = z->acor[i] - c * z->acorp[i];
+        errq = z->tq[2] * bdf_normw(z, z->acorhat, z->ewt);
+        z->etaq[2] = 1.0 / (M_POW(biasqp1 * errq, 1.0 / (double)(q + 2)) + addon);
+      }
+      z->q_age = q - 1;
+    }
+    z->eta = 1.0;
+    if (z->etaq[1] > z->eta) { z->eta = z->etaq[1]; z->deltaq = 0; }
+    if (z->etaq[0] > z->eta) { z->eta = z->etaq[0]; z->deltaq = -1; }
+    if (z->etaq[2] > z->eta) { z->eta = z->etaq[2]; z->deltaq = 1; }
+    if (z->eta <= bdf_eta_thresh) { z->eta = 1.0; z->deltaq = 0; }
+    if (z->eta > bdf_eta_max) z->eta = bdf_eta_max;
+  } else {
+    if (q - 1 < z->q_age) z->q_age = q - 1;
+  }
+  for (i = 0; i < neq; i++) z->acorp[i] = z->acor[i];
+  z->tq2save = z->tq[3];
+}
+static int solve_bdf(zone_t *z, int kstep, int *its) { /* :155-310 */
+  const ox_ctl *ctl = z->ctl; int ny = z->ny, neq = z->neq, k, kts, rc_;
+  const int max_it_nrslv = ctl->kitmx > bdf_max_it_nr ? ctl->kitmx : bdf_max_it_nr;
+  const int first = !z->bdf_started;       /* kstep == 1 of this zone's run */
+  if (first) { bdf_reset(z); z->bdf_started = 1; }
+  z->ierr_ts = *its;
+  z->ierr_nr = (z->ierr_ts != BDF_SUCCESS) ? BDF_SKIP : BDF_FAIL;
+  for (k = 0; k < ny; k++) z->ydot0[k] = z->ydot[k];
+  if (ctl->iheat > 0) z->t9dot0 = z->t9dot;
+  z->eta_next = bdf_eta_max; z->nit_ts = 0; z->nerr_ts = 0; z->ncf_ts = 0;
+  if (!first) bdf_adjust(z);
+  for (kts = 1; kts <= bdf_max_it_ts; kts++) {
+    const int active = z->ierr_nr == BDF_FAIL;
+    if (active) bdf_update(z, first ? 1 : 2);
+    if (active) bdf_predict(z);
+    rc_ = bdf_step(z, kstep, active, max_it_nrslv); if (rc_) return rc_;
+    bdf_check(z, active);
+    if (z->ierr_nr != BDF_FAIL) break;
+  }
+  bdf_correct(z);
+  bdf_eta(z);
+  z->tdel_next = z->eta * z->tdel;
+  if (z->ierr_nr == BDF_SUCCESS) {
+    z->ierr_ts = BDF_SUCCESS;
+    for (k = 0; k < ny; k++) { z->yt[k] = BZ(z->bz, 0, k); z->yo[k] = z->y[k]; z->y[k] = z->yt[k]; }
+    if (ctl->iheat > 0) z->t9t = BZ(z->bz, 0, neq - 1);
+    z->nto = z->nt; z->nt = z->ntt; z->to = z->t; z->t = z->tt; z->t9o = z->t9; z->t9 = z->t9t;
+    z->rhoo = z->rho; z->rho = z->rhot; z->yeo = z->ye; z->ye = z->yet;
+  } else if (z->ierr_nr == BDF_FAIL || z->ierr_ts == BDF_FAIL) z->ierr_ts = BDF_FAIL;
+  z->kmon[0] = z->nit_ts; z->ktot[0] += z->nit_ts; z->kmon[1] = z->nit_nrslv;
+  *its = z->ierr_ts;
+  return 0;
+}
+
 static void benuc(const zone_t *z, const double *y, double *enb, double *enm) {
   /* xnet_data.F90:157-175 */
   const ox_net *net = z->net; double ztot = 0.0, btot = 0.0; int k;
@@ -708,6 +1058,10 @@ static zone_t *zone_new(const ox_net *net, const ox_ctl *ctl) {
   z->phasei = dalloc(net->nffn); z->dphaseidt9 = dalloc(net->nffn);
   z->dydotdy = dalloc((size_t)z->msize * z->msize); z->jac = dalloc((size_t)z->msize * z->msize);
   z->rhs = dalloc(z->msize); z->indx = (int *)calloc(z->msize, sizeof(int));
+  z->neq = z->msize;
+  z->bz = dalloc((size_t)6 * z->neq); z->bz0 = dalloc((size_t)6 * z->neq); z->bzt0 = dalloc((size_t)6 * z->neq);
+  z->ewt = dalloc(z->neq); z->acor = dalloc(z->neq); z->acorp = dalloc(z->neq); z->acorhat = dalloc(z->neq);
+  z->dvec = dalloc(z->neq); z->ydot0 = dalloc(ny); z->brtol = dalloc(z->neq); z->batol = dalloc(z->neq);
   return z;
 }
 static void zone_free(zone_t *z) {
@@ -718,6 +1072,8 @@ static void zone_free(zone_t *z) {
     for (r = 0; r <= c; r++) free(z->n_n[c][r]);
   }
   free(z->gg); free(z->dlngdt9); free(z->rffn); free(z->dlnrffndt9); free(z->qkffn); free(z->phasei); free(z->dphaseidt9);
+  free(z->bz); free(z->bz0); free(z->bzt0); free(z->ewt); free(z->acor); free(z->acorp); free(z->acorhat); free(z->dvec);
+  free(z->ydot0); free(z->brtol); free(z->batol);
   free(z->dydotdy); free(z->jac); free(z->rhs); free(z->indx); free(z);
 }
 static void zone_reset_scratch(zone_t *z) {
@@ -783,7 +1139,7 @@ static int full_net_zone(zone_t *z, const ox_zones *zn, int iz, ox_out *out) {
   z->rho = z->has_scale ? zn->rhostart[fx] * z->rho_scale : zn->rhostart[fx];
   z->ye = zn->yestart[fx];
   for (k = 0; k < ny; k++) z->y[k] = zn->ystart[(size_t)fx * ny + k];
-  its = 0; lzsolve = 1;
+  its = 0; lzsolve = 1; z->bdf_started = 0;
   for (k = 0; k < 5; k++) { z->kmon[k] = 0; z->ktot[k] = 0; }
   z->ints = 0; z->intso = 0;
   if (out->hist_cap > 0) out->hist_n[iz] = 0;
@@ -814,7 +1170,8 @@ static int full_net_zone(zone_t *z, const ox_zones *zn, int iz, ox_out *out) {
   for (kstep = kstep0 + 1; kstep <= kstep0 + ctl->kstmx; kstep++) {
     int lzoutput;
     if (lzsolve) { rc_ = timestep(z, kstep); if (rc_) break; }
-    rc_ = solve_be(z, kstep, &its); if (rc_) break;
+    if (ctl->isolv == 3) rc_ = solve_bdf(z, kstep, &its); else rc_ = solve_be(z, kstep, &its);
+    if (rc_) break;
     lzoutput = 1;
     if (its == 0) {
       enold = enm;

@@ -44,6 +44,8 @@ PROBLEMS = {
     # 16 zones with their own trajectory / abundance files, self-heating + screening, zone batching
     # (test/test_xnet.sh tests 61/62: test_settings_batch + setup_batch_torch47; BASELINE configs[1] batch variant)
     'torch47_batch': ('test_settings_batch', 'setup_batch_torch47'),
+    # variable-order BDF integrator, self-heating + screening, six C/O-burn trajectories (test/test_xnet.sh test 54)
+    'sn160_bdf': ('test_settings_bdf', 'setup_bdf_sn160'),
 }
 
 

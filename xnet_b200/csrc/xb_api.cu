@@ -86,6 +86,7 @@ static __device__ void zone_prologue(const DevScratch &scr, double *csect, doubl
     s->g_yo = g + scr.off_yo;
     s->g_dcsect = dcsect ? dcsect : g + scr.off_dcsect;
     s->g_dlnrffn = g + scr.off_dlnrffn;
+    s->g_bdf = g + scr.off_bdf;
     reinterpret_cast<double *>(xb_smem + c_net.lay.yt)[c_net.ny] = 1.0;
   }
   __syncthreads();
@@ -666,6 +667,8 @@ static int configure_launch(xb_ctx *c) {
   s.off_yo = o; o += (size_t)c->dn.ny;
   o = (o + 15) / 16 * 16;
   s.off_jac = o; if (!c->jac_in_smem) o += (size_t)(N + 1) * c->ld;   // + the right-hand side as column N
+  o = (o + 15) / 16 * 16;
+  s.off_bdf = o; if (c->ctl.isolv == 3) o += (size_t)kBdfScalDoubles + (size_t)kBdfVectors * N;   // Nordsieck arrays and work vectors of the BDF integrator
   s.stride = (o + 15) / 16 * 16;
   const size_t nblocks = std::max<size_t>(c->grid, c->nzevolve);
   CUDA_TRY(c->scratch.resize(nblocks * s.stride));
@@ -679,7 +682,9 @@ static int configure_launch(xb_ctx *c) {
 
 int xb_ctx_create(const xb_net *net, const xb_ctl *ctl, int32_t nzevolve, int32_t device, xb_ctx **ctx) {
   if (!net || !ctl || !ctx || nzevolve < 1) return fail(XB_ERR_ARG, "xb_ctx_create: bad argument");
-  if (ctl->isolv != 1) return fail(XB_ERR_UNSUPPORTED, "only isolv=1 (backward Euler) is built");
+  if (ctl->isolv != 1 && ctl->isolv != 3)
+    return fail(XB_ERR_UNSUPPORTED, "isolv = 1 (backward Euler) and 3 (BDF) are built; Bader-Deuflhard (2) is dead code in the reference");
+  if (ctl->isolv == 3 && ctl->solver != 0) return fail(XB_ERR_UNSUPPORTED, "the structured solver integrates with backward Euler only");
   int ndev = 0;
   CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(XB_ERR_CUDA, "no such CUDA device");

@@ -115,7 +115,7 @@ struct DevOut {
 struct DevScratch {
   double *base;            // [ncta][stride]
   size_t stride;           // doubles per CTA
-  size_t off_csect, off_rffn, off_qkffn, off_jac, off_prod, off_yo, off_dcsect, off_dlnrffn;  // offsets (doubles)
+  size_t off_csect, off_rffn, off_qkffn, off_jac, off_prod, off_yo, off_dcsect, off_dlnrffn, off_bdf;  // offsets (doubles)
   unsigned long long *phase;  // [PH_COUNT] cycle counters, see enum Phase
 };
 

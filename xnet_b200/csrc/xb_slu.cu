@@ -39,6 +39,7 @@ __device__ void slu_zone_prologue(const DevScratch &scr) {
     s->g_yo = g + scr.off_yo;
     s->g_dcsect = g + scr.off_dcsect;
     s->g_dlnrffn = g + scr.off_dlnrffn;
+    s->g_bdf = nullptr;                  // the structured kernel integrates with backward Euler only
     reinterpret_cast<double *>(xb_smem + c_net.lay.yt)[c_net.ny] = 1.0;
   }
   slu_stage_tables();

@@ -13,6 +13,14 @@
 namespace xb {
 
 // Per-zone scalars (shared memory).  Written by thread 0 between barriers, read by everyone.
+// per-zone scalars of the BDF integrator (xb_bdf.cuh; module variables of xnet_integrate_bdf.F90 :66-127)
+struct BdfScalars {
+  int q, deltaq, q_age, j_age, p_age, nit_nrslv, nit_nr, nit_ts, nerr_ts, ncf_ts, ierr_nr, ierr_ts, retry_ts, started;
+  int refactor, rebuild, iterate, restore, rescale, reload, conv;
+  double hvec[6], lvec[6], dt_scale, etaq[3], eta, eta_next, gam, gamhat, gamratio, t9dot0, acnrm, crate, tq[4], tq2save;
+  double del, delp, a1;
+};
+
 struct ZoneScalars {
   double t, tt, to, tdel, tdel_next, tdel_old, tdelstart, tstart, tstop;
   double t9, t9t, t9o, t9dot, rho, rhot, rhoo, ye, yet, yeo, cv, etae, detaedt9;
@@ -27,6 +35,7 @@ struct ZoneScalars {
   const double *th, *t9h, *rhoh;
   double *g_csect, *g_rffn, *g_qkffn, *g_prod, *g_jac, *g_yo;  // per-CTA global scratch (set in the kernel prologue)
   double *g_dcsect, *g_dlnrffn;   // self-heating: d csect / d T9 [nrtot], d ln rffn / d T9 [nffn]
+  double *g_bdf;                  // BDF (isolv = 3): BdfScalars, then the Nordsieck arrays and work vectors (kBdfVectors x msize doubles)
   int nh, has_scale, nt, ntt, nto, ints, iweak;
   int kmon[5], ktot[5];
   int inr, its, flag, piv, info, tile_ctr;
@@ -1296,6 +1305,12 @@ __device__ inline void hist_put(const DevOut &out, int iz, int ny, int kstep, co
   if (threadIdx.x == 0) out.hist_n[iz] = n + 1;
 }
 
+}  // namespace xb
+#ifndef XB_SLU
+#include "xb_bdf.cuh"
+#endif
+namespace xb {
+
 // --- full_net for one zone (xnet_evolve.F90:19-269; zone load net.F90:246-272) ------------------
 template <bool STRICT>
 __device__ __forceinline__ void full_net_cta(const DevZones &zn, const DevOut &out, int iz) {
@@ -1316,6 +1331,7 @@ __device__ __forceinline__ void full_net_cta(const DevZones &zn, const DevOut &o
     for (int k = 0; k < 5; ++k) { s->kmon[k] = 0; s->ktot[k] = 0; }
     for (int k = 0; k < PH_COUNT; ++k) s->ph[k] = 0;
     s->ints = 0; s->its = 0; s->edot = 0.0; s->sqnu = 0.0;
+    if (ctl.isolv == 3) reinterpret_cast<BdfScalars *>(s->g_bdf)->started = 0;
     if (out.hist_cap > 0) out.hist_n[iz] = 0;
     if (restart) {
       s->t = zn.rs_t[iz]; s->tdel = zn.rs_tdel[iz]; s->tdel_next = A::mul(s->tdel, ctl.tdel_maxmult);
@@ -1364,7 +1380,11 @@ __device__ __forceinline__ void full_net_cta(const DevZones &zn, const DevOut &o
   bool lzsolve = true;
   for (int kstep = kstep0 + 1; kstep <= kstep0 + ctl.kstmx; ++kstep) {
     timestep_cta<STRICT>();
+#ifndef XB_SLU
+    if (ctl.isolv == 3) solve_bdf_cta<STRICT>(); else solve_be_cta<STRICT>();
+#else
     solve_be_cta<STRICT>();
+#endif
     bool lzoutput = true;
     const int its = s->its;
     __syncthreads();
