@@ -184,3 +184,83 @@ def test_structured_lu_restatement(name, oracle_problem, gpu_problem):
         r1 = np.abs(a @ x1 - rhs).max(); r0 = np.abs(a @ x_ref - rhs).max()
         assert r1 <= 50 * r0 + 1e-14 * np.abs(rhs).max()
     assert nfail == 0, 'threshold test (tau = %.2f) failed on %d sampled systems' % (TAU, nfail)
+
+
+def _replay_schedule(slu, net, heat, S0, b, nwl):
+    """numpy replay of slu_factor's pivot loop as the kernel runs it (xb_slu.cuh): round by round, warp by warp, lane by
+    lane from the pivot schedule (structured_lu_schedule, xb_loader.cpp); the right-hand side is the pseudo-column at
+    rhs_off.  Returns the store, the carried right-hand side and the first failing pivot (or None)."""
+    nround, rhs_off = (int(v) for v in net.slu_table('sched_sizes/%d' % nwl, heat))
+    warp = net.slu_table('sched_warp/%d' % nwl, heat).view(np.uint32).reshape(-1, nwl, 2)
+    lane = net.slu_table('sched_lane/%d' % nwl, heat).view(np.uint32).reshape(-1, nwl, 32)
+    assert warp.shape[0] == nround + 2 and lane.shape[0] == nround + 2      # two idle rounds for the prefetch
+    assert (warp[nround:, :, 1] & 0xff == 0).all()
+    n, nh, nb = slu.n, slu.nh, slu.nb
+    S = np.zeros(rhs_off + n + 16)
+    S[:slu.nstore] = S0
+    S[rhs_off:rhs_off + n] = b
+    S[slu.bo + n * slu.bs: slu.bo + n * slu.bs + nb] = b[nh:]        # border entries ride in column n of the border block
+    kfail = None
+    touched = {}
+    for r in range(nround):
+        snap = S.copy()                                # every warp of a round reads the state the barrier left
+        for w in range(nwl):
+            lp, pv = int(warp[r, w, 0] & 0xffff), int(warp[r, w, 0] >> 16)
+            nrow, ntest, k = int(warp[r, w, 1] & 15), int((warp[r, w, 1] >> 4) & 15), int(warp[r, w, 1] >> 8)
+            assert pv == slu.cb[k] + k
+            piv = snap[pv]
+            rk = 1.0 / piv
+            for t in range(ntest):
+                if TAU * abs(snap[lp + t]) > abs(piv):
+                    kfail = k if kfail is None else min(kfail, k)
+            for l in range(32):
+                ap, up = int(lane[r, w, l] & 0xffff), int(lane[r, w, l] >> 16)
+                if ap == lp:
+                    continue
+                un = snap[up] * rk
+                for t in range(nrow):
+                    key = (k, ap + t)
+                    assert key not in touched, 'element updated twice by one pivot'
+                    touched[key] = 1
+                    assert snap[ap + t] == S[ap + t], 'two warps of a round touch the same element'
+                    S[ap + t] = snap[ap + t] - snap[lp + t] * un
+    return S, kfail
+
+
+@pytest.mark.parametrize('name,nwl', [('alpha', 4), ('torch47', 4), ('sn160_scrn', 4), ('sn160_heat', 4), ('sn160_scrn', 2), ('xrb304', 8)])
+def test_pivot_schedule_replay(name, nwl, oracle_problem, gpu_problem):
+    """The pivot schedule does exactly what the index arithmetic of the restatement does: same store and carried
+    right-hand side, bit for bit (every element receives the same single update per pivot), same verdict of the column test."""
+    op = oracle_problem(name)
+    ctl, net, fx = gpu_problem(name)
+    heat = 1 if ctl['iheat'] > 0 else 0
+    slu = Slu(net, heat)
+    nh = slu.nh
+    for a, rhs in _systems(op, name, heat, 2):
+        S0 = slu.scatter(a)
+        Sref = S0.copy()
+        # the restatement's heavy part only: stop before the border block by replaying its loop here
+        b = rhs[slu.perm].copy()
+        bref = b.copy()
+        fail_ref = None
+        ntest = slu.n - heat
+        for k in range(nh):
+            piv = Sref[slu.cb[k] + k]
+            rk = 1.0 / piv
+            rows = slu.rows(k)
+            l = np.array([Sref[slu.addr(i, k)] for i in rows])
+            if any(TAU * abs(v) > abs(piv) for v, i in zip(l, rows) if i < ntest) and fail_ref is None:
+                fail_ref = k
+            for j in slu.cols(k):
+                u = Sref[slu.cb[j] + k] * rk
+                for v, i in zip(l, rows):
+                    Sref[slu.addr(i, j)] -= v * u
+            u = bref[k] * rk
+            for v, i in zip(l, rows):
+                bref[i] -= v * u
+        S, kfail = _replay_schedule(slu, net, heat, S0, b, nwl)
+        rhs_off = int(net.slu_table('sched_sizes/%d' % nwl, heat)[1])
+        assert np.array_equal(S[:slu.bo + slu.n * slu.bs], Sref[:slu.bo + slu.n * slu.bs])
+        assert np.array_equal(S[rhs_off:rhs_off + nh], bref[:nh])
+        assert np.array_equal(S[slu.bo + slu.n * slu.bs: slu.bo + slu.n * slu.bs + slu.nb], bref[nh:])
+        assert kfail == fail_ref

@@ -43,6 +43,9 @@ struct DevSlu {
   int fail_rel;                              // ZoneScalars::slu_fail as a 32-bit word offset from S (negative: the scalars precede the store)
   const uint2 *tab;                          // [n+1] x = cb | cf << 16 (entry n: the right-hand side), y = ncb | nrb << 8
   const int *pos;                            // [n] equation (species, then T9) -> position in the reordered system
+  int nround;                                // rounds of the pivot schedule
+  const uint2 *sch_warp;                     // [nround+2][nwl]     lp | pv << 16,  nrow | ntest << 4 | k << 8   (SluSchedule, xb_host.h)
+  const unsigned *sch_lane;                  // [nround+2][nwl*32]  ap | up << 16
 };
 
 struct DevNet {

@@ -91,6 +91,24 @@ struct SluTables {
   }
 };
 void structured_lu_tables(const Network &net, int heat, SluTables &t);
+// Pivot schedule of the structured LU: everything slu_factor's index arithmetic would derive per pivot, per warp and per
+// lane, laid out as the kernel reads it.  One ROUND = one barrier interval in which each of the nwl factoring warps
+// updates one chunk of up to 8 rows (band rows of the pivot, or the border rows) of up to 32 columns (lane = column:
+// the first 16 band columns, the border columns and the right-hand side, further band columns in extra rounds).  A
+// pivot takes one round unless it has more chunks than warps or more columns than lanes.  All addresses are double
+// indices into the store S (the right-hand side = the pseudo-column at rhs_off).
+//   warp[(r * nwl + w) * 2]     = lp | pv << 16   lp: multipliers of the chunk (column k), pv: the pivot a(k,k)
+//   warp[(r * nwl + w) * 2 + 1] = nrow | ntest << 4 | k << 8   rows of the chunk, how many of them are subject to the
+//                                                  threshold test (0 in the rounds that revisit a chunk), the pivot
+//   lane[(r * nwl + w) * 32 + l] = ap | up << 16  ap: first row of the chunk in this lane's column, up: u(k, column);
+//                                                  ap == lp marks an idle lane (it loads, stores nothing)
+// Two idle rounds are appended (the kernel prefetches two rounds ahead).
+struct SluSchedule {
+  int nround = 0, nwl = 0;
+  std::vector<uint32_t> warp, lane;
+};
+// ntest_rows: equations 0..ntest_rows-1 are tested (all but the T9 row)
+void structured_lu_schedule(const SluTables &t, int nwl, int rhs_off, int ntest_rows, SluSchedule &s);
 int index_from_name(const Network &net, const std::string &name);
 void load_helm_table(const std::string &path, Network &net);
 

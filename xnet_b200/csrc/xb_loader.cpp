@@ -469,6 +469,80 @@ void structured_lu_tables(const Network &net, int heat, SluTables &t) {
   }
 }
 
+void structured_lu_schedule(const SluTables &t, int nwl, int rhs_off, int ntest_rows, SluSchedule &s) {
+  const int n = t.n, nb = t.nbord, nh = n - nb, bo = t.bo, bs = t.bs;
+  s = SluSchedule();
+  s.nwl = nwl;
+  // column j = n is the right-hand side: base rhs_off, stored from row 0, border rows in column n of the border block
+  auto colbase = [&](int j) { return j < n ? t.cb[j] : rhs_off; };
+  auto colfirst = [&](int j) { return j < n ? t.cf[j] : 0; };
+  struct Item { int k, q, c0; bool test; };
+  auto idle_round = [&](int pv, int k) {
+    for (int w = 0; w < nwl; ++w) {
+      s.warp.push_back((uint32_t)pv | ((uint32_t)pv << 16));
+      s.warp.push_back((uint32_t)k << 8);
+      for (int l = 0; l < 32; ++l) s.lane.push_back((uint32_t)pv | ((uint32_t)pv << 16));
+    }
+    ++s.nround;
+  };
+  const int nbt = ntest_rows - nh;                  // tested border rows
+  for (int k = 0; k < nh; ++k) {
+    const int ncb = t.ncb[k], nrb = t.nrb[k], ncx = nb + 1;
+    const int nchunk = (nrb + 7) / 8;               // band chunks; chunk number nchunk = the border rows
+    const int nslot = (ncb <= 16) ? 16 + ncx : ncb + ncx;
+    const int pv = t.cb[k] + k, lband = pv + 1, lbord = bo + k * bs;
+    // lane slots: 0..15 the first 16 band columns (16 distinct bank pairs per row), then the border columns and the
+    // right-hand side, then the band columns past the 16th
+    auto slot_col = [&](int c) {
+      if (c < 16) return c < ncb ? k + 1 + c : -1;
+      const int e = c - 16;
+      if (e < ncx) return nh + e;
+      const int cc = e - ncx + 16;
+      return cc < ncb ? k + 1 + cc : -1;
+    };
+    std::vector<Item> items;
+    for (int c0 = 0; c0 < nslot; c0 += 32)
+      for (int q = 0; q <= nchunk; ++q) {
+        bool any = false;
+        for (int l = 0; l < 32 && !any; ++l) { const int j = slot_col(c0 + l); any = j >= 0 && colfirst(j) <= k; }
+        const bool test = c0 == 0 && (q < nchunk || nbt > 0);
+        if (any || test) items.push_back({k, q, c0, test});
+      }
+    for (size_t i0 = 0; i0 < items.size(); i0 += (size_t)nwl) {
+      for (int w = 0; w < nwl; ++w) {
+        if (i0 + w >= items.size()) {                 // idle warp
+          s.warp.push_back((uint32_t)pv | ((uint32_t)pv << 16));
+          s.warp.push_back((uint32_t)k << 8);
+          for (int l = 0; l < 32; ++l) s.lane.push_back((uint32_t)pv | ((uint32_t)pv << 16));
+          continue;
+        }
+        const Item &it = items[i0 + w];
+        const bool band = it.q < nchunk;
+        const int r0 = it.q * 8;
+        const int lp = band ? lband + r0 : lbord;
+        const int nrow = band ? std::min(8, nrb - r0) : nb;
+        const int ntest = it.test ? (band ? nrow : std::max(0, std::min(nbt, nb))) : 0;
+        s.warp.push_back((uint32_t)lp | ((uint32_t)pv << 16));
+        s.warp.push_back((uint32_t)nrow | ((uint32_t)ntest << 4) | ((uint32_t)k << 8));
+        for (int l = 0; l < 32; ++l) {
+          const int j = slot_col(it.c0 + l);
+          if (j >= 0 && colfirst(j) <= k) {
+            const int ap = band ? colbase(j) + k + 1 + r0 : bo + j * bs;
+            s.lane.push_back((uint32_t)ap | ((uint32_t)(colbase(j) + k) << 16));
+          } else {
+            s.lane.push_back((uint32_t)lp | ((uint32_t)pv << 16));
+          }
+        }
+      }
+      ++s.nround;
+    }
+  }
+  const int pv_last = nh > 0 ? t.cb[nh - 1] + nh - 1 : 0;
+  const int real = s.nround;
+  idle_round(pv_last, std::max(nh - 1, 0)); idle_round(pv_last, std::max(nh - 1, 0));
+  s.nround = real;
+}
+
 namespace {
 void read_ffn(const std::string &dir, int iweak0, Network &net) {
   const int nf = std::max(net.nffn, 1);

@@ -103,11 +103,17 @@ slu_test_kernel(const double *__restrict__ a, const double *__restrict__ b, doub
   int *ipiv = reinterpret_cast<int *>(s->g_jac + (size_t)(n + 1) * n);
   if (mode < 2) {
     if (mode == 0) {
-      slu_factor(S, true);
+      slu_factor(S);
       __syncthreads();
       slu_solve(S, zm.rhs, s->slu_ipb, true);
     } else {
-      slu_factor(S, false);
+      // the factorisation always carries the right-hand side: keep a copy for the separate forward + backward solve
+      double *keep = s->g_jac;
+      for (int k = tid; k < n; k += nt) keep[k] = zm.rhs[k];
+      __syncthreads();
+      slu_factor(S);
+      __syncthreads();
+      for (int k = tid; k < n; k += nt) zm.rhs[k] = keep[k];
       __syncthreads();
       slu_solve(S, zm.rhs, s->slu_ipb, false);
     }
@@ -228,6 +234,15 @@ int xb_slu_configure(xb_ctx *c) {
     CUDA_TRY(c->slu_tabd.put(tab));
     d.slu.tab = c->slu_tabd.p;
   }
+  {
+    // pivot schedule: per round, warp and lane the addresses slu_factor works on (read from L2, two rounds ahead)
+    SluSchedule sc;
+    structured_lu_schedule(T, d.slu.nwl, d.slu.rhs_off, d.slu.ntest, sc);
+    CUDA_TRY(c->slu_schw.put(sc.warp)); CUDA_TRY(c->slu_schl.put(sc.lane));
+    d.slu.nround = sc.nround;
+    d.slu.sch_warp = reinterpret_cast<const uint2 *>(c->slu_schw.p);
+    d.slu.sch_lane = c->slu_schl.p;
+  }
   // zones per SM by shared memory, then whatever is left on the SM caches csect (tail of the reaction list first)
   SmemOff &L = d.lay;
   int per_sm = std::max(1, (int)(sm_smem / ((size_t)L.total + 1024 + 64)));
@@ -270,7 +285,7 @@ int xb_slu_configure(xb_ctx *c) {
 }
 
 void xb_slu_release(xb_ctx *c) {
-  c->slu_tabd.release(); c->slu_pos.release(); c->scratch_slu.release();
+  c->slu_tabd.release(); c->slu_pos.release(); c->slu_schw.release(); c->slu_schl.release(); c->scratch_slu.release();
   xb_ctx::PlanBufs *pb[] = {&c->pby_slu, &c->pbj_slu};
   for (auto *b : pb) {
     b->a.release(); b->nn.release(); b->mc.release(); b->seg_start.release(); b->seg_dest.release();

@@ -73,12 +73,14 @@ __device__ __forceinline__ int slu_addr(const SluIdx &I, const int i, const int 
 // One chunk of a pivot's update, eight rows of this lane's column:  a[t] -= l[t] * u,  stored for t < nleft, as ONE block
 // of PTX in exactly the order the hardware should see: the 16 loads, a warp-level ordering point that keeps ptxas from
 // sinking the loads to their uses (load - multiply-add - store chains, eight exposed latencies), the multiply-adds, the
-// predicated stores.  Every load is unconditional (a conditionally written register would have to be kept alive around
+// predicated stores.  The ordering point is a bar.warp.sync whose member mask is a run-time value (wm = the warp's
+// activemask, read once): with a literal full mask in straight-line code ptxas proves convergence, drops the barrier
+// and interleaves loads and multiply-adds again.  Every load is unconditional (a conditionally written register would have to be kept alive around
 // the pivot loop: ptxas spills it): rows past the span read what follows in the store, idle lanes are handed the
 // multipliers' address (a broadcast the warp performs anyway); nothing of that is stored.
 // lp / ap: shared addresses of the multipliers (the same for every lane) and of the column segment; un = -u.
 // Returns a[0] (the next pivot, for the lane that owns it).
-__device__ __forceinline__ double slu_chunk8(const unsigned lp, const unsigned ap, const int nleft, const double un) {
+__device__ __forceinline__ double slu_chunk8(const unsigned lp, const unsigned ap, const int nleft, const double un, const unsigned wm) {
   double a0;
   asm volatile(
       "{\n\t"
@@ -90,7 +92,7 @@ __device__ __forceinline__ double slu_chunk8(const unsigned lp, const unsigned a
       "ld.shared.f64 a4, [%2+32];\n\tld.shared.f64 a5, [%2+40];\n\tld.shared.f64 a6, [%2+48];\n\tld.shared.f64 a7, [%2+56];\n\t"
       "setp.gt.s32 p0, %3, 0;\n\tsetp.gt.s32 p1, %3, 1;\n\tsetp.gt.s32 p2, %3, 2;\n\tsetp.gt.s32 p3, %3, 3;\n\t"
       "setp.gt.s32 p4, %3, 4;\n\tsetp.gt.s32 p5, %3, 5;\n\tsetp.gt.s32 p6, %3, 6;\n\tsetp.gt.s32 p7, %3, 7;\n\t"
-      "bar.warp.sync 0xffffffff;\n\t"
+      "bar.warp.sync %5;\n\t"
       "fma.rn.f64 a0, l0, %4, a0;\n\tfma.rn.f64 a1, l1, %4, a1;\n\tfma.rn.f64 a2, l2, %4, a2;\n\tfma.rn.f64 a3, l3, %4, a3;\n\t"
       "fma.rn.f64 a4, l4, %4, a4;\n\tfma.rn.f64 a5, l5, %4, a5;\n\tfma.rn.f64 a6, l6, %4, a6;\n\tfma.rn.f64 a7, l7, %4, a7;\n\t"
       "@p0 st.shared.f64 [%2], a0;\n\t@p1 st.shared.f64 [%2+8], a1;\n\t@p2 st.shared.f64 [%2+16], a2;\n\t@p3 st.shared.f64 [%2+24], a3;\n\t"
@@ -98,43 +100,35 @@ __device__ __forceinline__ double slu_chunk8(const unsigned lp, const unsigned a
       "mov.f64 %0, a0;\n\t"
       "}"
       : "=d"(a0)
-      : "r"(lp), "r"(ap), "r"(nleft), "d"(un)
+      : "r"(lp), "r"(ap), "r"(nleft), "d"(un), "r"(wm)
       : "memory");
   return a0;
 }
 
-__device__ __forceinline__ void slu_sync(const int nwl) {
-  if (nwl == 1) __syncwarp(); else bar_named(1, nwl * 32);
-}
-
 // ---- factorisation -----------------------------------------------------------------------------------------------
 // Executed by the first nwl warps of the CTA (the others return at once; the caller's __syncthreads joins them).
-// with_rhs: the right-hand side (S + rhs_off, position order) is carried along as an extra column: it leaves as
-// L^-1 P b.  ZoneScalars::slu_fail is set when a heavy column violates the threshold test or a pivot is zero/NaN,
-// slu_fail_k receives the first such column (caller initialises it to a large value), slu_ipb the interchanges of the
-// border block.  On return the diagonal of U holds the RECIPROCALS of the pivots.
+// The right-hand side (S + rhs_off, position order) is carried along as an extra column: it leaves as L^-1 P b.
+// ZoneScalars::slu_fail is set when a heavy column violates the threshold test or a pivot is zero/NaN, slu_fail_k
+// receives the first such column (caller initialises it to a large value), slu_ipb the interchanges of the border
+// block.  On return the diagonal of U holds the RECIPROCALS of the pivots.
 //
-// The pivot loop is latency bound (a zone has four warps; an SM three or four zones): what counts is the number of
-// instructions and above all of branches on a warp's path through one pivot.  Hence: the lane -> column map is a
-// chain of selects, every warp owns exactly one chunk of rows per pivot (a warp without rows runs the chunk with a zero
-// store count), the rare wide pivots (more chunks than warps, more columns than lanes) take a separate loop.
-__device__ __forceinline__ int slu_slot_col(const int k, const int ncb, const int ncx, const int nh, const int c) {
-  // lane slots of a pivot: 0..15 the first 16 band columns (consecutive columns: 16 distinct banks per row), 16.. the
-  // border columns and the right-hand side, then the band columns past the 16th.  Returns the column (n = rhs) or -1.
-  const int e = c - 16, cc = e - ncx + 16;
-  const int lo = (c < ncb) ? k + 1 + c : -1;
-  const int hi = (e < ncx) ? nh + e : ((cc < ncb) ? k + 1 + cc : -1);
-  return (c < 16) ? lo : hi;
-}
-__device__ __noinline__ void slu_factor(double *__restrict__ S, const bool with_rhs) {
+// The pivot loop is latency bound (a zone has four warps; an SM three zones): what counts is the number of
+// instructions and above all of branches on a warp's path through one pivot.  Nothing about WHERE a pivot works
+// depends on the data, so all of it -- which column a lane owns, whether that column reaches the pivot row, where its
+// segment and its u(k,j) live, how many rows the warp's chunk has and how many of them are tested -- comes from the
+// pivot schedule the host derives once per network (structured_lu_schedule, xb_loader.cpp): 4 bytes per lane and 8 per
+// warp and round, zone-invariant, streamed from L2 two rounds ahead of their use.  A round is then: barrier, pivot,
+// reciprocal, u, one chunk (slu_chunk8), the column test of the chunk's own rows (lanes = rows, folded into every warp:
+// no warp is singled out), flat control flow.  A pivot with more chunks than warps or more columns than lanes takes
+// further rounds; they recompute the reciprocal from the untouched pivot (thread 0 stores a reciprocal over its
+// pivot only once the schedule has moved on).
+__device__ __noinline__ void slu_factor(double *__restrict__ S) {
   XB_ASSUME_SHARED(S);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const DevSlu &D = c_net.slu;
   const int nwl = D.nwl;
   if (w >= nwl) return;
   const int n = D.n, nb = D.nbord, nh = n - nb, bo = D.bo, bs = D.bs;
-  // everything the loop touches is addressed relative to S (one shared-memory base): the index table, the right-hand side
-  const uint2 *__restrict__ tcol = reinterpret_cast<const uint2 *>(S) + D.tab_rel;
   double *rhs = S + D.rhs_off;
   int *fail = reinterpret_cast<int *>(S) + D.fail_rel, *ipb = fail + 2;      // ZoneScalars::slu_fail, slu_fail_k, slu_ipb[8]
   const unsigned sS = (unsigned)__cvta_generic_to_shared(S);
@@ -143,81 +137,64 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S, const bool with_
   // not element growth (elimination without interchanges is invariant under row scaling).
   const double tau = D.tau, itau = D.itau;
   const int nbt = D.ntest - nh;                      // border rows subject to the test
-  const int ncx = nb + (with_rhs ? 1 : 0);           // border columns (+ right-hand side) after the band columns
+  const bool with_rhs = true;
   bool viol = false;
   // the border entries of the right-hand side ride in column n of the border block (same address rule as the matrix columns)
-  if (with_rhs && w == 0 && lane < nb) S[bo + n * bs + lane] = rhs[nh + lane];
-  uint2 tk = tcol[0];
-  double rprev = 0.0; int dprev = -1;                // reciprocal of the previous pivot, stored over it one barrier later
+  if (w == 0 && lane < nb) S[bo + n * bs + lane] = rhs[nh + lane];
+  // loop constants pinned in registers (an opaque move: otherwise they are re-read from the constant bank every round)
+  int nround = D.nround, nfl = nwl * 32, nwr = nwl;
+  asm volatile("mov.b32 %0, %0;\n\tmov.b32 %1, %1;\n\tmov.b32 %2, %2;" : "+r"(nround), "+r"(nfl), "+r"(nwr));
+  unsigned wm;
+  asm volatile("activemask.b32 %0;" : "=r"(wm));
+  const unsigned *__restrict__ lt = D.sch_lane + tid;
+  const uint2 *__restrict__ wt = D.sch_warp + w;
+  unsigned e0 = __ldg(lt), e1 = __ldg(lt + nfl);
+  uint2 g0 = __ldg(wt), g1 = __ldg(wt + nwr);
+  lt += 2 * nfl; wt += 2 * nwr;
+  const int row = lane & 7;
+  double rprev = 0.0; unsigned dprev = 0xffffffffu;   // reciprocal of the previous pivot, stored over it once the schedule has left that pivot
+  int kfail = 0x7fffffff;
 #ifdef XB_SLU_PROF
   long long pt[5] = {0, 0, 0, 0, 0}, pc0 = clock64();
 #define SLU_PT(i) { const long long now_ = clock64(); pt[i] += now_ - pc0; pc0 = now_; }
 #else
 #define SLU_PT(i)
 #endif
-  for (int k = 0; k < nh; ++k) {
+#pragma unroll 1
+  for (int r = 0; r < nround; ++r) {
+    const unsigned e2 = __ldg(lt); const uint2 g2 = __ldg(wt);        // two rounds ahead (the tables end with two idle rounds)
+    lt += nfl; wt += nwr;
     SLU_PT(4)
-    slu_sync(nwl);
+    bar_named(1, nfl);
     SLU_PT(0)
-    const uint2 tk1 = tcol[min(k + 1, nh - 1)];      // next pivot's entry, in flight during this one
-    const int ncb = (int)(tk.y & 0xffu), nrb = (int)((tk.y >> 8) & 0xffu);
-    const int cbk = (int)(tk.x & 0xffffu);
-    const int lband = cbk + k + 1, lbord = bo + k * bs;   // multipliers (unscaled): band rows, border rows
-    const double piv = S[lband - 1];
-    if (tid == 0 && dprev >= 0) S[dprev] = rprev;
-    const int j = slu_slot_col(k, ncb, ncx, nh, lane);
-    const unsigned tj = tcol[max(j, 0)].x;
-    const double rk = pivot_rcp<false>(piv);
-    const bool act = j >= 0 && (int)(tj >> 16) <= k;
-    const int cbj = (int)(tj & 0xffffu);
-    // idle lanes are handed the multipliers' addresses (broadcasts the warp performs anyway) and store nothing
-    const double un = -(S[act ? cbj + k : lband - 1] * rk);
+    const unsigned lp = g0.x & 0xffffu, pv = g0.x >> 16, ap = e0 & 0xffffu, up = e0 >> 16;
+    const double piv = S[pv];
+    const double u = S[up];
+    const double tv = S[lp + row];                      // this lane's row of the chunk for the column test
+    if (tid == 0 && dprev != pv && dprev != 0xffffffffu) S[dprev] = rprev;
+    // reciprocal of the pivot without a range branch: a pivot outside 1e-280..1e280 (or zero, or NaN) fails the
+    // factorisation below, and the dense fallback redoes it with true divisions
+    double rk;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rk) : "d"(piv));
+    {
+      double e = fma(-piv, rk, 1.0);                    // seed good to ~20 bits; r (1 + e + e^2) leaves e^3 < 2^-58
+      e = fma(e, e, e);
+      rk = fma(rk, e, rk);
+    }
+    const double un = -(u * rk);
 #ifdef XB_SLU_PROF
     if (__double2hiint(un) == 0x7ff12345) viol = true;   // consume u: the time stamp below waits for the operand loads
     SLU_PT(1)
 #endif
-    const int nchunk = (nrb + 7) >> 3;               // chunks of band rows; chunk number nchunk = the border rows
-    {
-      const int q = w, r0 = q << 3;
-      const bool band = q < nchunk;
-      const int lpi = band ? lband + r0 : lbord;
-      const int api = act ? (band ? cbj + k + 1 + r0 : bo + j * bs) : lpi;
-      const int nrow = band ? nrb - r0 : ((q == nchunk) ? nb : 0);
-      slu_chunk8(sS + 8u * (unsigned)lpi, sS + 8u * (unsigned)api, act ? nrow : 0, un);
-    }
-    if (nchunk >= nwl || ncb + ncx > 32) {
-      // wide pivot: the chunks beyond one per warp, then the lane slots from 32 on with all their chunks
-      const int nslot = (ncb <= 16) ? 16 + ncx : ncb + ncx;
-#pragma unroll 1
-      for (int c0 = 0; c0 < nslot; c0 += 32) {
-        const int j2 = slu_slot_col(k, ncb, ncx, nh, c0 + lane);
-        const unsigned t2 = tcol[max(j2, 0)].x;
-        const bool act2 = j2 >= 0 && (int)(t2 >> 16) <= k;
-        const int cb2 = (int)(t2 & 0xffffu);
-        const double un2 = -(S[act2 ? cb2 + k : lband - 1] * rk);
-#pragma unroll 1
-        for (int q = (c0 == 0) ? w + nwl : w; q <= nchunk; q += nwl) {
-          const bool band = q < nchunk;
-          const int r0 = q << 3;
-          const int lpi = band ? lband + r0 : lbord;
-          const int api = act2 ? (band ? cb2 + k + 1 + r0 : bo + j2 * bs) : lpi;
-          slu_chunk8(sS + 8u * (unsigned)lpi, sS + 8u * (unsigned)api, act2 ? (band ? nrb - r0 : nb) : 0, un2);
-        }
-      }
-    }
+    const int nrow = (int)(g0.y & 15u), ntest = (int)((g0.y >> 4) & 15u);
+    slu_chunk8(sS + 8u * lp, sS + 8u * ap, (ap != lp) ? nrow : 0, un, wm);
     SLU_PT(2)
-    // column test by the last warp that factors, lanes = rows: |a(i,k)| > thr  <=>  tau |a(i,k)| > |a(k,k)|
-    if (w == nwl - 1) {
-      const double apiv = fabs(piv), thr = apiv * itau;
-      const int nt_ = nrb + nbt;
-      double v = 0.0;
-      if (lane < nt_) v = fabs(S[(lane < nrb) ? lband + lane : lbord + (lane - nrb)]);
-      bool vk = !(apiv > 0.0) || v > thr;            // zero or NaN pivot fails
-#pragma unroll 1
-      for (int r = lane + 32; r < nt_; r += 32) vk |= fabs(S[(r < nrb) ? lband + r : lbord + (r - nrb)]) > thr;
-      if (vk) { viol = true; atomicMin(fail + 1, k); }
-    }
-    rprev = rk; dprev = lband - 1; tk = tk1;
+    // column test, lanes = rows of this warp's chunk: |a(i,k)| > thr  <=>  tau |a(i,k)| > |a(k,k)|
+    const double apiv = fabs(piv), thr = apiv * itau;
+    const bool bad = ((row < ntest) & (fabs(tv) > thr)) | !((apiv > 1e-280) & (apiv < 1e280));
+    kfail = min(kfail, bad ? (int)(g0.y >> 8) : 0x7fffffff);
+    rprev = rk; dprev = pv;
+    e0 = e1; e1 = e2; g0 = g1; g1 = g2;
     SLU_PT(3)
   }
 #ifdef XB_SLU_PROF
@@ -226,8 +203,9 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S, const bool with_
     for (int i = 0; i < 5; ++i) ph[PH_DBG0 + 4 + i] += pt[i];
   }
 #endif
-  slu_sync(nwl);
-  if (tid == 0 && dprev >= 0) S[dprev] = rprev;
+  if (kfail != 0x7fffffff) { viol = true; atomicMin(fail + 1, kfail); }
+  bar_named(1, nfl);
+  if (tid == 0 && dprev != 0xffffffffu) S[dprev] = rprev;
   // ---- border block, one warp, lane c holds column c of the block (lane nb: the right-hand side).  The diagonal is
   // the pivot while it passes the threshold test against the tested rows below it; otherwise the largest entry of the
   // column (any row) is brought up.

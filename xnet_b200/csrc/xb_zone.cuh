@@ -998,7 +998,7 @@ __device__ __noinline__ void step_be_cta() {
     if (tid == 0 && rebuild) { s->slu_fail = 0; s->slu_fail_k = 0x7fffffff; s->nlu_zone += 1; }
     __syncthreads();
     if (rebuild) {
-      slu_factor(zm.jac, true);
+      slu_factor(zm.jac);
       __syncthreads();
       const bool forced = net.slu.force_fb > 0 && (s->nlu_zone % net.slu.force_fb) == 0;
       if (s->slu_fail != 0 || forced) {
