@@ -193,7 +193,7 @@ def _replay_schedule(slu, net, heat, S0, b, nwl):
     nround, rhs_off = (int(v) for v in net.slu_table('sched_sizes/%d' % nwl, heat))
     warp = net.slu_table('sched_warp/%d' % nwl, heat).view(np.uint32).reshape(-1, nwl, 2)
     lane = net.slu_table('sched_lane/%d' % nwl, heat).view(np.uint32).reshape(-1, nwl, 32)
-    assert warp.shape[0] == nround + 2 and lane.shape[0] == nround + 2      # two idle rounds for the prefetch
+    assert nround % 3 == 0 and warp.shape[0] == nround + 3 and lane.shape[0] == nround + 3      # three idle rounds for the prefetch
     assert (warp[nround:, :, 1] & 0xff == 0).all()
     n, nh, nb = slu.n, slu.nh, slu.nb
     S = np.zeros(rhs_off + n + 16)

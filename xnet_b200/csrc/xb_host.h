@@ -102,7 +102,8 @@ void structured_lu_tables(const Network &net, int heat, SluTables &t);
 //                                                  threshold test (0 in the rounds that revisit a chunk), the pivot
 //   lane[(r * nwl + w) * 32 + l] = ap | up << 16  ap: first row of the chunk in this lane's column, up: u(k, column);
 //                                                  ap == lp marks an idle lane (it loads, stores nothing)
-// Two idle rounds are appended (the kernel prefetches two rounds ahead).
+// nround is padded to a multiple of three with idle rounds and three more idle rounds follow (the kernel runs three
+// rounds per loop trip and prefetches three rounds ahead).
 struct SluSchedule {
   int nround = 0, nwl = 0;
   std::vector<uint32_t> warp, lane;

@@ -538,8 +538,10 @@ void structured_lu_schedule(const SluTables &t, int nwl, int rhs_off, int ntest_
     }
   }
   const int pv_last = nh > 0 ? t.cb[nh - 1] + nh - 1 : 0;
+  // the kernel runs three rounds per loop trip and reads three rounds ahead
+  while (s.nround % 3) idle_round(pv_last, std::max(nh - 1, 0));
   const int real = s.nround;
-  idle_round(pv_last, std::max(nh - 1, 0)); idle_round(pv_last, std::max(nh - 1, 0));
+  for (int i = 0; i < 3; ++i) idle_round(pv_last, std::max(nh - 1, 0));
   s.nround = real;
 }
 

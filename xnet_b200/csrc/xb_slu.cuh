@@ -84,7 +84,7 @@ __device__ __forceinline__ double slu_chunk8(const unsigned lp, const unsigned a
   double a0;
   asm volatile(
       "{\n\t"
-      ".reg .pred p0, p1, p2, p3, p4, p5, p6, p7;\n\t"
+      ".reg .pred p0, p1, p2, p3, p4, p5, p6, p7, pz;\n\t"
       ".reg .f64 l0, l1, l2, l3, l4, l5, l6, l7, a0, a1, a2, a3, a4, a5, a6, a7;\n\t"
       "ld.shared.f64 l0, [%1];\n\tld.shared.f64 l1, [%1+8];\n\tld.shared.f64 l2, [%1+16];\n\tld.shared.f64 l3, [%1+24];\n\t"
       "ld.shared.f64 l4, [%1+32];\n\tld.shared.f64 l5, [%1+40];\n\tld.shared.f64 l6, [%1+48];\n\tld.shared.f64 l7, [%1+56];\n\t"
@@ -92,7 +92,7 @@ __device__ __forceinline__ double slu_chunk8(const unsigned lp, const unsigned a
       "ld.shared.f64 a4, [%2+32];\n\tld.shared.f64 a5, [%2+40];\n\tld.shared.f64 a6, [%2+48];\n\tld.shared.f64 a7, [%2+56];\n\t"
       "setp.gt.s32 p0, %3, 0;\n\tsetp.gt.s32 p1, %3, 1;\n\tsetp.gt.s32 p2, %3, 2;\n\tsetp.gt.s32 p3, %3, 3;\n\t"
       "setp.gt.s32 p4, %3, 4;\n\tsetp.gt.s32 p5, %3, 5;\n\tsetp.gt.s32 p6, %3, 6;\n\tsetp.gt.s32 p7, %3, 7;\n\t"
-      "bar.warp.sync %5;\n\t"
+      "bar.warp.sync 0xffffffff;\n\t"
       "fma.rn.f64 a0, l0, %4, a0;\n\tfma.rn.f64 a1, l1, %4, a1;\n\tfma.rn.f64 a2, l2, %4, a2;\n\tfma.rn.f64 a3, l3, %4, a3;\n\t"
       "fma.rn.f64 a4, l4, %4, a4;\n\tfma.rn.f64 a5, l5, %4, a5;\n\tfma.rn.f64 a6, l6, %4, a6;\n\tfma.rn.f64 a7, l7, %4, a7;\n\t"
       "@p0 st.shared.f64 [%2], a0;\n\t@p1 st.shared.f64 [%2+8], a1;\n\t@p2 st.shared.f64 [%2+16], a2;\n\t@p3 st.shared.f64 [%2+24], a3;\n\t"
@@ -146,11 +146,20 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S) {
   asm volatile("mov.b32 %0, %0;\n\tmov.b32 %1, %1;\n\tmov.b32 %2, %2;" : "+r"(nround), "+r"(nfl), "+r"(nwr));
   unsigned wm;
   asm volatile("activemask.b32 %0;" : "=r"(wm));
+  // Schedule entries travel L2 -> registers three rounds ahead of their use.  The loop body is instantiated three times
+  // (round r works from register set r mod 3 and refills it for round r + 3 as soon as it has unpacked it): a rotation
+  // through register moves would have to read a freshly loaded register at the end of the same round.  The host pads
+  // the schedule to a multiple of three rounds plus three idle ones.
   const unsigned *__restrict__ lt = D.sch_lane + tid;
   const uint2 *__restrict__ wt = D.sch_warp + w;
-  unsigned e0 = __ldg(lt), e1 = __ldg(lt + nfl);
-  uint2 g0 = __ldg(wt), g1 = __ldg(wt + nwr);
-  lt += 2 * nfl; wt += 2 * nwr;
+  unsigned eA = __ldg(lt), eB = __ldg(lt + nfl), eC = __ldg(lt + 2 * nfl);
+  uint2 gA = __ldg(wt), gB = __ldg(wt + nwr), gC = __ldg(wt + 2 * nwr);
+  lt += 3 * nfl; wt += 3 * nwr;
+  // Never true (0xffffffff is no schedule entry), but lane dependent as far as ptxas can tell: from here on the warp
+  // counts as possibly diverged, so the bar.warp.sync inside slu_chunk8 stays a real (4-cycle) convergence check that
+  // memory operations are not moved across.  Without it the ordering point is dropped from this branch-free loop and
+  // each multiply-add of a chunk waits for a shared-memory load issued right in front of it (+200 cycles per round).
+  if (eA == 0xffffffffu) return;
   const int row = lane & 7;
   double rprev = 0.0; unsigned dprev = 0xffffffffu;   // reciprocal of the previous pivot, stored over it once the schedule has left that pivot
   int kfail = 0x7fffffff;
@@ -160,14 +169,14 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S) {
 #else
 #define SLU_PT(i)
 #endif
-#pragma unroll 1
-  for (int r = 0; r < nround; ++r) {
-    const unsigned e2 = __ldg(lt); const uint2 g2 = __ldg(wt);        // two rounds ahead (the tables end with two idle rounds)
+  auto round = [&](unsigned &e, uint2 &g) {
+    const unsigned lp = g.x & 0xffffu, pv = g.x >> 16, ap = e & 0xffffu, up = e >> 16;
+    const int nrow = (int)(g.y & 15u), ntest = (int)((g.y >> 4) & 15u), kk = (int)(g.y >> 8);
+    e = __ldg(lt); g = __ldg(wt);                       // three rounds ahead
     lt += nfl; wt += nwr;
     SLU_PT(4)
     bar_named(1, nfl);
     SLU_PT(0)
-    const unsigned lp = g0.x & 0xffffu, pv = g0.x >> 16, ap = e0 & 0xffffu, up = e0 >> 16;
     const double piv = S[pv];
     const double u = S[up];
     const double tv = S[lp + row];                      // this lane's row of the chunk for the column test
@@ -177,26 +186,26 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S) {
     double rk;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rk) : "d"(piv));
     {
-      double e = fma(-piv, rk, 1.0);                    // seed good to ~20 bits; r (1 + e + e^2) leaves e^3 < 2^-58
-      e = fma(e, e, e);
-      rk = fma(rk, e, rk);
+      double er = fma(-piv, rk, 1.0);                   // seed good to ~20 bits; r (1 + e + e^2) leaves e^3 < 2^-58
+      er = fma(er, er, er);
+      rk = fma(rk, er, rk);
     }
     const double un = -(u * rk);
 #ifdef XB_SLU_PROF
     if (__double2hiint(un) == 0x7ff12345) viol = true;   // consume u: the time stamp below waits for the operand loads
     SLU_PT(1)
 #endif
-    const int nrow = (int)(g0.y & 15u), ntest = (int)((g0.y >> 4) & 15u);
     slu_chunk8(sS + 8u * lp, sS + 8u * ap, (ap != lp) ? nrow : 0, un, wm);
     SLU_PT(2)
     // column test, lanes = rows of this warp's chunk: |a(i,k)| > thr  <=>  tau |a(i,k)| > |a(k,k)|
     const double apiv = fabs(piv), thr = apiv * itau;
     const bool bad = ((row < ntest) & (fabs(tv) > thr)) | !((apiv > 1e-280) & (apiv < 1e280));
-    kfail = min(kfail, bad ? (int)(g0.y >> 8) : 0x7fffffff);
+    kfail = min(kfail, bad ? kk : 0x7fffffff);
     rprev = rk; dprev = pv;
-    e0 = e1; e1 = e2; g0 = g1; g1 = g2;
     SLU_PT(3)
-  }
+  };
+#pragma unroll 1
+  for (int r = 0; r < nround; r += 3) { round(eA, gA); round(eB, gB); round(eC, gC); }
 #ifdef XB_SLU_PROF
   if (lane == 0 && w == 0) {
     long long *ph = reinterpret_cast<long long *>(S) + D.ph_rel;
