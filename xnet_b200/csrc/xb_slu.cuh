@@ -71,36 +71,50 @@ __device__ __forceinline__ int slu_addr(const SluIdx &I, const int i, const int 
 }
 
 // One chunk of a pivot's update, eight rows of this lane's column:  a[t] -= l[t] * u,  stored for t < nleft, as ONE block
-// of PTX in exactly the order the hardware should see: the 16 loads, a warp-level ordering point that keeps ptxas from
-// sinking the loads to their uses (load - multiply-add - store chains, eight exposed latencies), the multiply-adds, the
-// predicated stores.  The ordering point is a bar.warp.sync whose member mask is a run-time value (wm = the warp's
-// activemask, read once): with a literal full mask in straight-line code ptxas proves convergence, drops the barrier
-// and interleaves loads and multiply-adds again.  Every load is unconditional (a conditionally written register would have to be kept alive around
-// the pivot loop: ptxas spills it): rows past the span read what follows in the store, idle lanes are handed the
-// multipliers' address (a broadcast the warp performs anyway); nothing of that is stored.
+// of PTX: the 16 loads, the multiply-adds, the predicated stores.  What matters is that all sixteen loads are in flight
+// before the first multiply-add issues (an SM issues in order: a multiply-add placed between the loads waits for its own
+// two operands while the loads behind it are not even issued -- eight exposed shared-memory latencies instead of one).
+// ptxas schedules for its own latency model and interleaves them, ordering points it can prove redundant are dropped,
+// so the order is enforced through a DATA dependency: the multiplier every multiply-add uses is un with (the OR of the
+// low words of all sixteen loaded values) & zero folded into its low word, where zero is a run-time 0 that ptxas cannot
+// see through -- nine LOP3, bit-identical arithmetic.
+// Every load is unconditional (a conditionally written register would have to be kept alive around the pivot loop:
+// ptxas spills it): rows past the span read what follows in the store, idle lanes are handed the multipliers' address
+// (a broadcast the warp performs anyway); nothing of that is stored.
 // lp / ap: shared addresses of the multipliers (the same for every lane) and of the column segment; un = -u.
 // Returns a[0] (the next pivot, for the lane that owns it).
-__device__ __forceinline__ double slu_chunk8(const unsigned lp, const unsigned ap, const int nleft, const double un, const unsigned wm) {
+__device__ __forceinline__ double slu_chunk8(const unsigned lp, const unsigned ap, const int nleft, const double un, const unsigned zero) {
   double a0;
   asm volatile(
       "{\n\t"
-      ".reg .pred p0, p1, p2, p3, p4, p5, p6, p7, pz;\n\t"
-      ".reg .f64 l0, l1, l2, l3, l4, l5, l6, l7, a0, a1, a2, a3, a4, a5, a6, a7;\n\t"
+      ".reg .pred p0, p1, p2, p3, p4, p5, p6, p7;\n\t"
+      ".reg .f64 l0, l1, l2, l3, l4, l5, l6, l7, a0, a1, a2, a3, a4, a5, a6, a7, ug;\n\t"
+      ".reg .b32 x0, x1, x2, x3, x4, x5, x6, x7, y0, y1, y2, y3, y4, y5, y6, y7, hi, acc, ulo, uhi;\n\t"
       "ld.shared.f64 l0, [%1];\n\tld.shared.f64 l1, [%1+8];\n\tld.shared.f64 l2, [%1+16];\n\tld.shared.f64 l3, [%1+24];\n\t"
       "ld.shared.f64 l4, [%1+32];\n\tld.shared.f64 l5, [%1+40];\n\tld.shared.f64 l6, [%1+48];\n\tld.shared.f64 l7, [%1+56];\n\t"
       "ld.shared.f64 a0, [%2];\n\tld.shared.f64 a1, [%2+8];\n\tld.shared.f64 a2, [%2+16];\n\tld.shared.f64 a3, [%2+24];\n\t"
       "ld.shared.f64 a4, [%2+32];\n\tld.shared.f64 a5, [%2+40];\n\tld.shared.f64 a6, [%2+48];\n\tld.shared.f64 a7, [%2+56];\n\t"
       "setp.gt.s32 p0, %3, 0;\n\tsetp.gt.s32 p1, %3, 1;\n\tsetp.gt.s32 p2, %3, 2;\n\tsetp.gt.s32 p3, %3, 3;\n\t"
       "setp.gt.s32 p4, %3, 4;\n\tsetp.gt.s32 p5, %3, 5;\n\tsetp.gt.s32 p6, %3, 6;\n\tsetp.gt.s32 p7, %3, 7;\n\t"
-      "bar.warp.sync 0xffffffff;\n\t"
-      "fma.rn.f64 a0, l0, %4, a0;\n\tfma.rn.f64 a1, l1, %4, a1;\n\tfma.rn.f64 a2, l2, %4, a2;\n\tfma.rn.f64 a3, l3, %4, a3;\n\t"
-      "fma.rn.f64 a4, l4, %4, a4;\n\tfma.rn.f64 a5, l5, %4, a5;\n\tfma.rn.f64 a6, l6, %4, a6;\n\tfma.rn.f64 a7, l7, %4, a7;\n\t"
+      // the gate: ug = un with (OR of the low words of all sixteen loads) & zero folded into its low word
+      "mov.b64 {x0, hi}, l0;\n\tmov.b64 {x1, hi}, l1;\n\tmov.b64 {x2, hi}, l2;\n\tmov.b64 {x3, hi}, l3;\n\t"
+      "mov.b64 {x4, hi}, l4;\n\tmov.b64 {x5, hi}, l5;\n\tmov.b64 {x6, hi}, l6;\n\tmov.b64 {x7, hi}, l7;\n\t"
+      "mov.b64 {y0, hi}, a0;\n\tmov.b64 {y1, hi}, a1;\n\tmov.b64 {y2, hi}, a2;\n\tmov.b64 {y3, hi}, a3;\n\t"
+      "mov.b64 {y4, hi}, a4;\n\tmov.b64 {y5, hi}, a5;\n\tmov.b64 {y6, hi}, a6;\n\tmov.b64 {y7, hi}, a7;\n\t"
+      "lop3.b32 acc, x0, x1, x2, 0xFE;\n\tlop3.b32 acc, acc, x3, x4, 0xFE;\n\tlop3.b32 acc, acc, x5, x6, 0xFE;\n\t"
+      "lop3.b32 acc, acc, x7, y0, 0xFE;\n\tlop3.b32 acc, acc, y1, y2, 0xFE;\n\tlop3.b32 acc, acc, y3, y4, 0xFE;\n\t"
+      "lop3.b32 acc, acc, y5, y6, 0xFE;\n\tor.b32 acc, acc, y7;\n\t"
+      "mov.b64 {ulo, uhi}, %4;\n\t"
+      "lop3.b32 ulo, ulo, acc, %5, 0xF8;\n\t"          // ulo | (acc & zero)
+      "mov.b64 ug, {ulo, uhi};\n\t"
+      "fma.rn.f64 a0, l0, ug, a0;\n\tfma.rn.f64 a1, l1, ug, a1;\n\tfma.rn.f64 a2, l2, ug, a2;\n\tfma.rn.f64 a3, l3, ug, a3;\n\t"
+      "fma.rn.f64 a4, l4, ug, a4;\n\tfma.rn.f64 a5, l5, ug, a5;\n\tfma.rn.f64 a6, l6, ug, a6;\n\tfma.rn.f64 a7, l7, ug, a7;\n\t"
       "@p0 st.shared.f64 [%2], a0;\n\t@p1 st.shared.f64 [%2+8], a1;\n\t@p2 st.shared.f64 [%2+16], a2;\n\t@p3 st.shared.f64 [%2+24], a3;\n\t"
       "@p4 st.shared.f64 [%2+32], a4;\n\t@p5 st.shared.f64 [%2+40], a5;\n\t@p6 st.shared.f64 [%2+48], a6;\n\t@p7 st.shared.f64 [%2+56], a7;\n\t"
       "mov.f64 %0, a0;\n\t"
       "}"
       : "=d"(a0)
-      : "r"(lp), "r"(ap), "r"(nleft), "d"(un), "r"(wm)
+      : "r"(lp), "r"(ap), "r"(nleft), "d"(un), "r"(zero)
       : "memory");
   return a0;
 }
@@ -144,8 +158,7 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S) {
   // loop constants pinned in registers (an opaque move: otherwise they are re-read from the constant bank every round)
   int nround = D.nround, nfl = nwl * 32, nwr = nwl;
   asm volatile("mov.b32 %0, %0;\n\tmov.b32 %1, %1;\n\tmov.b32 %2, %2;" : "+r"(nround), "+r"(nfl), "+r"(nwr));
-  unsigned wm;
-  asm volatile("activemask.b32 %0;" : "=r"(wm));
+  const unsigned zero = (unsigned)nfl >> 20;         // 0, but not to ptxas (nfl is pinned above): the load gate of slu_chunk8
   // Schedule entries travel L2 -> registers three rounds ahead of their use.  The loop body is instantiated three times
   // (round r works from register set r mod 3 and refills it for round r + 3 as soon as it has unpacked it): a rotation
   // through register moves would have to read a freshly loaded register at the end of the same round.  The host pads
@@ -155,11 +168,6 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S) {
   unsigned eA = __ldg(lt), eB = __ldg(lt + nfl), eC = __ldg(lt + 2 * nfl);
   uint2 gA = __ldg(wt), gB = __ldg(wt + nwr), gC = __ldg(wt + 2 * nwr);
   lt += 3 * nfl; wt += 3 * nwr;
-  // Never true (0xffffffff is no schedule entry), but lane dependent as far as ptxas can tell: from here on the warp
-  // counts as possibly diverged, so the bar.warp.sync inside slu_chunk8 stays a real (4-cycle) convergence check that
-  // memory operations are not moved across.  Without it the ordering point is dropped from this branch-free loop and
-  // each multiply-add of a chunk waits for a shared-memory load issued right in front of it (+200 cycles per round).
-  if (eA == 0xffffffffu) return;
   const int row = lane & 7;
   double rprev = 0.0; unsigned dprev = 0xffffffffu;   // reciprocal of the previous pivot, stored over it once the schedule has left that pivot
   int kfail = 0x7fffffff;
@@ -195,7 +203,7 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S) {
     if (__double2hiint(un) == 0x7ff12345) viol = true;   // consume u: the time stamp below waits for the operand loads
     SLU_PT(1)
 #endif
-    slu_chunk8(sS + 8u * lp, sS + 8u * ap, (ap != lp) ? nrow : 0, un, wm);
+    slu_chunk8(sS + 8u * lp, sS + 8u * ap, (ap != lp) ? nrow : 0, un, zero);
     SLU_PT(2)
     // column test, lanes = rows of this warp's chunk: |a(i,k)| > thr  <=>  tau |a(i,k)| > |a(k,k)|
     const double apiv = fabs(piv), thr = apiv * itau;
