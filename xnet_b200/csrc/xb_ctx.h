@@ -97,7 +97,8 @@ struct xb_ctx {
   PlanBufs pby_slu, pbj_slu;
   DevBuf<uint2> slu_tabd;
   DevBuf<int> slu_pos;
-  DevBuf<uint32_t> slu_schw, slu_schl;        // pivot schedule of the structured LU (SluSchedule, xb_host.h)
+  DevBuf<uint32_t> slu_schw, slu_schl, slu_soll;
+  DevBuf<int> slu_solo;        // pivot schedule of the structured LU (SluSchedule, xb_host.h)
   DevScratch scr_slu{};
   DevBuf<double> scratch_slu;
 };

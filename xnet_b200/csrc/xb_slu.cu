@@ -243,6 +243,29 @@ int xb_slu_configure(xb_ctx *c) {
     d.slu.sch_warp = reinterpret_cast<const uint2 *>(c->slu_schw.p);
     d.slu.sch_lane = c->slu_schl.p;
   }
+  {
+    // back-substitution over the band (slu_solve, phase C): per step k = nh-1 .. 0 and lane the address of U(i,k) for the
+    // window row i = k - ((k - lane) & 31), of the pivot's reciprocal for i = k, 0xffff where the column does not reach
+    const int ngroup = ((nh + 3) / 4 + 1) / 2 * 2;
+    std::vector<uint32_t> sl((size_t)(ngroup + 2) * 32 * 2, 0xffffffffu);
+    std::vector<int> so;
+    for (int k = nh - 1; k >= 0; --k) {
+      const int stp = nh - 1 - k, g = stp / 4, sidx = stp % 4;
+      if (T.cf[k] <= k - 32) so.push_back(k);
+      for (int l = 0; l < 32; ++l) {
+        const int i = k - ((k - l) & 31);
+        unsigned ad = 0xffffu;
+        if (i == k || (i >= 0 && i >= T.cf[k])) ad = (unsigned)(T.cb[k] + i);
+        uint32_t &wd = sl[((size_t)g * 32 + l) * 2 + sidx / 2];
+        wd = (sidx % 2) ? ((wd & 0x0000ffffu) | (ad << 16)) : ((wd & 0xffff0000u) | ad);
+      }
+    }
+    so.push_back(-1000000);
+    CUDA_TRY(c->slu_soll.put(sl)); CUDA_TRY(c->slu_solo.put(so));
+    d.slu.sol_ngroup = ngroup;
+    d.slu.sol_lane = reinterpret_cast<const uint2 *>(c->slu_soll.p);
+    d.slu.sol_out = c->slu_solo.p;
+  }
   // zones per SM by shared memory, then whatever is left on the SM caches csect (tail of the reaction list first)
   SmemOff &L = d.lay;
   int per_sm = std::max(1, (int)(sm_smem / ((size_t)L.total + 1024 + 64)));
@@ -285,7 +308,7 @@ int xb_slu_configure(xb_ctx *c) {
 }
 
 void xb_slu_release(xb_ctx *c) {
-  c->slu_tabd.release(); c->slu_pos.release(); c->slu_schw.release(); c->slu_schl.release(); c->scratch_slu.release();
+  c->slu_tabd.release(); c->slu_pos.release(); c->slu_schw.release(); c->slu_schl.release(); c->slu_soll.release(); c->slu_solo.release(); c->scratch_slu.release();
   xb_ctx::PlanBufs *pb[] = {&c->pby_slu, &c->pbj_slu};
   for (auto *b : pb) {
     b->a.release(); b->nn.release(); b->mc.release(); b->seg_start.release(); b->seg_dest.release();

@@ -352,35 +352,57 @@ __device__ __noinline__ void slu_solve(const double *__restrict__ S, double *__r
     b[i] = acc;
   }
   __syncthreads();
-  // C: the band
+  // C: the band, from a per-step, per-lane table (sol_lane: four 16-bit entries per lane and group of four steps, read
+  // from L2 two groups ahead): the address of U(i,k) for the window row i = k - ((k - lane) & 31) this lane holds at
+  // step k, the address of the reciprocal of the pivot for the lane that owns row k, 0xffff = structurally zero.
   if (w0 && nh > 0) {
+    const DevSlu &D = c_net.slu;
+    const uint2 *__restrict__ st = D.sol_lane + lane;
+    const int *__restrict__ outl = D.sol_out;          // steps with rows above the window, descending, then a negative end mark
+    uint2 qA = __ldg(st), qB = __ldg(st + 32);
+    st += 64;
+    int nxt = __ldg(outl), oi = 1;
     int k = nh - 1;
-    const int lk = (k - lane) & 31;                // this lane's window row at step kk is kk - ((kk - lane) & 31): the offset drops by one per step
-    auto load_u = [&](const unsigned t, const int kk, const int off) {      // off = (kk - lane) & 31; row kk - off, off = 0: the unknown itself
-      const int i = kk - off;
-      return (off != 0 && i >= (int)(t >> 16)) ? S[(int)(t & 0xffffu) + i] : 0.0;     // i >= cf >= 0
-    };
     double bv, be = 0.0;
-    { const int i = k - lk; bv = (i >= 0) ? b[i] : 0.0; }
-    unsigned t_cur = I.col[k].x, t_next = (k >= 1) ? I.col[k - 1].x : 0u;
-    double u_cur = load_u(t_cur, k, lk), r_cur = S[(int)(t_cur & 0xffffu) + k];
-    int off = lk;
-    for (; k >= 0; --k) {
-      const int offn = (off - 1) & 31;             // offset at step k-1
-      const unsigned t_n2 = I.col[max(k - 2, 0)].x;
-      const double u_next = load_u(t_next, k - 1, offn);                  // k = 0: t_next = 0 -> row -1 - offn < 0 is never >= cf... guarded below
-      const double r_next = S[(int)(t_next & 0xffffu) + max(k - 1, 0)];
-      const double x = __shfl_sync(kFull, bv, k & 31) * r_cur;
-      if (off == 31 && k + 1 < nh) bv = be;       // row k-31 enters the window (loaded a step ago); off == 31 <=> lane == (k+1) & 31
-      const int cfk = (int)(t_cur >> 16), cbk = (int)(t_cur & 0xffffu);
-      if (cfk <= k - 32) {                                     // outlier column: rows above the window, in shared memory
+    { const int i = k - ((k - lane) & 31); bv = (i >= 0) ? b[i] : 0.0; }
+    bool enter = false;                                // this lane owned the previous step: its next window row (loaded then) enters now
+    const unsigned sB = (unsigned)__cvta_generic_to_shared(b);
+    auto step = [&](const double v) {
+      const bool own = lane == (k & 31);
+      const double x = __shfl_sync(kFull, bv * v, k & 31);      // owner: b(k) times the reciprocal of the pivot
+      if (enter) bv = be;
+      if (k == nxt) {                                  // outlier column: rows above the window, in shared memory
+        const unsigned t = I.col[k].x;
+        const int cfk = (int)(t >> 16), cbk = (int)(t & 0xffffu);
         for (int i = cfk + lane; i <= k - 32; i += 32) b[i] = fma(-S[cbk + i], x, b[i]);
         __syncwarp();
+        nxt = __ldg(outl + oi); ++oi;
       }
-      bv = fma(-u_cur, x, bv);
-      if (off == 0) { b[k] = x; be = (k >= 32) ? b[k - 32] : 0.0; }
-      t_cur = t_next; t_next = t_n2; u_cur = u_next; r_cur = r_next; off = offn;
-    }
+      bv = fma(-v, x, bv);
+      // the owner stores x(k) and fetches the row that takes its place in the window, b(k-32): predicated, no branch
+      // (k < 32: a harmless read of b(0); rows above the first never own a step and meet only zero entries)
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "setp.ne.s32 p, %3, 0;\n\t"
+          "@p st.shared.f64 [%1], %4;\n\t"
+          "@p ld.shared.f64 %0, [%2];\n\t}"
+          : "+d"(be)
+          : "r"(sB + 8u * (unsigned)max(k, 0)), "r"(sB + 8u * (unsigned)max(k - 32, 0)), "r"((int)(own && k >= 0)), "d"(x)
+          : "memory");
+      enter = own;
+      --k;
+    };
+    auto group = [&](uint2 &q) {
+      const unsigned a0 = q.x & 0xffffu, a1 = q.x >> 16, a2 = q.y & 0xffffu, a3 = q.y >> 16;
+      q = __ldg(st); st += 32;                         // two groups ahead (the table ends with two idle groups)
+      // U's entries of the four steps before the first of them runs (S is not written here)
+      const double v0 = (a0 != 0xffffu) ? S[a0] : 0.0, v1 = (a1 != 0xffffu) ? S[a1] : 0.0;
+      const double v2 = (a2 != 0xffffu) ? S[a2] : 0.0, v3 = (a3 != 0xffffu) ? S[a3] : 0.0;
+      step(v0); step(v1); step(v2); step(v3);
+    };
+    const int ngroup = D.sol_ngroup;                   // even
+#pragma unroll 1
+    for (int g = 0; g < ngroup; g += 2) { group(qA); group(qB); }
   }
 }
 
