@@ -493,6 +493,10 @@ __device__ __noinline__ void cross_sect_cta() {
 #pragma unroll
     for (int j = 0; j < 7; ++j) rc[j] = __ldg(rcT + (size_t)j * nrtot + k);
     const int c = (k >= net.roff[3]) ? 3 : (k >= net.roff[2]) ? 2 : (k >= net.roff[1]) ? 1 : 0;
+    // the screening data of the reaction travels with the coefficients (same L2 round trip, not three more behind zw > 0)
+    const bool scr = ctl.iscrn > 0 && c > 0;
+    const double zw = scr ? __ldg(net.sc_zw + k) : 0.0, zi = scr ? __ldg(net.sc_zi + k) : 0.0;
+    const int2 izp = scr ? __ldg(net.sc_iz + k) : make_int2(0, 0);
     double cs, dcs = 0.0;
     if ((iweak < 0 && iwk == 0) || (iweak == 0 && iwk != 0)) {
       cs = 0.0;
@@ -506,11 +510,8 @@ __device__ __noinline__ void cross_sect_cta() {
       }
       // h = ascrn*h + lambda (xnet_integrate.F90:711-762); h = screening factor when iscrn > 0
       double hscr = 0.0;
-      if (ctl.iscrn > 0 && c > 0) {
-        const double zw = __ldg(net.sc_zw + k);
+      if (scr) {
         if (zw > 0.0) {
-          const double zi = __ldg(net.sc_zi + k);
-          const int2 izp = __ldg(net.sc_iz + k);
           const double *fhs = zm.fhs, *dfhs = zm.fhs + net.nzs;
           const int i1 = izp.x & 255, i2 = (izp.x >> 8) & 255, i3 = (izp.x >> 16) & 255, i4 = (izp.x >> 24) & 255, ic = izp.y;
           const double lambda = A::mul(s->hw0, zw);
