@@ -535,8 +535,23 @@ def main():
     except Exception:
         pass
     slu = ctx.solver_info()
+    # roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at this zone count, from
+    # the ncu --set full capture of the same command kept under profiles/ (tools/ncu_summary.py writes the file)
+    traffic, traffic_src = None, 'profiles/r02d_evolve_slu_ncu_%dzones.txt' % nz
+    try:
+        rd = wr = None
+        for ln in open(os.path.join(ROOT, traffic_src)):
+            f = ln.split()
+            if len(f) >= 3 and f[0] == 'dram__bytes_read.sum' and rd is None:
+                rd = float(f[-1]) * {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[f[1]]
+            if len(f) >= 3 and f[0] == 'dram__bytes_write.sum' and wr is None:
+                wr = float(f[-1]) * {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[f[1]]
+        if rd is not None and wr is not None and arith == 0 and args.solver == 'structured' and args.workload == 'sn160_scrn':
+            traffic = rd + wr
+    except Exception:
+        pass
     roof = {'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak / 1e12, 'unit': 'TFLOP/s',
-            'frac': achieved / (fp64_peak / 1e12), 'traffic': None,
+            'frac': achieved / (fp64_peak / 1e12), 'traffic': traffic,
             'kernel': ctx.kernel_name + ' (fused rates+ydot+Jacobian+LU+bksub+Newton/timestep control)',
             'algorithmic': '2/3*N^3 flops x ktot(3) LU factorizations per launch (N=%d, %d factorizations)' % (N, int(nlu)),
             'bound_note': 'FP64 compute (the LU): neither HBM nor the bf16 tensor peak bounds this path; the FP64 tensor '
@@ -544,8 +559,9 @@ def main():
             'peak_source': 'FP64 FMA peak measured live on this GPU (DFMA microbenchmark); MEASURED_PEAKS.json has only bf16/HBM entries',
             'phase_share': {k: round(ph[k] / phase_tot, 4) for k in ('rates', 'yderiv', 'jac', 'lu', 'bksub', 'other', 'lu_panel', 'lu_swap_trsm', 'lu_gemm')},
             'cycles_per_newton_iter': phase_tot / max(newton, 1.0),
-            'traffic_note': 'dram__bytes of one launch from ncu: profiles/r02_evolve_ncu.txt (the Jacobian, csect and the zone state '
-                            'never touch HBM; HBM sees the restart state in, the results out and the cold misses of the tables)',
+            'traffic_note': 'bytes; dram__bytes_read + dram__bytes_write of one launch from the ncu capture ' + traffic_src +
+                            ' (the Jacobian, csect and the zone state never touch HBM; HBM sees the restart state in, the '
+                            'results out, the zone-invariant tables and the pivot schedule on their first touch)',
             'hbm_io_gbs': (h2d + d2h) / (ms_launch * 1e-3) / 1e9, 'hbm_peak_gbs': peaks.get('hbm_gbs', 6650.0)}
     if slu:
         # structured solver: the flops actually executed are a few per cent of the dense count; `achieved` above stays the

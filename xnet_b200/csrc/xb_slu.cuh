@@ -159,9 +159,8 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S) {
   int nround = D.nround, nfl = nwl * 32, nwr = nwl;
   asm volatile("mov.b32 %0, %0;\n\tmov.b32 %1, %1;\n\tmov.b32 %2, %2;" : "+r"(nround), "+r"(nfl), "+r"(nwr));
   const unsigned zero = (unsigned)nfl >> 20;         // 0, but not to ptxas (nfl is pinned above): the load gate of slu_chunk8
-  // Schedule entries travel L2 -> registers three rounds ahead of their use.  The loop body is instantiated three times
-  // (round r works from register set r mod 3 and refills it for round r + 3 as soon as it has unpacked it): a rotation
-  // through register moves would have to read a freshly loaded register at the end of the same round.  The host pads
+  // Schedule entries travel L2 -> registers one loop trip (three rounds) ahead of their use: a rotation through
+  // register moves per round would have to read a freshly loaded register at the end of the same round.  The host pads
   // the schedule to a multiple of three rounds plus three idle ones.
   const unsigned *__restrict__ lt = D.sch_lane + tid;
   const uint2 *__restrict__ wt = D.sch_warp + w;
@@ -177,11 +176,9 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S) {
 #else
 #define SLU_PT(i)
 #endif
-  auto round = [&](unsigned &e, uint2 &g) {
+  auto round = [&](const unsigned e, const uint2 g) {
     const unsigned lp = g.x & 0xffffu, pv = g.x >> 16, ap = e & 0xffffu, up = e >> 16;
     const int nrow = (int)(g.y & 15u), ntest = (int)((g.y >> 4) & 15u), kk = (int)(g.y >> 8);
-    e = __ldg(lt); g = __ldg(wt);                       // three rounds ahead
-    lt += nfl; wt += nwr;
     SLU_PT(4)
     bar_named(1, nfl);
     SLU_PT(0)
@@ -213,7 +210,17 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S) {
     SLU_PT(3)
   };
 #pragma unroll 1
-  for (int r = 0; r < nround; r += 3) { round(eA, gA); round(eB, gB); round(eC, gC); }
+  for (int r = 0; r < nround; r += 3) {
+    // this trip's entries move to their own registers and all three loads for the next trip are issued at once: whatever
+    // register shuffling the compiler does at the loop's back edge then touches values that were requested three
+    // rounds earlier (a load issued in the trip's last round would be waited for at the back edge)
+    const unsigned fA = eA, fB = eB, fC = eC;
+    const uint2 hA = gA, hB = gB, hC = gC;
+    eA = __ldg(lt); eB = __ldg(lt + nfl); eC = __ldg(lt + 2 * nfl);
+    gA = __ldg(wt); gB = __ldg(wt + nwr); gC = __ldg(wt + 2 * nwr);
+    lt += 3 * nfl; wt += 3 * nwr;
+    round(fA, hA); round(fB, hB); round(fC, hC);
+  }
 #ifdef XB_SLU_PROF
   if (lane == 0 && w == 0) {
     long long *ph = reinterpret_cast<long long *>(S) + D.ph_rel;
