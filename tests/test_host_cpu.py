@@ -178,7 +178,7 @@ def test_committed_bench_line_has_the_contract_keys():
               'dtype', 'data', 'config', 'e2e', 'gpu_launches', 'clocks', 'roofline', 'cpu_baseline'):
         assert k in d, k
     assert d['metric'] == 'zone-Newton-iters/sec' and d['dtype'] == 'f64' and d['scaling'] == 'weak' and d['warmup'] >= 3
-    assert 'workload' in d['config'] and d['config']['zones_per_gpu'] == 16384 and d['config']['all_zones_finished']
+    assert 'workload' in d['config'] and d['config']['zones_per_gpu'] == 16384 and d['config'].get('all_zones_ok', d['config'].get('all_zones_finished'))
     assert set(('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step')) <= set(d['e2e']) and d['e2e']['h2d_bytes_per_step'] > 0
     assert d['gpu_launches'] > 0 and not d['clocks']['reasons']
     r = d['roofline']
