@@ -279,6 +279,11 @@ int xb_slu_configure(xb_ctx *c) {
     L.total = (int)(((size_t)L.total + (size_t)ncache * 8 + 15) / 16 * 16);
   }
   c->slu_smem = (size_t)L.total;
+  if (env_int("XB_SLU_VERBOSE", 0))
+    std::fprintf(stderr, "structured LU: n %d, store %d doubles, zone without rate cache %zu B (scalars %zu, part %d), rates cached %d of %d, "
+                         "%d zones per SM by shared memory, %d threads, schedule %d rounds\n",
+                 n, T.nstore, (size_t)L.total - (size_t)(d.nrtot - d.cs_lo) * 8, sizeof(ZoneScalars), c->slu_npart, d.nrtot - d.cs_lo, d.nrtot,
+                 per_sm, threads, d.slu.nround);
   CUDA_TRY(cudaFuncSetAttribute(evolve_slu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slu_smem));
   int occ = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evolve_slu_kernel, threads, c->slu_smem));
