@@ -66,7 +66,7 @@ void structured_lu_plan(Network &net);
 // pattern, then the border (light particles, T9).  Storage, S[nstore] doubles:
 //   rows i < nh  : COLUMN-major, column j holds rows ct[j] = cf[j] .. cbot[j] contiguously, element (i,j) at cb[j] + i.
 //                  Heavy columns: cbot[j] = last heavy row whose stored part reaches column j (>= j); border columns: all
-//                  heavy rows.  Column starts are padded so that the bases cb[j] of any 16 consecutive columns differ mod 16:
+//                  heavy rows.  Column starts are padded so that the bases cb[j] of any 8 (XB_SLU_PADW) consecutive columns differ mod 16:
 //                  lanes working on consecutive columns at one row hit distinct shared-memory banks.
 //   rows i >= nh : also by column, element (i,j) at bo + j * bs + (i - nh) with an odd stride bs >= nbord; n + 1 columns, the
 //                  last one carries the border rows' right-hand side entries through the factorisation.

@@ -18,7 +18,8 @@
 // by the warp, and the column bases are padded (cb[j] mod 16 distinct over 8 neighbours; odd stride in the border) so
 // that one row of consecutive columns is nearly bank-conflict free.  Rows are split in chunks of 8 over the nwl warps
 // that factor.  With three zones of four warps on an SM every instruction of a pivot's dependent chain costs its full
-// latency, so the pivot loop is written for instruction count: ~70 per warp and pivot.
+// latency, so the pivot loop is written for instruction count: all index arithmetic is done once per network on the
+// host (the pivot schedule, structured_lu_schedule in xb_loader.cpp), 93 instructions per warp and round remain.
 //
 // Numerical safety: every heavy column is verified, tau*|a(i,k)| <= |a(k,k)| for all rows below (the test the dense
 // fast path applies to its predicted pivot; tau = 1e-3, see kSluTauDefault below).  The border block at the end keeps
