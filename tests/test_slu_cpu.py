@@ -264,3 +264,73 @@ def test_pivot_schedule_replay(name, nwl, oracle_problem, gpu_problem):
         assert np.array_equal(S[rhs_off:rhs_off + nh], bref[:nh])
         assert np.array_equal(S[slu.bo + slu.n * slu.bs: slu.bo + slu.n * slu.bs + slu.nb], bref[nh:])
         assert kfail == fail_ref
+
+
+def _replay_solve_table(slu, net, heat, S, b):
+    """numpy replay of slu_solve's phase C (xb_slu.cuh) as the warp runs it: 32 window rows in 'registers' (lane = row mod
+    32), one table entry per lane and step, the owner's product broadcast, the row leaving the window stored and the row
+    entering it fetched; rows above the window updated in memory at the listed steps.  b: right-hand side after phases A
+    and B (border unknowns solved, their columns subtracted from the heavy rows); returns b with the heavy unknowns."""
+    words = net.slu_table('sol_lane', heat).view(np.uint32).reshape(-1, 32, 2)
+    outl = net.slu_table('sol_out', heat).tolist()
+    ent = np.empty((words.shape[0], 32, 4), np.int64)
+    ent[:, :, 0] = words[:, :, 0] & 0xffff; ent[:, :, 1] = words[:, :, 0] >> 16
+    ent[:, :, 2] = words[:, :, 1] & 0xffff; ent[:, :, 3] = words[:, :, 1] >> 16
+    nh = slu.nh
+    ngroup = words.shape[0] - 2
+    assert ngroup % 2 == 0 and 4 * ngroup >= nh and (ent[ngroup:] == 0xffff).all() and outl[-1] < -nh
+    b = b.copy()
+    k = nh - 1
+    bv = np.array([b[k - ((k - l) & 31)] if k - ((k - l) & 31) >= 0 else 0.0 for l in range(32)])
+    be = np.zeros(32)
+    enter = np.zeros(32, bool)
+    oi = 0
+    for g in range(ngroup):
+        for s4 in range(4):
+            v = np.array([S[a] if a != 0xffff else 0.0 for a in ent[g, :, s4]])
+            own = np.arange(32) == (k & 31)
+            x = (bv * v)[k & 31]
+            bv = np.where(enter, be, bv)
+            if k == outl[oi]:
+                for i in range(slu.cf[k], k - 31):
+                    b[i] -= S[slu.cb[k] + i] * x
+                oi += 1
+            bv = bv - v * x
+            if k >= 0:
+                b[k] = x
+                be[k & 31] = b[k - 32] if k >= 32 else b[0]
+            enter = own
+            k -= 1
+    assert outl[oi] < 0
+    return b
+
+
+@pytest.mark.parametrize('name', ['alpha', 'torch47', 'sn160_scrn', 'sn160_heat', 'xrb304'])
+def test_solve_table_replay(name, oracle_problem, gpu_problem):
+    """The table-driven band back-substitution equals the restatement's column sweep (same products, same order per row:
+    bit for bit), including the columns that reach above the 32-row window."""
+    op = oracle_problem(name)
+    ctl, net, fx = gpu_problem(name)
+    heat = 1 if ctl['iheat'] > 0 else 0
+    slu = Slu(net, heat)
+    n, nh = slu.n, slu.nh
+    nout = 0
+    for a, rhs in _systems(op, name, heat, 2):
+        S = slu.scatter(a)
+        rinv, ipb, fail, bf = slu.factor(S, rhs[slu.perm])
+        x_ref = slu.solve(S, rinv, ipb, bf, True)
+        # phases A and B in the restatement's arithmetic: border unknowns, then their columns off the heavy rows
+        b = bf.copy()
+        for k in range(n - 1, nh - 1, -1):
+            x = b[k] * rinv[k]
+            b[k] = x
+            for i in range(slu.cf[k], k):
+                b[i] -= S[slu.addr(i, k)] * x
+        Sr = S.copy()
+        for k in range(nh):
+            Sr[slu.cb[k] + k] = rinv[k]              # the kernel keeps the reciprocals over the pivots
+        got = _replay_solve_table(slu, net, heat, Sr, b)
+        assert np.array_equal(got[:nh], x_ref[:nh])
+        nout += sum(1 for k in range(nh) if slu.cf[k] <= k - 32)
+    if name in ('sn160_scrn', 'xrb304'):
+        assert nout > 0                             # the out-of-window path is exercised

@@ -1282,6 +1282,16 @@ int xb_slu_table(const xb_net *net, int32_t heat, const char *what, int32_t *out
     for (size_t i = 0; i < src.size(); ++i) v[i] = (int32_t)src[i];
     return copy_out(v, out, cap, n);
   }
+  // band back-substitution table of slu_solve (phase C): "sol_lane" = [groups + 2][32][2] 32-bit words holding four 16-bit
+  // entries (steps k0, k0-1, k0-2, k0-3 of the group, k0 = nh-1-4g), "sol_out" = steps with rows above the 32-row window
+  if (w == "sol_lane" || w == "sol_out") {
+    std::vector<uint32_t> sl; std::vector<int32_t> so; int ngroup = 0;
+    structured_lu_solve_table(t, sl, so, &ngroup);
+    if (w == "sol_out") return copy_out(so, out, cap, n);
+    std::vector<int32_t> v(sl.size());
+    for (size_t i = 0; i < sl.size(); ++i) v[i] = (int32_t)sl[i];
+    return copy_out(v, out, cap, n);
+  }
   return fail(XB_ERR_ARG, "xb_slu_table: unknown key " + w);
 }
 

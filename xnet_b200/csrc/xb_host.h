@@ -110,6 +110,11 @@ struct SluSchedule {
 };
 // ntest_rows: equations 0..ntest_rows-1 are tested (all but the T9 row)
 void structured_lu_schedule(const SluTables &t, int nwl, int rhs_off, int ntest_rows, SluSchedule &s);
+// Band back-substitution table (slu_solve, phase C): per step k = nh-1 .. 0 and lane the address of U(i,k) for the window row
+// i = k - ((k - lane) & 31), of the pivot's reciprocal for i = k, 0xffff where the column does not reach; four 16-bit entries
+// per lane and group of four steps: lane_words[(g * 32 + lane) * 2 + s / 2], low half first; ngroup is even and two idle
+// groups follow.  out_steps: the steps whose column reaches above the window (cf[k] <= k - 32), descending, then -1000000.
+void structured_lu_solve_table(const SluTables &t, std::vector<uint32_t> &lane_words, std::vector<int32_t> &out_steps, int *ngroup);
 int index_from_name(const Network &net, const std::string &name);
 void load_helm_table(const std::string &path, Network &net);
 

@@ -547,6 +547,26 @@ void structured_lu_schedule(const SluTables &t, int nwl, int rhs_off, int ntest_
   s.nround = real;
 }
 
+void structured_lu_solve_table(const SluTables &T, std::vector<uint32_t> &sl, std::vector<int32_t> &so, int *ngroup_out) {
+  const int nh = T.n - T.nbord;
+  const int ngroup = ((nh + 3) / 4 + 1) / 2 * 2;
+  sl.assign((size_t)(ngroup + 2) * 32 * 2, 0xffffffffu);
+  so.clear();
+  for (int k = nh - 1; k >= 0; --k) {
+    const int stp = nh - 1 - k, g = stp / 4, sidx = stp % 4;
+    if (T.cf[k] <= k - 32) so.push_back(k);
+    for (int l = 0; l < 32; ++l) {
+      const int i = k - ((k - l) & 31);
+      unsigned ad = 0xffffu;
+      if (i == k || (i >= 0 && i >= T.cf[k])) ad = (unsigned)(T.cb[k] + i);
+      uint32_t &wd = sl[((size_t)g * 32 + l) * 2 + sidx / 2];
+      wd = (sidx % 2) ? ((wd & 0x0000ffffu) | (ad << 16)) : ((wd & 0xffff0000u) | ad);
+    }
+  }
+  so.push_back(-1000000);
+  *ngroup_out = ngroup;
+}
+
 namespace {
 void read_ffn(const std::string &dir, int iweak0, Network &net) {
   const int nf = std::max(net.nffn, 1);

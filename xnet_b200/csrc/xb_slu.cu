@@ -246,21 +246,8 @@ int xb_slu_configure(xb_ctx *c) {
   {
     // back-substitution over the band (slu_solve, phase C): per step k = nh-1 .. 0 and lane the address of U(i,k) for the
     // window row i = k - ((k - lane) & 31), of the pivot's reciprocal for i = k, 0xffff where the column does not reach
-    const int ngroup = ((nh + 3) / 4 + 1) / 2 * 2;
-    std::vector<uint32_t> sl((size_t)(ngroup + 2) * 32 * 2, 0xffffffffu);
-    std::vector<int> so;
-    for (int k = nh - 1; k >= 0; --k) {
-      const int stp = nh - 1 - k, g = stp / 4, sidx = stp % 4;
-      if (T.cf[k] <= k - 32) so.push_back(k);
-      for (int l = 0; l < 32; ++l) {
-        const int i = k - ((k - l) & 31);
-        unsigned ad = 0xffffu;
-        if (i == k || (i >= 0 && i >= T.cf[k])) ad = (unsigned)(T.cb[k] + i);
-        uint32_t &wd = sl[((size_t)g * 32 + l) * 2 + sidx / 2];
-        wd = (sidx % 2) ? ((wd & 0x0000ffffu) | (ad << 16)) : ((wd & 0xffff0000u) | ad);
-      }
-    }
-    so.push_back(-1000000);
+    std::vector<uint32_t> sl; std::vector<int> so; int ngroup = 0;
+    structured_lu_solve_table(T, sl, so, &ngroup);
     CUDA_TRY(c->slu_soll.put(sl)); CUDA_TRY(c->slu_solo.put(so));
     d.slu.sol_ngroup = ngroup;
     d.slu.sol_lane = reinterpret_cast<const uint2 *>(c->slu_soll.p);

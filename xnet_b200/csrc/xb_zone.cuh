@@ -353,7 +353,15 @@ __device__ __noinline__ void cross_sect_cta() {
   const int iweak = s->iweak;
   const bool worker = !split || tid < nt - 32;       // threads that run the FFN block and the first rate pass
   const int wnt = split ? nt - 32 : nt;
-  if (split && tid == nt - 32) eos_chain();
+  if (split && tid == nt - 32) {
+#ifdef XB_EOS_TIMER
+    const long long t0_ = clock64();
+    eos_chain();
+    s->ph[PH_DBG0 + 8] += clock64() - t0_;
+#else
+    eos_chain();
+#endif
+  }
   auto fhs_table = [&]() {
     // strong-screening energy per charge, DeWitt & Slattery (2003) fit (xnet_screening.F90:225-235)
     using R = Num<STRICT>;
@@ -480,8 +488,18 @@ __device__ __noinline__ void cross_sect_cta() {
     if (pass == 0) { kend = net.roff[1]; kstride = nt - 32; if (!worker) kbeg = kend; }
     else {
       kbeg = net.roff[1];
+#ifdef XB_EOS_TIMER
+      long long t1_ = 0;
+      if (tid == 0) t1_ = clock64();
+#endif
       __syncthreads();                                 // EOS chain and pass 0 done
+#ifdef XB_EOS_TIMER
+      if (tid == 0) { const long long n_ = clock64(); s->ph[PH_DBG0 + 9] += n_ - t1_; t1_ = n_; }
+#endif
       if (ctl.iscrn > 0) { fhs_table(); __syncthreads(); }
+#ifdef XB_EOS_TIMER
+      if (tid == 0) s->ph[PH_DBG0 + 10] += clock64() - t1_;
+#endif
     }
   }
 #pragma unroll kRateUnroll
