@@ -334,3 +334,123 @@ def test_solve_table_replay(name, oracle_problem, gpu_problem):
         nout += sum(1 for k in range(nh) if slu.cf[k] <= k - 32)
     if name in ('sn160_scrn', 'xrb304'):
         assert nout > 0                             # the out-of-window path is exercised
+
+
+def _replay_schedule2(slu, net, heat, S0, b, nwl):
+    """numpy replay of the rank-2 pivot loop (slu_factor with the pair schedule, xb_slu.cuh): one round eliminates the
+    pivots (k, k+1); every lane forms U(k+1, j) for its own column, the flagged item stores it one barrier later."""
+    nround, rhs_off, pair = (int(v) for v in net.slu_table('sched2_sizes/%d' % nwl, heat))
+    assert pair == 1
+    warp = net.slu_table('sched2_warp/%d' % nwl, heat).view(np.uint32).reshape(-1, nwl, 4)
+    lane = net.slu_table('sched2_lane/%d' % nwl, heat).view(np.uint32).reshape(-1, nwl, 32, 2)
+    assert nround % 3 == 0 and warp.shape[0] == nround + 3 and lane.shape[0] == nround + 3
+    n, nh, nb = slu.n, slu.nh, slu.nb
+    S = np.zeros(rhs_off + n + 16)
+    S[:slu.nstore] = S0
+    S[rhs_off:rhs_off + n] = b
+    S[slu.bo + n * slu.bs: slu.bo + n * slu.bs + nb] = b[nh:]
+    kfail = None
+    pend = []                                         # deferred stores of U(k+1, .): after the next barrier
+    recip = None                                      # (pv1, r1, pv2 or None, r2): stored once the schedule has left the pair
+    for r in range(nround):
+        for ad, v in pend:
+            S[ad] = v
+        pend = []
+        pv1_r = int(warp[r, 0, 2] & 0xffff)
+        if recip is not None and recip[0] != pv1_r:
+            S[recip[0]] = recip[1]
+            if recip[2] is not None:
+                S[recip[2]] = recip[3]
+            recip = None
+        snap = S.copy()
+        for w in range(nwl):
+            lp1, lp2 = int(warp[r, w, 0] & 0xffff), int(warp[r, w, 0] >> 16)
+            f = int(warp[r, w, 1])
+            nrow, nt1, nt2, commit, single = f & 15, (f >> 4) & 15, (f >> 8) & 15, (f >> 12) & 1, (f >> 13) & 1
+            pv1, u12 = int(warp[r, w, 2] & 0xffff), int(warp[r, w, 2] >> 16)
+            k = int(warp[r, w, 3])
+            assert pv1 == slu.cb[k] + k and pv1 == pv1_r
+            piv1, l21, u12v, piv2 = snap[pv1], snap[pv1 + 1], snap[u12], snap[u12 + 1]
+            rk1 = 1.0 / piv1
+            un1k1 = -(u12v * rk1)
+            p2 = piv2 + l21 * un1k1
+            rk2 = 0.0 if single else 1.0 / p2
+            if not single:
+                assert u12 == slu.cb[k + 1] + k
+                if TAU * abs(l21) > abs(piv1):
+                    kfail = k if kfail is None else min(kfail, k)
+            for t in range(nt1):
+                if TAU * abs(snap[lp1 + t]) > abs(piv1):
+                    kfail = k if kfail is None else min(kfail, k)
+            for t in range(nt2):
+                l2t = snap[lp2 + t] + snap[lp1 + t] * un1k1
+                if TAU * abs(l2t) > abs(p2):
+                    kfail = k + 1 if kfail is None else min(kfail, k + 1)
+            recip = (pv1, rk1, None if single else u12 + 1, rk2)
+            for l in range(32):
+                ap, up1 = int(lane[r, w, l, 0] & 0xffff), int(lane[r, w, l, 0] >> 16)
+                up2, col2 = int(lane[r, w, l, 1] & 0xffff), int(lane[r, w, l, 1] >> 16) & 1
+                if ap == lp1:
+                    continue
+                un1 = -(snap[up1] * rk1)
+                upr = snap[up2] + l21 * un1
+                un2 = 0.0 if (col2 or single) else -(upr * rk2)
+                for t in range(nrow):
+                    l1 = snap[lp1 + t]
+                    l2 = snap[lp2 + t] + l1 * un1k1
+                    assert snap[ap + t] == S[ap + t], 'two warps of a round touch the same element'
+                    S[ap + t] = (snap[ap + t] + l1 * un1) + l2 * un2
+                if commit and not col2:
+                    pend.append((up2, upr))
+    for ad, v in pend:
+        S[ad] = v
+    return S, kfail, recip
+
+
+@pytest.mark.parametrize('name,nwl', [('alpha', 4), ('torch47', 4), ('sn160_scrn', 4), ('sn160_heat', 4), ('sn160_scrn', 2), ('xrb304', 8)])
+def test_pair_schedule_replay(name, nwl, oracle_problem, gpu_problem, monkeypatch):
+    """The rank-2 schedule (two pivots per round; XB_SLU_PAIR=1, parked: measured slower on B200) leaves the same store,
+    carried right-hand side and column-test verdict as the pivot-by-pivot elimination: each element receives the same
+    two updates in the same order, so the match is exact."""
+    monkeypatch.setenv('XB_SLU_PAIR', '1')
+    op = oracle_problem(name)
+    ctl, net, fx = gpu_problem(name)
+    heat = 1 if ctl['iheat'] > 0 else 0
+    slu = Slu(net, heat)
+    nh = slu.nh
+    for a, rhs in _systems(op, name, heat, 2):
+        S0 = slu.scatter(a)
+        Sref = S0.copy()
+        b = rhs[slu.perm].copy()
+        bref = b.copy()
+        fail_ref = None
+        ntest = slu.n - heat
+        for k in range(nh):
+            piv = Sref[slu.cb[k] + k]
+            rk = 1.0 / piv
+            rows = slu.rows(k)
+            l = np.array([Sref[slu.addr(i, k)] for i in rows])
+            if any(TAU * abs(v) > abs(piv) for v, i in zip(l, rows) if i < ntest) and fail_ref is None:
+                fail_ref = k
+            for j in slu.cols(k):
+                u = -(Sref[slu.cb[j] + k] * rk)
+                for v, i in zip(l, rows):
+                    Sref[slu.addr(i, j)] += v * u
+            u = -(bref[k] * rk)
+            for v, i in zip(l, rows):
+                bref[i] += v * u
+        S, kfail, recip = _replay_schedule2(slu, net, heat, S0, b, nwl)
+        rhs_off = int(net.slu_table('sched2_sizes/%d' % nwl, heat)[1])
+        end = slu.bo + slu.n * slu.bs
+        # pivots: the replay has stored the reciprocals of all pairs but the last
+        for k in range(nh):
+            ad = slu.cb[k] + k
+            if recip is not None and ad in (recip[0], recip[2]):
+                assert S[ad] == Sref[ad]
+            else:
+                assert S[ad] == 1.0 / Sref[ad]
+                S[ad] = Sref[ad]
+        assert np.array_equal(S[:end], Sref[:end])
+        assert np.array_equal(S[rhs_off:rhs_off + nh], bref[:nh])
+        assert np.array_equal(S[end:end + slu.nb], bref[nh:])
+        assert kfail == fail_ref

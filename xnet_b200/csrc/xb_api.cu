@@ -1269,12 +1269,21 @@ int xb_slu_table(const xb_net *net, int32_t heat, const char *what, int32_t *out
   if (w == "sizes") { std::vector<int32_t> v{t.n, t.nstore, t.nbord, (int32_t)t.flops, t.bo, t.bs, (int32_t)t.flops_envelope}; return copy_out(v, out, cap, n); }
   // pivot schedule (SluSchedule, xb_host.h) for NWL factoring warps: "sched_warp/NWL", "sched_lane/NWL" (the 32-bit words),
   // "sched_sizes/NWL" (rounds, rhs_off); the right-hand side sits at rhs_off = nstore + 16 in this export
-  if (w.rfind("sched_", 0) == 0 && w.find('/') != std::string::npos) {
+  if (w.rfind("sched", 0) == 0 && w.find('/') != std::string::npos) {
     const int nwl = std::atoi(w.c_str() + w.find('/') + 1);
     if (nwl < 1 || nwl > 8) return fail(XB_ERR_ARG, "xb_slu_table: warps outside 1..8");
     const std::string key = w.substr(0, w.find('/'));
     SluSchedule sc;
     structured_lu_schedule(t, nwl, t.nstore + 16, t.n - (heat ? 1 : 0), sc);
+    if (key == "sched2_sizes" || key == "sched2_warp" || key == "sched2_lane") {
+      SluSchedule2 s2;
+      structured_lu_schedule2(t, nwl, t.nstore + 16, t.n - (heat ? 1 : 0), s2);
+      if (key == "sched2_sizes") { std::vector<int32_t> v{s2.nround, t.nstore + 16, t.pair}; return copy_out(v, out, cap, n); }
+      const std::vector<uint32_t> &src2 = key == "sched2_warp" ? s2.warp : s2.lane;
+      std::vector<int32_t> v(src2.size());
+      for (size_t i = 0; i < src2.size(); ++i) v[i] = (int32_t)src2[i];
+      return copy_out(v, out, cap, n);
+    }
     if (key == "sched_sizes") { std::vector<int32_t> v{sc.nround, t.nstore + 16}; return copy_out(v, out, cap, n); }
     const std::vector<uint32_t> &src = key == "sched_warp" ? sc.warp : sc.lane;
     if (key != "sched_warp" && key != "sched_lane") return fail(XB_ERR_ARG, "xb_slu_table: unknown key " + w);

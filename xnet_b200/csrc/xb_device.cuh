@@ -46,6 +46,9 @@ struct DevSlu {
   int nround;                                // rounds of the pivot schedule
   const uint2 *sch_warp;                     // [nround+2][nwl]     lp | pv << 16,  nrow | ntest << 4 | k << 8   (SluSchedule, xb_host.h)
   const unsigned *sch_lane;                  // [nround+2][nwl*32]  ap | up << 16
+  int pair;                                  // 1: pair-aligned tables, two pivots per round (sch2_*); 0: one pivot per round (sch_*)
+  const uint4 *sch2_warp;                    // [nround+3][nwl]     SluSchedule2 (xb_host.h)
+  const uint2 *sch2_lane;                    // [nround+3][nwl*32]
   int sol_ngroup;                            // groups of four back-substitution steps (even)
   const uint2 *sol_lane;                     // [sol_ngroup+2][32] four 16-bit entries: address of U(i,k) / of the pivot's reciprocal / 0xffff (slu_solve, phase C)
   const int *sol_out;                        // steps whose column reaches above the 32-row window, descending, then -1000000

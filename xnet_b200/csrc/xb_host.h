@@ -79,6 +79,7 @@ struct SluTables {
   std::vector<int32_t> rf, cf;                // [n] first structural column of row i / first structural row of column j
   std::vector<int32_t> cb, cbot;              // [n] column base (address of a virtual row 0), last stored heavy row
   std::vector<int32_t> nrb, ncb;              // [nh] per pivot k: rows k+1..k+nrb and columns k+1..k+ncb of the heavy part take part
+  int pair = 0;                               // XB_SLU_PAIR=1: profiles rounded down to even, pivots (k, k+1), k even, share rows and columns (rank-2 rounds; measured slower, off)
   double flops = 0;                           // of one factorisation over the structural pattern (2 per multiply-add, 1 per multiplier)
   double flops_envelope = 0;                  // what the kernel executes (spans instead of patterns)
   bool inside(int i, int j) const {
@@ -110,6 +111,21 @@ struct SluSchedule {
 };
 // ntest_rows: equations 0..ntest_rows-1 are tested (all but the T9 row)
 void structured_lu_schedule(const SluTables &t, int nwl, int rhs_off, int ntest_rows, SluSchedule &s);
+// Rank-2 schedule (pair-aligned tables): one round eliminates the pivots (k, k+1), k even (a last odd pivot runs as a
+// "single": its second pivot is switched off).  Chunks cover the rows k+2.. (single: k+1..) and the border rows; row k+1,
+// i.e. U(k+1, .), is formed by every lane for its own column and stored, one barrier later, by the lanes of the item
+// flagged `commit`.  Per warp and round four words:
+//   [0] lp1 | lp2 << 16         the chunk's rows in column k and in column k+1
+//   [1] nrow | ntest1 << 4 | ntest2 << 8 | commit << 12 | single << 13
+//   [2] pv1 | u12 << 16         a(k,k) and a(k,k+1); a(k+1,k) = pv1 + 1, a(k+1,k+1) = u12 + 1
+//   [3] k
+// per lane and round two words:  [0] ap | up1 << 16  (column segment, a(k,j));  [1] up2 | col2 << 16  (a(k+1,j); col2: j = k+1,
+// the lane that leaves the updated multipliers of pivot k+1 behind);  ap == lp1 marks an idle lane.  Padding as above.
+struct SluSchedule2 {
+  int nround = 0, nwl = 0;
+  std::vector<uint32_t> warp, lane;
+};
+void structured_lu_schedule2(const SluTables &t, int nwl, int rhs_off, int ntest_rows, SluSchedule2 &s);
 // Band back-substitution table (slu_solve, phase C): per step k = nh-1 .. 0 and lane the address of U(i,k) for the window row
 // i = k - ((k - lane) & 31), of the pivot's reciprocal for i = k, 0xffff where the column does not reach; four 16-bit entries
 // per lane and group of four steps: lane_words[(g * 32 + lane) * 2 + s / 2], low half first; ngroup is even and two idle

@@ -431,6 +431,14 @@ void structured_lu_tables(const Network &net, int heat, SluTables &t) {
   // the border rows and columns are stored in full: the pivoting inside the border exchanges whole rows
   for (int p = n - t.nbord; p < n; ++p) { t.rf[p] = 0; t.cf[p] = 0; }
   const int nh = n - t.nbord;
+  // Pair alignment (XB_SLU_PAIR=1, off by default): slu_factor then eliminates the pivots (k, k+1), k even, in ONE round (a
+  // rank-2 update).  For that the two pivots must work on the same rows and columns: row and column profiles are rounded
+  // down to even, i.e. a stored zero at (i, k) for every row whose pattern starts in column k+1 and at (k, j) likewise
+  // (SN160: +2 % storage).  Bit-identical to the pivot-by-pivot elimination and parity-green, but measured SLOWER on B200
+  // (SN160 + screening 2.44e6 against 2.63e6 zone-it/s): every lane re-forms the multipliers of the second pivot for its
+  // rows (+50 % shared-memory loads and FP64 work) and the two reciprocals are a serial chain; see DESIGN 4c.
+  if (const char *v = std::getenv("XB_SLU_PAIR")) t.pair = (*v && std::atoi(v) != 0) ? 1 : 0;
+  if (t.pair) for (int p = 0; p < nh; ++p) { t.rf[p] &= ~1; t.cf[p] &= ~1; }
   // spans of the heavy part per pivot, last stored heavy row per column
   t.nrb.assign(nh, 0); t.ncb.assign(nh, 0); t.cbot.assign(n, nh - 1);
   for (int k = 0; k < nh; ++k) {
@@ -544,6 +552,86 @@ void structured_lu_schedule(const SluTables &t, int nwl, int rhs_off, int ntest_
   while (s.nround % 3) idle_round(pv_last, std::max(nh - 1, 0));
   const int real = s.nround;
   for (int i = 0; i < 3; ++i) idle_round(pv_last, std::max(nh - 1, 0));
+  s.nround = real;
+}
+
+void structured_lu_schedule2(const SluTables &t, int nwl, int rhs_off, int ntest_rows, SluSchedule2 &s) {
+  const int n = t.n, nb = t.nbord, nh = n - nb, bo = t.bo, bs = t.bs;
+  s = SluSchedule2();
+  s.nwl = nwl;
+  auto colbase = [&](int j) { return j < n ? t.cb[j] : rhs_off; };
+  auto colfirst = [&](int j) { return j < n ? t.cf[j] : 0; };
+  const int nbt = std::max(0, std::min(ntest_rows - nh, nb));          // tested border rows
+  int last_pv1 = 0, last_k = 0;
+  auto push_idle_warp = [&](int pv1, int u12, int k, bool single) {
+    s.warp.push_back((uint32_t)pv1 | ((uint32_t)pv1 << 16));
+    s.warp.push_back(single ? (1u << 13) : 0u);
+    s.warp.push_back((uint32_t)pv1 | ((uint32_t)u12 << 16));
+    s.warp.push_back((uint32_t)k);
+    for (int l = 0; l < 32; ++l) { s.lane.push_back((uint32_t)pv1 | ((uint32_t)pv1 << 16)); s.lane.push_back((uint32_t)pv1); }
+  };
+  for (int k = 0; k < nh; k += 2) {
+    const bool single = k + 1 >= nh;
+    const int ncb = t.ncb[k], nrb = t.nrb[k], ncx = nb + 1;
+    const int row0 = single ? k + 1 : k + 2, nband = std::max(0, single ? nrb : nrb - 1);
+    const int nchunk = (nband + 7) / 8;
+    const int nslot = (ncb <= 16) ? 16 + ncx : ncb + ncx;
+    const int pv1 = t.cb[k] + k, u12 = single ? pv1 : t.cb[k + 1] + k;
+    last_pv1 = pv1; last_k = k;
+    auto slot_col = [&](int c) {
+      if (c < 16) return c < ncb ? k + 1 + c : -1;
+      const int e = c - 16;
+      if (e < ncx) return nh + e;
+      const int cc = e - ncx + 16;
+      return cc < ncb ? k + 1 + cc : -1;
+    };
+    // slot groups last to first, the rows of a group last chunk (the border) to first: the lane of column k+1 (slot 0 of
+    // group 0) overwrites the multipliers of pivot k+1 that every other item of the same rows reads, and the item of the
+    // first rows hands row k+1 of U over for the deferred store -- both have to come last.  A group starts a new round.
+    const int ngrp = (nslot + 31) / 32;
+    for (int gi = ngrp - 1; gi >= 0; --gi) {
+      const int c0 = gi * 32;
+      struct Item { int q; };
+      std::vector<Item> items;
+      for (int q = nchunk; q >= 0; --q) items.push_back({q});
+      for (size_t i0 = 0; i0 < items.size(); i0 += (size_t)nwl) {
+        for (int w = 0; w < nwl; ++w) {
+          if (i0 + w >= items.size()) { push_idle_warp(pv1, u12, k, single); continue; }
+          const int q = items[i0 + w].q;
+          const bool band = q < nchunk, lastitem = (i0 + w + 1 == items.size());
+          const int r0 = row0 + q * 8;
+          const int lp1 = band ? t.cb[k] + r0 : bo + k * bs;
+          const int lp2 = single ? lp1 : (band ? t.cb[k + 1] + r0 : bo + (k + 1) * bs);
+          const int nrow = band ? std::min(8, nband - q * 8) : nb;
+          const int nt = (gi == 0) ? (band ? nrow : nbt) : 0;
+          const int commit = (!single && lastitem) ? 1 : 0;
+          s.warp.push_back((uint32_t)lp1 | ((uint32_t)lp2 << 16));
+          s.warp.push_back((uint32_t)nrow | ((uint32_t)nt << 4) | ((uint32_t)(single ? 0 : nt) << 8) | ((uint32_t)commit << 12) |
+                           ((uint32_t)(single ? 1 : 0) << 13));
+          s.warp.push_back((uint32_t)pv1 | ((uint32_t)u12 << 16));
+          s.warp.push_back((uint32_t)k);
+          for (int l = 0; l < 32; ++l) {
+            const int j = slot_col(c0 + l);
+            if (j >= 0 && colfirst(j) <= k) {
+              const int ap = band ? colbase(j) + r0 : bo + j * bs;
+              const int up1 = colbase(j) + k, up2 = single ? up1 : up1 + 1;
+              const int col2 = (!single && j == k + 1) ? 1 : 0;
+              s.lane.push_back((uint32_t)ap | ((uint32_t)up1 << 16));
+              s.lane.push_back((uint32_t)up2 | ((uint32_t)col2 << 16));
+            } else {
+              s.lane.push_back((uint32_t)lp1 | ((uint32_t)pv1 << 16));
+              s.lane.push_back((uint32_t)pv1);
+            }
+          }
+        }
+        ++s.nround;
+      }
+    }
+  }
+  auto idle_round = [&]() { for (int w = 0; w < nwl; ++w) push_idle_warp(last_pv1, last_pv1, last_k, true); ++s.nround; };
+  while (s.nround % 3) idle_round();
+  const int real = s.nround;
+  for (int i = 0; i < 3; ++i) idle_round();
   s.nround = real;
 }
 

@@ -235,13 +235,26 @@ int xb_slu_configure(xb_ctx *c) {
     d.slu.tab = c->slu_tabd.p;
   }
   {
-    // pivot schedule: per round, warp and lane the addresses slu_factor works on (read from L2, two rounds ahead)
-    SluSchedule sc;
-    structured_lu_schedule(T, d.slu.nwl, d.slu.rhs_off, d.slu.ntest, sc);
-    CUDA_TRY(c->slu_schw.put(sc.warp)); CUDA_TRY(c->slu_schl.put(sc.lane));
-    d.slu.nround = sc.nround;
-    d.slu.sch_warp = reinterpret_cast<const uint2 *>(c->slu_schw.p);
-    d.slu.sch_lane = c->slu_schl.p;
+    // pivot schedule: per round, warp and lane the addresses slu_factor works on (read from L2, three rounds ahead);
+    // pair-aligned tables: two pivots per round
+    d.slu.pair = T.pair;
+    if (T.pair) {
+      SluSchedule2 sc;
+      structured_lu_schedule2(T, d.slu.nwl, d.slu.rhs_off, d.slu.ntest, sc);
+      CUDA_TRY(c->slu_schw.put(sc.warp)); CUDA_TRY(c->slu_schl.put(sc.lane));
+      d.slu.nround = sc.nround;
+      d.slu.sch2_warp = reinterpret_cast<const uint4 *>(c->slu_schw.p);
+      d.slu.sch2_lane = reinterpret_cast<const uint2 *>(c->slu_schl.p);
+      d.slu.sch_warp = nullptr; d.slu.sch_lane = nullptr;
+    } else {
+      SluSchedule sc;
+      structured_lu_schedule(T, d.slu.nwl, d.slu.rhs_off, d.slu.ntest, sc);
+      CUDA_TRY(c->slu_schw.put(sc.warp)); CUDA_TRY(c->slu_schl.put(sc.lane));
+      d.slu.nround = sc.nround;
+      d.slu.sch_warp = reinterpret_cast<const uint2 *>(c->slu_schw.p);
+      d.slu.sch_lane = c->slu_schl.p;
+      d.slu.sch2_warp = nullptr; d.slu.sch2_lane = nullptr;
+    }
   }
   {
     // back-substitution over the band (slu_solve, phase C): per step k = nh-1 .. 0 and lane the address of U(i,k) for the

@@ -120,42 +120,60 @@ __device__ __forceinline__ double slu_chunk8(const unsigned lp, const unsigned a
   return a0;
 }
 
-// ---- factorisation -----------------------------------------------------------------------------------------------
-// Executed by the first nwl warps of the CTA (the others return at once; the caller's __syncthreads joins them).
-// The right-hand side (S + rhs_off, position order) is carried along as an extra column: it leaves as L^-1 P b.
-// ZoneScalars::slu_fail is set when a heavy column violates the threshold test or a pivot is zero/NaN, slu_fail_k
-// receives the first such column (caller initialises it to a large value), slu_ipb the interchanges of the border
-// block.  On return the diagonal of U holds the RECIPROCALS of the pivots.
-//
-// The pivot loop is latency bound (a zone has four warps; an SM three zones): what counts is the number of
-// instructions and above all of branches on a warp's path through one pivot.  Nothing about WHERE a pivot works
-// depends on the data, so all of it -- which column a lane owns, whether that column reaches the pivot row, where its
-// segment and its u(k,j) live, how many rows the warp's chunk has and how many of them are tested -- comes from the
-// pivot schedule the host derives once per network (structured_lu_schedule, xb_loader.cpp): 4 bytes per lane and 8 per
-// warp and round, zone-invariant, streamed from L2 two rounds ahead of their use.  A round is then: barrier, pivot,
-// reciprocal, u, one chunk (slu_chunk8), the column test of the chunk's own rows (lanes = rows, folded into every warp:
-// no warp is singled out), flat control flow.  A pivot with more chunks than warps or more columns than lanes takes
-// further rounds; they recompute the reciprocal from the untouched pivot (thread 0 stores a reciprocal over its
-// pivot only once the schedule has moved on).
-__device__ __noinline__ void slu_factor(double *__restrict__ S) {
-  XB_ASSUME_SHARED(S);
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+// The rank-2 chunk: eight rows of this lane's column take the updates of the pivots k and k+1 at once,
+//   l2[t] = c2[t] + l1[t] * un1k   (the multipliers of pivot k+1 after pivot k's update; every lane forms them itself)
+//   a[t]  = (a[t] + l1[t] * un1) + l2[t] * un2
+// -- the same operations in the same order as two rank-1 rounds, hence the same bits.  24 loads up front (the gate of
+// slu_chunk8 over all of them, applied to the three multipliers), 24 multiply-adds, predicated stores.
+// lp1 / lp2: the rows' entries in columns k and k+1; ap: the column segment.
+__device__ __forceinline__ void slu_chunk8x2(const unsigned lp1, const unsigned lp2, const unsigned ap, const int nleft, const double un1k,
+                                             const double un1, const double un2, const unsigned zero) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p0, p1, p2, p3, p4, p5, p6, p7;\n\t"
+      ".reg .f64 l0, l1, l2, l3, l4, l5, l6, l7, c0, c1, c2, c3, c4, c5, c6, c7, a0, a1, a2, a3, a4, a5, a6, a7, g0, g1, g2;\n\t"
+      ".reg .b32 x0, x1, x2, x3, x4, x5, x6, x7, y0, y1, y2, y3, y4, y5, y6, y7, z0, z1, z2, z3, z4, z5, z6, z7, hi, acc, lo0, hi0, lo1, hi1, lo2, hi2;\n\t"
+      "ld.shared.f64 l0, [%0];\n\tld.shared.f64 l1, [%0+8];\n\tld.shared.f64 l2, [%0+16];\n\tld.shared.f64 l3, [%0+24];\n\t"
+      "ld.shared.f64 l4, [%0+32];\n\tld.shared.f64 l5, [%0+40];\n\tld.shared.f64 l6, [%0+48];\n\tld.shared.f64 l7, [%0+56];\n\t"
+      "ld.shared.f64 c0, [%1];\n\tld.shared.f64 c1, [%1+8];\n\tld.shared.f64 c2, [%1+16];\n\tld.shared.f64 c3, [%1+24];\n\t"
+      "ld.shared.f64 c4, [%1+32];\n\tld.shared.f64 c5, [%1+40];\n\tld.shared.f64 c6, [%1+48];\n\tld.shared.f64 c7, [%1+56];\n\t"
+      "ld.shared.f64 a0, [%2];\n\tld.shared.f64 a1, [%2+8];\n\tld.shared.f64 a2, [%2+16];\n\tld.shared.f64 a3, [%2+24];\n\t"
+      "ld.shared.f64 a4, [%2+32];\n\tld.shared.f64 a5, [%2+40];\n\tld.shared.f64 a6, [%2+48];\n\tld.shared.f64 a7, [%2+56];\n\t"
+      "setp.gt.s32 p0, %3, 0;\n\tsetp.gt.s32 p1, %3, 1;\n\tsetp.gt.s32 p2, %3, 2;\n\tsetp.gt.s32 p3, %3, 3;\n\t"
+      "setp.gt.s32 p4, %3, 4;\n\tsetp.gt.s32 p5, %3, 5;\n\tsetp.gt.s32 p6, %3, 6;\n\tsetp.gt.s32 p7, %3, 7;\n\t"
+      "mov.b64 {x0, hi}, l0;\n\tmov.b64 {x1, hi}, l1;\n\tmov.b64 {x2, hi}, l2;\n\tmov.b64 {x3, hi}, l3;\n\t"
+      "mov.b64 {x4, hi}, l4;\n\tmov.b64 {x5, hi}, l5;\n\tmov.b64 {x6, hi}, l6;\n\tmov.b64 {x7, hi}, l7;\n\t"
+      "mov.b64 {y0, hi}, c0;\n\tmov.b64 {y1, hi}, c1;\n\tmov.b64 {y2, hi}, c2;\n\tmov.b64 {y3, hi}, c3;\n\t"
+      "mov.b64 {y4, hi}, c4;\n\tmov.b64 {y5, hi}, c5;\n\tmov.b64 {y6, hi}, c6;\n\tmov.b64 {y7, hi}, c7;\n\t"
+      "mov.b64 {z0, hi}, a0;\n\tmov.b64 {z1, hi}, a1;\n\tmov.b64 {z2, hi}, a2;\n\tmov.b64 {z3, hi}, a3;\n\t"
+      "mov.b64 {z4, hi}, a4;\n\tmov.b64 {z5, hi}, a5;\n\tmov.b64 {z6, hi}, a6;\n\tmov.b64 {z7, hi}, a7;\n\t"
+      "lop3.b32 acc, x0, x1, x2, 0xFE;\n\tlop3.b32 acc, acc, x3, x4, 0xFE;\n\tlop3.b32 acc, acc, x5, x6, 0xFE;\n\t"
+      "lop3.b32 acc, acc, x7, y0, 0xFE;\n\tlop3.b32 acc, acc, y1, y2, 0xFE;\n\tlop3.b32 acc, acc, y3, y4, 0xFE;\n\t"
+      "lop3.b32 acc, acc, y5, y6, 0xFE;\n\tlop3.b32 acc, acc, y7, z0, 0xFE;\n\tlop3.b32 acc, acc, z1, z2, 0xFE;\n\t"
+      "lop3.b32 acc, acc, z3, z4, 0xFE;\n\tlop3.b32 acc, acc, z5, z6, 0xFE;\n\tor.b32 acc, acc, z7;\n\t"
+      "mov.b64 {lo0, hi0}, %4;\n\tmov.b64 {lo1, hi1}, %5;\n\tmov.b64 {lo2, hi2}, %6;\n\t"
+      "lop3.b32 lo0, lo0, acc, %7, 0xF8;\n\tlop3.b32 lo1, lo1, acc, %7, 0xF8;\n\tlop3.b32 lo2, lo2, acc, %7, 0xF8;\n\t"
+      "mov.b64 g0, {lo0, hi0};\n\tmov.b64 g1, {lo1, hi1};\n\tmov.b64 g2, {lo2, hi2};\n\t"
+      "fma.rn.f64 c0, l0, g0, c0;\n\tfma.rn.f64 c1, l1, g0, c1;\n\tfma.rn.f64 c2, l2, g0, c2;\n\tfma.rn.f64 c3, l3, g0, c3;\n\t"
+      "fma.rn.f64 c4, l4, g0, c4;\n\tfma.rn.f64 c5, l5, g0, c5;\n\tfma.rn.f64 c6, l6, g0, c6;\n\tfma.rn.f64 c7, l7, g0, c7;\n\t"
+      "fma.rn.f64 a0, l0, g1, a0;\n\tfma.rn.f64 a1, l1, g1, a1;\n\tfma.rn.f64 a2, l2, g1, a2;\n\tfma.rn.f64 a3, l3, g1, a3;\n\t"
+      "fma.rn.f64 a4, l4, g1, a4;\n\tfma.rn.f64 a5, l5, g1, a5;\n\tfma.rn.f64 a6, l6, g1, a6;\n\tfma.rn.f64 a7, l7, g1, a7;\n\t"
+      "fma.rn.f64 a0, c0, g2, a0;\n\tfma.rn.f64 a1, c1, g2, a1;\n\tfma.rn.f64 a2, c2, g2, a2;\n\tfma.rn.f64 a3, c3, g2, a3;\n\t"
+      "fma.rn.f64 a4, c4, g2, a4;\n\tfma.rn.f64 a5, c5, g2, a5;\n\tfma.rn.f64 a6, c6, g2, a6;\n\tfma.rn.f64 a7, c7, g2, a7;\n\t"
+      "@p0 st.shared.f64 [%2], a0;\n\t@p1 st.shared.f64 [%2+8], a1;\n\t@p2 st.shared.f64 [%2+16], a2;\n\t@p3 st.shared.f64 [%2+24], a3;\n\t"
+      "@p4 st.shared.f64 [%2+32], a4;\n\t@p5 st.shared.f64 [%2+40], a5;\n\t@p6 st.shared.f64 [%2+48], a6;\n\t@p7 st.shared.f64 [%2+56], a7;\n\t"
+      "}"
+      :
+      : "r"(lp1), "r"(lp2), "r"(ap), "r"(nleft), "d"(un1k), "d"(un1), "d"(un2), "r"(zero)
+      : "memory");
+}
+
+// ---- the pivot rounds, one pivot per round (tables without pair alignment: XB_SLU_PAIR=0) -----------------------------
+__device__ __forceinline__ void slu_rounds1(double *__restrict__ S, const unsigned sS, const int tid, const int lane, const int w,
+                                            int &kfail, bool &viol) {
   const DevSlu &D = c_net.slu;
   const int nwl = D.nwl;
-  if (w >= nwl) return;
-  const int n = D.n, nb = D.nbord, nh = n - nb, bo = D.bo, bs = D.bs;
-  double *rhs = S + D.rhs_off;
-  int *fail = reinterpret_cast<int *>(S) + D.fail_rel, *ipb = fail + 2;      // ZoneScalars::slu_fail, slu_fail_k, slu_ipb[8]
-  const unsigned sS = (unsigned)__cvta_generic_to_shared(S);
-  // The temperature equation (self-heating: the last row) is exempt from the test: it is the linear functional
-  // -sum_i mex_i (row i) / cv of the abundance rows, i.e. a row in different units whose multipliers measure mex/cv and
-  // not element growth (elimination without interchanges is invariant under row scaling).
-  const double tau = D.tau, itau = D.itau;
-  const int nbt = D.ntest - nh;                      // border rows subject to the test
-  const bool with_rhs = true;
-  bool viol = false;
-  // the border entries of the right-hand side ride in column n of the border block (same address rule as the matrix columns)
-  if (w == 0 && lane < nb) S[bo + n * bs + lane] = rhs[nh + lane];
+  const double itau = D.itau;
   // loop constants pinned in registers (an opaque move: otherwise they are re-read from the constant bank every round)
   int nround = D.nround, nfl = nwl * 32, nwr = nwl;
   asm volatile("mov.b32 %0, %0;\n\tmov.b32 %1, %1;\n\tmov.b32 %2, %2;" : "+r"(nround), "+r"(nfl), "+r"(nwr));
@@ -170,7 +188,6 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S) {
   lt += 3 * nfl; wt += 3 * nwr;
   const int row = lane & 7;
   double rprev = 0.0; unsigned dprev = 0xffffffffu;   // reciprocal of the previous pivot, stored over it once the schedule has left that pivot
-  int kfail = 0x7fffffff;
 #ifdef XB_SLU_PROF
   long long pt[5] = {0, 0, 0, 0, 0}, pc0 = clock64();
 #define SLU_PT(i) { const long long now_ = clock64(); pt[i] += now_ - pc0; pc0 = now_; }
@@ -228,9 +245,128 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S) {
     for (int i = 0; i < 5; ++i) ph[PH_DBG0 + 4 + i] += pt[i];
   }
 #endif
-  if (kfail != 0x7fffffff) { viol = true; atomicMin(fail + 1, kfail); }
   bar_named(1, nfl);
   if (tid == 0 && dprev != 0xffffffffu) S[dprev] = rprev;
+}
+
+// ---- the pivot rounds, two pivots per round (pair-aligned tables, SluSchedule2 in xb_host.h) -----------------------------
+// One barrier, one pass over the rows for the pivots k and k+1: the second pivot a(k+1,k+1) - l(k+1,k) u(k,k+1) and its
+// reciprocal are formed by every thread from four broadcast loads, every lane forms U(k+1,j) for its own column (and
+// from it the second multiplier), every lane forms the multipliers of pivot k+1 for the rows of its chunk.  Row k+1 of U
+// is stored one barrier later by the lanes of the item the schedule flags (other warps of the same round still read the
+// old row); the lane of column k+1 leaves the updated multipliers behind; thread 0 stores both reciprocals once the
+// schedule has left the pair.  Arithmetic identical to two rank-1 rounds, operation by operation.
+__device__ __forceinline__ void slu_rounds2(double *__restrict__ S, const unsigned sS, const int tid, const int lane, const int w, int &kfail) {
+  const DevSlu &D = c_net.slu;
+  const double itau = D.itau;
+  int nround = D.nround, nfl = D.nwl * 32, nwr = D.nwl;
+  asm volatile("mov.b32 %0, %0;\n\tmov.b32 %1, %1;\n\tmov.b32 %2, %2;" : "+r"(nround), "+r"(nfl), "+r"(nwr));
+  const unsigned zero = (unsigned)nfl >> 20;         // 0, but not to ptxas: the load gate of the chunk
+  const uint2 *__restrict__ lt = D.sch2_lane + tid;
+  const uint4 *__restrict__ wt = D.sch2_warp + w;
+  uint2 eA = __ldg(lt), eB = __ldg(lt + nfl), eC = __ldg(lt + 2 * nfl);
+  uint4 gA = __ldg(wt), gB = __ldg(wt + nwr), gC = __ldg(wt + 2 * nwr);
+  lt += 3 * nfl; wt += 3 * nwr;
+  const int row = lane & 7;
+  const unsigned none = 0xffffffffu;
+  double r1prev = 0.0, r2prev = 0.0, pend_val = 0.0;
+  unsigned d1prev = none, d2prev = none, pend_ad = none;
+  auto rcp = [](const double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double er = fma(-x, r, 1.0);                       // seed good to ~20 bits; r (1 + e + e^2) leaves e^3 < 2^-58
+    er = fma(er, er, er);
+    return fma(r, er, r);
+  };
+  auto round = [&](const uint2 e, const uint4 g) {
+    const unsigned lp1 = g.x & 0xffffu, lp2 = g.x >> 16, pv1 = g.z & 0xffffu, u12 = g.z >> 16;
+    const unsigned ap = e.x & 0xffffu, up1 = e.x >> 16, up2 = e.y & 0xffffu;
+    const bool col2 = (e.y >> 16) & 1u;
+    const int nrow = (int)(g.y & 15u), nt1 = (int)((g.y >> 4) & 15u), nt2 = (int)((g.y >> 8) & 15u), kk = (int)g.w;
+    const bool commit = (g.y >> 12) & 1u, single = (g.y >> 13) & 1u;
+    bar_named(1, nfl);
+    const double piv1 = S[pv1], l21 = S[pv1 + 1], u12v = S[u12], piv2 = S[u12 + 1];
+    const double u1 = S[up1], a2 = S[up2];
+    const double tv1 = S[lp1 + row], tc2 = S[lp2 + row];  // this lane's row of the chunk for the two column tests
+    if (pend_ad != none) S[pend_ad] = pend_val;
+    const bool st1 = tid == 0 && d1prev != pv1 && d1prev != none, st2 = st1 && d2prev != none;
+    if (st1) S[d1prev] = r1prev;
+    if (st2) S[d2prev] = r2prev;
+    const double rk1 = rcp(piv1);
+    const double un1k = -(u12v * rk1);
+    const double p2 = fma(l21, un1k, piv2);
+    const double rk2f = rcp(p2);                         // a single's second pivot is switched off: integer selects, no branch
+    const double rk2 = __hiloint2double(single ? 0 : __double2hiint(rk2f), single ? 0 : __double2loint(rk2f));
+    const double un1 = -(u1 * rk1);
+    const double upr = fma(l21, un1, a2);               // U(k+1, j)
+    const double un2 = col2 ? 0.0 : -(upr * rk2);
+    const bool active = ap != lp1;
+    slu_chunk8x2(sS + 8u * lp1, sS + 8u * lp2, sS + 8u * ap, active ? nrow : 0, un1k, un1, un2, zero);
+    // column tests, lanes = rows of this warp's chunk; a pivot outside 1e-280..1e280 (or zero, or NaN) fails
+    const double ap1 = fabs(piv1), thr1 = ap1 * itau, ap2 = fabs(p2), thr2 = ap2 * itau;
+    const double l2t = fma(tv1, un1k, tc2);
+    const bool bad1 = ((row < nt1) & (fabs(tv1) > thr1)) | (!single & (fabs(l21) > thr1)) | !((ap1 > 1e-280) & (ap1 < 1e280));
+    const bool bad2 = ((row < nt2) & (fabs(l2t) > thr2)) | (!single & !((ap2 > 1e-280) & (ap2 < 1e280)));
+    kfail = min(kfail, bad1 ? kk : 0x7fffffff);
+    kfail = min(kfail, bad2 ? kk + 1 : 0x7fffffff);
+    pend_ad = (commit & active & !col2) ? up2 : none;
+    pend_val = upr;
+    r1prev = rk1; r2prev = rk2; d1prev = pv1; d2prev = single ? none : u12 + 1u;
+  };
+#pragma unroll 1
+  for (int r = 0; r < nround; r += 3) {
+    const uint2 fA = eA, fB = eB, fC = eC;
+    const uint4 hA = gA, hB = gB, hC = gC;
+    eA = __ldg(lt); eB = __ldg(lt + nfl); eC = __ldg(lt + 2 * nfl);
+    gA = __ldg(wt); gB = __ldg(wt + nwr); gC = __ldg(wt + 2 * nwr);
+    lt += 3 * nfl; wt += 3 * nwr;
+    round(fA, hA); round(fB, hB); round(fC, hC);
+  }
+  bar_named(1, nfl);
+  if (pend_ad != none) S[pend_ad] = pend_val;
+  if (tid == 0 && d1prev != none) { S[d1prev] = r1prev; if (d2prev != none) S[d2prev] = r2prev; }
+}
+
+// ---- factorisation -----------------------------------------------------------------------------------------------
+// Executed by the first nwl warps of the CTA (the others return at once; the caller's __syncthreads joins them).
+// The right-hand side (S + rhs_off, position order) is carried along as an extra column: it leaves as L^-1 P b.
+// ZoneScalars::slu_fail is set when a heavy column violates the threshold test or a pivot is zero/NaN, slu_fail_k
+// receives the first such column (caller initialises it to a large value), slu_ipb the interchanges of the border
+// block.  On return the diagonal of U holds the RECIPROCALS of the pivots.
+//
+// The pivot loop is latency bound (a zone has four warps; an SM three zones): what counts is the number of
+// instructions and above all of branches on a warp's path through one pivot.  Nothing about WHERE a pivot works
+// depends on the data, so all of it -- which column a lane owns, whether that column reaches the pivot row, where its
+// segment and its u(k,j) live, how many rows the warp's chunk has and how many of them are tested -- comes from the
+// pivot schedule the host derives once per network (structured_lu_schedule, xb_loader.cpp): 4 bytes per lane and 8 per
+// warp and round, zone-invariant, streamed from L2 two rounds ahead of their use.  A round is then: barrier, pivot,
+// reciprocal, u, one chunk (slu_chunk8), the column test of the chunk's own rows (lanes = rows, folded into every warp:
+// no warp is singled out), flat control flow.  A pivot with more chunks than warps or more columns than lanes takes
+// further rounds; they recompute the reciprocal from the untouched pivot (thread 0 stores a reciprocal over its
+// pivot only once the schedule has moved on).
+__device__ __noinline__ void slu_factor(double *__restrict__ S) {
+  XB_ASSUME_SHARED(S);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const DevSlu &D = c_net.slu;
+  const int nwl = D.nwl;
+  if (w >= nwl) return;
+  const int n = D.n, nb = D.nbord, nh = n - nb, bo = D.bo, bs = D.bs;
+  double *rhs = S + D.rhs_off;
+  int *fail = reinterpret_cast<int *>(S) + D.fail_rel, *ipb = fail + 2;      // ZoneScalars::slu_fail, slu_fail_k, slu_ipb[8]
+  const unsigned sS = (unsigned)__cvta_generic_to_shared(S);
+  // The temperature equation (self-heating: the last row) is exempt from the test: it is the linear functional
+  // -sum_i mex_i (row i) / cv of the abundance rows, i.e. a row in different units whose multipliers measure mex/cv and
+  // not element growth (elimination without interchanges is invariant under row scaling).
+  const double tau = D.tau, itau = D.itau;
+  const int nbt = D.ntest - nh;                      // border rows subject to the test
+  const bool with_rhs = true;
+  bool viol = false;
+  // the border entries of the right-hand side ride in column n of the border block (same address rule as the matrix columns)
+  if (w == 0 && lane < nb) S[bo + n * bs + lane] = rhs[nh + lane];
+  int kfail = 0x7fffffff;
+  if (D.pair) slu_rounds2(S, sS, tid, lane, w, kfail);
+  else slu_rounds1(S, sS, tid, lane, w, kfail, viol);
+  if (kfail != 0x7fffffff) { viol = true; atomicMin(fail + 1, kfail); }
   // ---- border block, one warp, lane c holds column c of the block (lane nb: the right-hand side).  The diagonal is
   // the pivot while it passes the threshold test against the tested rows below it; otherwise the largest entry of the
   // column (any row) is brought up.

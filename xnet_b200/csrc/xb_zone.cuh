@@ -597,7 +597,10 @@ __device__ __noinline__ void cross_sect_cta() {
 
 // --- term plans -------------------------------------------------------------------------------------
 // product of one record:  (((a*csect[mu])*y[n0])*y[n1])*y[n2])*y[n3]   (absent factors are y[ny]=1)
-constexpr int kPlanU = 8;   // records in flight per thread (host pads L to a multiple)
+#ifndef XB_PLAN_U
+#define XB_PLAN_U 8
+#endif
+constexpr int kPlanU = XB_PLAN_U;   // records in flight per thread (host pads L to a multiple)
 
 template <bool STRICT>
 __device__ __forceinline__ double plan_mul(const double a, const double c, const uint2 nn, const double *y) {
