@@ -359,7 +359,6 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S) {
   // not element growth (elimination without interchanges is invariant under row scaling).
   const double tau = D.tau, itau = D.itau;
   const int nbt = D.ntest - nh;                      // border rows subject to the test
-  const bool with_rhs = true;
   bool viol = false;
   // the border entries of the right-hand side ride in column n of the border block (same address rule as the matrix columns)
   if (w == 0 && lane < nb) S[bo + n * bs + lane] = rhs[nh + lane];
@@ -367,67 +366,53 @@ __device__ __noinline__ void slu_factor(double *__restrict__ S) {
   if (D.pair) slu_rounds2(S, sS, tid, lane, w, kfail);
   else slu_rounds1(S, sS, tid, lane, w, kfail, viol);
   if (kfail != 0x7fffffff) { viol = true; atomicMin(fail + 1, kfail); }
-  // ---- border block, one warp, lane c holds column c of the block (lane nb: the right-hand side).  The diagonal is
-  // the pivot while it passes the threshold test against the tested rows below it; otherwise the largest entry of the
-  // column (any row) is brought up.
+  // ---- border block, one warp, in place in shared memory; lane c works on column c of the block (lane nb: the right-hand
+  // side).  The diagonal is the pivot while it passes the threshold test against the tested rows below it; otherwise the
+  // largest entry of the column (any row) is brought up.  Rolled loops over rows and pivots: the block is 5-7 wide, and
+  // what counts for a once-per-factorisation piece of code is its instruction footprint (a register-resident, fully
+  // unrolled version was 4400 instructions, 28 KB of them executed per factorisation, against 250 here).
   if (w == 0) {
-    double v[kSluBord], rb[kSluBord];
     const int c = lane;
-    const bool mine = c < nb || (c == nb && with_rhs);
-#pragma unroll
-    for (int r = 0; r < kSluBord; ++r) v[r] = (r < nb && mine) ? S[bo + (nh + c) * bs + r] : 0.0;     // c = nb: column n, the right-hand side
-    int sw[kSluBord];
-#pragma unroll
-    for (int jj = 0; jj < kSluBord; ++jj) {
-      sw[jj] = jj; rb[jj] = 0.0;
-      if (jj < nb) {
-        // lane jj: largest entry of column jj from the diagonal down (first maximum), and the largest among the tested rows
-        double best = -1.0, bestt = -1.0; int p = jj;
-#pragma unroll
-        for (int r = 0; r < kSluBord; ++r) {
-          if (r >= jj && r < nb) {
-            const double av = fabs(v[r]);
-            if (av > best) { best = av; p = r; }
-            if (r < nbt && av > bestt) bestt = av;
-          }
-        }
-        const double ad = fabs(v[jj]);
-        if (ad > 0.0 && !(tau * bestt > ad)) p = jj;
-        p = __shfl_sync(kFull, p, jj);
-        sw[jj] = p;
-        if (p != jj) {
-#pragma unroll
-          for (int r = 0; r < kSluBord; ++r) if (r == p) { const double tmp = v[jj]; v[jj] = v[r]; v[r] = tmp; }
-        }
-        const double pv = __shfl_sync(kFull, v[jj], jj);
-        if (!(fabs(pv) > 0.0)) viol = true;
-        const double rk = pivot_rcp<false>(pv);
-        rb[jj] = rk;
-#pragma unroll
-        for (int r = 0; r < kSluBord; ++r) {
-          if (r > jj && r < nb) {
-            const double lr = __shfl_sync(kFull, v[r], jj) * rk;
-            if (c > jj) v[r] = fma(-lr, v[jj], v[r]);
-          }
-        }
+    const bool mine = c <= nb;
+    const int colc = bo + ((c < nb) ? nh + c : n) * bs;
+#pragma unroll 1
+    for (int jj = 0; jj < nb; ++jj) {
+      const int colj = bo + (nh + jj) * bs;
+      // every lane scans column jj itself (broadcast loads, the same decision in all lanes): largest entry from the
+      // diagonal down (first maximum) and the largest among the tested rows
+      double best = -1.0, bestt = -1.0; int p = jj;
+#pragma unroll 1
+      for (int r = jj; r < nb; ++r) {
+        const double av = fabs(S[colj + r]);
+        if (av > best) { best = av; p = r; }
+        if (r < nbt && av > bestt) bestt = av;
       }
-    }
-#pragma unroll
-    for (int r = 0; r < kSluBord; ++r) {
-      if (r < nb) {
-        if (c < nb) S[bo + (nh + c) * bs + r] = (r == c) ? rb[r] : v[r];       // reciprocal over the pivot
-        else if (c == nb && with_rhs) rhs[nh + r] = v[r];
+      const double ad = fabs(S[colj + jj]);
+      if (ad > 0.0 && !(tau * bestt > ad)) p = jj;
+      __syncwarp();
+      if (lane == 0) ipb[jj] = p;
+      if (p != jj && mine) { const double t = S[colc + jj]; S[colc + jj] = S[colc + p]; S[colc + p] = t; }
+      __syncwarp();
+      const double pv = S[colj + jj];
+      if (!(fabs(pv) > 0.0)) viol = true;
+      const double rk = pivot_rcp<false>(pv);
+      if (mine && c > jj) {
+        const double ujc = S[colc + jj];
+#pragma unroll 1
+        for (int r = jj + 1; r < nb; ++r) { const double lr = S[colj + r] * rk; S[colc + r] = fma(-lr, ujc, S[colc + r]); }
       }
+      __syncwarp();
+      if (lane == jj) S[colj + jj] = rk;                 // reciprocal over the pivot
     }
+    __syncwarp();
+    if (lane < nb) rhs[nh + lane] = S[bo + n * bs + lane];
     // the same interchanges on the heavy-column part of the border rows (their multipliers), in order
-#pragma unroll
-    for (int jj = 0; jj < kSluBord; ++jj) {
-      if (jj < nb) {
-        if (lane == 0) ipb[jj] = sw[jj];
-        if (sw[jj] != jj) {
-          const int la = bo + jj, lb = bo + sw[jj];
-          for (int cc = lane; cc < nh; cc += 32) { const double ta = S[la + cc * bs], tb = S[lb + cc * bs]; S[la + cc * bs] = tb; S[lb + cc * bs] = ta; }
-        }
+#pragma unroll 1
+    for (int jj = 0; jj < nb; ++jj) {
+      const int pj = ipb[jj];
+      if (pj != jj) {
+        const int la = bo + jj, lb = bo + pj;
+        for (int cc = lane; cc < nh; cc += 32) { const double ta = S[la + cc * bs], tb = S[lb + cc * bs]; S[la + cc * bs] = tb; S[lb + cc * bs] = ta; }
       }
     }
   }

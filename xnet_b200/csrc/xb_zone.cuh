@@ -598,9 +598,11 @@ __device__ __noinline__ void cross_sect_cta() {
 // --- term plans -------------------------------------------------------------------------------------
 // product of one record:  (((a*csect[mu])*y[n0])*y[n1])*y[n2])*y[n3]   (absent factors are y[ny]=1)
 #ifndef XB_PLAN_U
-#define XB_PLAN_U 8
+#define XB_PLAN_U 2
 #endif
-constexpr int kPlanU = XB_PLAN_U;   // records in flight per thread (host pads L to a multiple)
+constexpr int kPlanU = XB_PLAN_U;   // records in flight per thread (host pads L to a multiple).  2 is the measured optimum of the
+                                    // structured kernel (8: 2.63e6, 4: 2.68e6, 2: 2.71e6 zone-it/s on SN160): the smaller loop body wins
+                                    // more through the instruction cache than the deeper batches win in memory-level parallelism
 
 template <bool STRICT>
 __device__ __forceinline__ double plan_mul(const double a, const double c, const uint2 nn, const double *y) {
