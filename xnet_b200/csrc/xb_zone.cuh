@@ -567,15 +567,16 @@ __device__ __noinline__ void cross_sect_cta() {
           dlnrpf = A::sub(dlnrpf, sr);
         }
       }
+      const double eh = Mx::safe_exp(h);                // one copy of exp in the loop body (the branches below share it)
       if (c == 0) {
-        if (iwk == 1) cs = A::mul(A::mul(ene, rpf), Mx::safe_exp(h));
+        if (iwk == 1) cs = A::mul(A::mul(ene, rpf), eh);
         else if (iwk == 2 || iwk == 3) cs = zm.rffn[net.iffn[k] - 1];
         else if (iwk == 7 || iwk == 8) cs = A::mul(rpf, 0.0);
-        else cs = A::mul(rpf, Mx::safe_exp(h));
+        else cs = A::mul(rpf, eh);
       } else {
         const double rf = (c == 1) ? rhot : (c == 2) ? rho2 : rho3;
-        if (iwk == 1) cs = A::mul(A::mul(A::mul(rf, ene), rpf), Mx::safe_exp(h));
-        else cs = A::mul(A::mul(rf, rpf), Mx::safe_exp(h));
+        if (iwk == 1) cs = A::mul(A::mul(A::mul(rf, ene), rpf), eh);
+        else cs = A::mul(A::mul(rf, rpf), eh);
         if (c == 2 && cs < 1.0e-20) cs = 0.0;
       }
       if (heat) {   // xnet_integrate.F90:807-815 and the corresponding blocks of the other classes
