@@ -175,6 +175,8 @@ __device__ void t9rhofind(const ZoneScalars *s, double tf, int *nf, double *t9f,
 }
 
 // --- block-wide helpers ----------------------------------------------------------------------------
+// (The thread-strided loops of this file carry `#pragma unroll 1`: they make one or two trips, and the four-fold unrolled
+// bodies the compiler would emit are instruction-cache footprint for nothing -- DESIGN 4c.)
 // Two sums over k < n of terms produced by f(k, ta, tb).  STRICT: terms are formed in parallel and
 // added by one thread in ascending k from 0.0 (the reference's sequential accumulation, bit for bit);
 // FAST: shuffle tree.  Results land in out2[0..1] (shared) and are visible to every thread on return.
@@ -182,6 +184,7 @@ template <bool STRICT, class F>
 __device__ __forceinline__ void block_sum2(const int n, F f, double *buf, double *out2) {
   const int tid = threadIdx.x, nt = blockDim.x;
   if (STRICT) {
+#pragma unroll 1
     for (int k = tid; k < n; k += nt) { double ta, tb; f(k, ta, tb); buf[k] = ta; buf[n + k] = tb; }
     __syncthreads();
     if (tid < 2) {
@@ -193,6 +196,7 @@ __device__ __forceinline__ void block_sum2(const int n, F f, double *buf, double
     __syncthreads();
   } else {
     double sa = 0.0, sb = 0.0;
+#pragma unroll 1
     for (int k = tid; k < n; k += nt) { double ta, tb; f(k, ta, tb); sa += ta; sb += tb; }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -220,6 +224,7 @@ template <class F>
 __device__ __forceinline__ void block_argmax_first(const int n, F f, double *buf, double *out, int *iout) {
   const int tid = threadIdx.x, nt = blockDim.x;
   double bv = -1.0; int bi = 0x7fffffff;
+#pragma unroll 1
   for (int k = tid; k < n; k += nt) { const double v = f(k); if (v > bv) { bv = v; bi = k; } }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
@@ -327,12 +332,15 @@ __device__ __noinline__ void cross_sect_cta() {
     for (; ii <= kNG; ++ii) if (t9t <= net.t9i[ii - 1]) break;
     if (tid == 0) zm.gg[0] = 1.0;
     if (ii == 1) {
+#pragma unroll 1
       for (int k = tid; k < ny; k += nt) zm.gg[k + 1] = net.g[k * kNG];
     } else if (ii == kNG + 1) {
+#pragma unroll 1
       for (int k = tid; k < ny; k += nt) zm.gg[k + 1] = net.g[k * kNG + kNG - 1];
     } else {
       double rdt9 = A::div(A::sub(t9t, net.t9i[ii - 2]), A::sub(net.t9i[ii - 1], net.t9i[ii - 2]));
       double omr = A::sub(1.0, rdt9);
+#pragma unroll 1
       for (int k = tid; k < ny; k += nt) {
         double v = A::add(A::mul(rdt9, net.lng[k * kNG + ii - 1]), A::mul(omr, net.lng[k * kNG + ii - 2]));
         zm.gg[k + 1] = Mx::safe_exp(v);
@@ -344,6 +352,7 @@ __device__ __noinline__ void cross_sect_cta() {
       const double dt = A::sub(net.t9i[idx], net.t9i[idx - 1]);
       double *dl = zm.gg + (ny + 1);
       if (tid == 0) dl[0] = 0.0;
+#pragma unroll 1
       for (int k = tid; k < ny; k += nt) dl[k + 1] = A::div(net.dlng[k * kNG + idx], dt);
     }
   }
@@ -368,6 +377,7 @@ __device__ __noinline__ void cross_sect_cta() {
     const double cds1 = -0.899172, cds2 = 0.602249, cds3 = -0.274823, cds4 = -1.401915, cds5 = 0.3230064;
     double *fhs = zm.fhs, *dfhs = zm.fhs + net.nzs;
     const double gammae = s->gammae;
+#pragma unroll 1
     for (int j = tid; j < net.nzs; j += nt) {
       if (j == 0) { fhs[0] = 0.0; dfhs[0] = 0.0; continue; }
       const R gammaz = R(gammae) * net.zseq53[j];
@@ -392,6 +402,7 @@ __device__ __noinline__ void cross_sect_cta() {
     const double dene = A::sub((double)(le1 + 1), (double)le1);
     const double rdene = A::div(A::sub(enel, (double)le1), dene);
     const int i1 = 13 * (le1 - 1) + lt1 - 1, i2 = i1 + 1, i3 = 13 * le1 + lt1 - 1, i4 = i3 + 1;  // 0-based
+#pragma unroll 1
     for (int k = tid; k < net.nffn; k += wnt) {
       const double *enu = net.ffnenu + (size_t)k * kNGrid, *sum = net.ffnsum + (size_t)k * kNGrid;
       double qdr1 = A::sub(enu[i2], enu[i1]), qdr2 = A::sub(enu[i4], enu[i3]);
@@ -697,6 +708,7 @@ __device__ __noinline__ void yderiv_cta() {
     plan_products_strict(P, zm.csect, zm.yt, zm.prod);
     __syncthreads();
     const double *prod = zm.prod;
+#pragma unroll 1
     for (int i = tid; i < ny; i += nt) {
       double s[4];
 #pragma unroll
@@ -712,6 +724,7 @@ __device__ __noinline__ void yderiv_cta() {
       if ((ctl & 3u) == 1u) ydot[ctl >> 3] = acc; else part[ctl >> 3] = acc;
     });
     __syncthreads();
+#pragma unroll 1
     for (int m = tid; m < P.nmulti; m += nt) {
       double sm = 0.0;
       for (int q = P.multi_start[m]; q < P.multi_start[m + 1]; ++q) sm += part[q];
@@ -749,6 +762,7 @@ __device__ __forceinline__ void jacobian_build_impl(const DevNet &net, const Zon
   // plan destinations are (column << 10 | row); row i of the matrix lives in slot pos[i]
   auto slot = [&](const unsigned d) { return (int)(d >> 10) * ld + pos[d & 1023u]; };
   if (STRICT) {   // strict arithmetic reproduces DGETRF's interchanges: no pivot prediction
+#pragma unroll 1
     for (int k = tid; k < N; k += nt) { pos[k] = k; zm.orig[k] = k; }
   }
   XB_DBG_MARK(zm);
@@ -762,6 +776,7 @@ __device__ __forceinline__ void jacobian_build_impl(const DevNet &net, const Zon
     plan_products_strict(P, zm.csect, zm.yt, zm.prod);
     __syncthreads();
     const double *prod = zm.prod;
+#pragma unroll 1
     for (int e = tid; e < P.nseg; e += nt) {
       double sc = 0.0;
       for (int q = P.seg_start[e]; q < P.seg_start[e + 1]; ++q) sc = __dadd_rn(sc, __ldcg(prod + q));
@@ -780,6 +795,7 @@ __device__ __forceinline__ void jacobian_build_impl(const DevNet &net, const Zon
     XB_DBG(zm, 1);
     __syncthreads();
     XB_DBG(zm, 2);
+#pragma unroll 1
     for (int m = tid; m < P.nmulti; m += nt) {
       double sm = 0.0;
       for (int q = P.multi_start[m]; q < P.multi_start[m + 1]; ++q) sm += part[q];
@@ -799,6 +815,7 @@ __device__ __forceinline__ void jacobian_build_impl(const DevNet &net, const Zon
       plan_products_strict(Py, zm.dcsect, zm.yt, zm.prod);
       __syncthreads();
       const double *prod = zm.prod;
+#pragma unroll 1
       for (int i = tid; i < ny; i += nt) {
         double s4[4];
 #pragma unroll
@@ -814,6 +831,7 @@ __device__ __forceinline__ void jacobian_build_impl(const DevNet &net, const Zon
         if ((ctl & 3u) == 1u) colT[pos[ctl >> 3]] = acc; else part[ctl >> 3] = acc;
       });
       __syncthreads();
+#pragma unroll 1
       for (int m = tid; m < Py.nmulti; m += nt) {
         double sm = 0.0;
         for (int q = Py.multi_start[m]; q < Py.multi_start[m + 1]; ++q) sm += part[q];
@@ -827,11 +845,14 @@ __device__ __forceinline__ void jacobian_build_impl(const DevNet &net, const Zon
       const int rT = pos[ny];
       double *mexs = part;   // mass excesses staged in shared memory, in slot order: mexs[pos[i]] = mex[i]
       if (!STRICT) {
+#pragma unroll 1
         for (int i = tid; i < N; i += nt) mexs[i] = 0.0;
         __syncthreads();
+#pragma unroll 1
         for (int i = tid; i < ny; i += nt) mexs[pos[i]] = net.mex[i];
         __syncthreads();
       }
+#pragma unroll 1
       for (int j = tid; j < N; j += nt) {
         const double *col = J + (size_t)j * ld;
         double sdot = 0.0;
@@ -891,6 +912,7 @@ __device__ __noinline__ void jacobian_build_cta() {
     else part[ctl_ >> 3] = acc;
   });
   __syncthreads();
+#pragma unroll 1
   for (int m = tid; m < P.nmulti; m += nt) {
     double sm = 0.0;
     for (int q = P.multi_start[m]; q < P.multi_start[m + 1]; ++q) sm += part[q];
@@ -910,6 +932,7 @@ __device__ __noinline__ void jacobian_build_cta() {
       if ((ctl_ & 3u) == 1u) S[t9col(ctl_ >> 3)] = acc; else part[ctl_ >> 3] = acc;
     });
     __syncthreads();
+#pragma unroll 1
     for (int m = tid; m < Py.nmulti; m += nt) {
       double sm = 0.0;
       for (int q = Py.multi_start[m]; q < Py.multi_start[m + 1]; ++q) sm += part[q];
@@ -918,12 +941,15 @@ __device__ __noinline__ void jacobian_build_cta() {
     __syncthreads();
     // row n-1: d t9dot / d(y_j, T9) = - sum_i mex_i dydotdy(i, j) / cv over the stored rows of column j
     double *mexp = part;                    // mass excesses in position order, 0 for the T9 row
+#pragma unroll 1
     for (int i = tid; i < n; i += nt) mexp[i] = 0.0;
     __syncthreads();
+#pragma unroll 1
     for (int i = tid; i < ny; i += nt) mexp[spos[i]] = net.mex[i];
     __syncthreads();
     const double cv = zm.s->cv;
     const int nbq = I.nb;
+#pragma unroll 1
     for (int pj = tid; pj < n; pj += nt) {
       double s0 = 0.0;
       const int cbj = slu_cb(I, pj);
@@ -935,8 +961,10 @@ __device__ __noinline__ void jacobian_build_cta() {
     __syncthreads();
     // jacobian_scale: jac = mult * dydotdy^T + diag on the diagonal
     const double rdt = zm.s->rdt, m = zm.s->mult;
+#pragma unroll 1
     for (int e = tid; e < D.nstore; e += nt) S[e] *= m;
     __syncthreads();
+#pragma unroll 1
     for (int p = tid; p < n; p += nt) S[slu_addr(I, p, p)] += rdt;
     __syncthreads();
   }
@@ -1012,9 +1040,11 @@ __device__ __noinline__ void step_be_cta() {
     const int *__restrict__ spos = net.slu.pos;
     auto fill_rhs = [&]() {
       if (kit > 1) {
+#pragma unroll 1
         for (int k = tid; k < ny; k += nt) zm.rhs[spos[k]] = A::mad(A::sub(zm.y[k], zm.yt[k]), rdt, zm.ydot[k]);
         if (ctl.iheat > 0 && tid == 0) zm.rhs[N - 1] = A::mad(A::sub(s->t9, s->t9t), rdt, s->t9dot);
       } else {
+#pragma unroll 1
         for (int k = tid; k < ny; k += nt) zm.rhs[spos[k]] = zm.ydot[k];
         if (ctl.iheat > 0 && tid == 0) zm.rhs[N - 1] = s->t9dot;
       }
@@ -1050,9 +1080,11 @@ __device__ __noinline__ void step_be_cta() {
     XB_PHASE_END(zm, PH_BKSUB);
 #else
     if (kit > 1) {
+#pragma unroll 1
       for (int k = tid; k < ny; k += nt) zm.rhs[zm.pos[k]] = A::mad(A::sub(zm.y[k], zm.yt[k]), rdt, zm.ydot[k]);
       if (ctl.iheat > 0 && tid == 0) zm.rhs[zm.pos[ny]] = A::mad(A::sub(s->t9, s->t9t), rdt, s->t9dot);
     } else {
+#pragma unroll 1
       for (int k = tid; k < ny; k += nt) zm.rhs[zm.pos[k]] = zm.ydot[k];
       if (ctl.iheat > 0 && tid == 0) zm.rhs[zm.pos[ny]] = s->t9dot;
     }
@@ -1212,6 +1244,7 @@ __device__ __noinline__ void solve_be_cta() {
     __syncthreads();
     if (inr == 0) {
       mykts = kts + 1;
+#pragma unroll 1
       for (int k = tid; k < ny; k += nt) zm.yt[k] = zm.y[k];
       if (tid == 0) {
         s->tdel = A::div(s->tdel, ctl.tdel_maxmult);
@@ -1233,6 +1266,7 @@ __device__ __noinline__ void solve_be_cta() {
   __syncthreads();
   const int inr = s->inr;
   if (inr > 0) {
+#pragma unroll 1
     for (int k = tid; k < ny; k += nt) { zm.yo[k] = zm.y[k]; zm.y[k] = zm.yt[k]; }
   }
   if (tid == 0) {
@@ -1369,11 +1403,13 @@ __device__ __forceinline__ void full_net_cta(const DevZones &zn, const DevOut &o
   }
   if (restart) {
     kstep0 = zn.rs_kstep0[iz];
+#pragma unroll 1
     for (int k = tid; k < ny; k += nt) {
       zm.y[k] = zn.rs_y[(size_t)iz * ny + k]; zm.yo[k] = zn.rs_yo[(size_t)iz * ny + k]; zm.yt[k] = zm.y[k];
       zm.ydot[k] = 0.0;
     }
   } else {
+#pragma unroll 1
     for (int k = tid; k < ny; k += nt) {
       const double v = zn.ystart[(size_t)fx * ny + k];
       zm.y[k] = v; zm.yo[k] = v; zm.yt[k] = v; zm.ydot[k] = 0.0;
@@ -1381,6 +1417,7 @@ __device__ __forceinline__ void full_net_cta(const DevZones &zn, const DevOut &o
   }
   for (int k = tid; k <= net.nffn; k += nt) zm.qkffn[k] = 0.0;
 #ifndef XB_SLU
+#pragma unroll 1
   for (int k = tid; k < net.msize; k += nt) { zm.orig[k] = k; zm.pos[k] = k; }   // no pivot history yet
 #else
   if (tid == 0) { s->lu_dense = 0; s->nlu_zone = 0; s->slu_fail = 0; }
@@ -1428,6 +1465,7 @@ __device__ __forceinline__ void full_net_cta(const DevZones &zn, const DevOut &o
     if (!lzsolve) break;
   }
   __syncthreads();
+#pragma unroll 1
   for (int k = tid; k < ny; k += nt) out.y[(size_t)iz * ny + k] = zm.y[k];
   if (tid == 0) {
     out.t[iz] = s->t; out.t9[iz] = s->t9; out.rho[iz] = s->rho; out.tdel[iz] = s->tdel;
