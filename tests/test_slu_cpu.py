@@ -135,10 +135,15 @@ class Slu:
         return b
 
 
+_HIST = {}
+
+
 def _systems(op, name, heat, nsamp=5):
     """(a[row, col], rhs) in equation order at nsamp accepted steps of the oracle's trajectory"""
     from oracle import xnet_oracle as O
-    h = op.run(nzone=1, hist_cap=6000)
+    if name not in _HIST:                              # the oracle's trajectory (XRB304: 35 s) is shared by the tests of this file
+        _HIST[name] = op.run(nzone=1, hist_cap=6000)
+    h = _HIST[name]
     n = int(h['hist_n'][0])
     out = []
     for k in np.linspace(2, n - 2, nsamp).astype(int):
